@@ -1,0 +1,93 @@
+/*
+ * accessmath_b200.h -- C ABI of libaccessmath_b200.so, the B200 (sm_100a) drop-in for the native part of
+ * LectureMath's per-frame content-extraction hot path.
+ *
+ * Plain C: pointers and sizes only, no torch types.  "d_" arguments are DEVICE pointers, "h_" are HOST
+ * pointers, `stream` is a cudaStream_t passed as void* (NULL = default stream).  Every function returns
+ * 0 on success, non-zero on failure (1 = CUDA error, 2 = bad argument, 3 = capacity exceeded) and logs to
+ * stderr; the reference's callers ignore return values.
+ *
+ * R/ = reference ACCESS2021_release/.
+ */
+#ifndef ACCESSMATH_B200_H
+#define ACCESSMATH_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ===== 1. Legacy entry point (host pointers, same signature as the reference) ================
+ * Replaces CC_AgeBoundaries, R/accessmath_lib.c:357-359 (argtypes R/AccessMath/preprocessing/content/
+ * labeler.py:159-165).  Stages H2D/D2H internally.  Precondition kept from the reference's callers:
+ * ages >= 0 (frame times); labels outside 1..count_labels are ignored instead of written out of bounds. */
+int CC_AgeBoundaries(int* labels, float* ages, int width, int height, int count_labels,
+                     int* out_mins_y, int* out_maxs_y, int* out_mins_x, int* out_maxs_x,
+                     int* out_counts, float* output_age);
+
+/* ===== 2. Library / device ================================================================== */
+int am_version(void);
+int am_device_count(void);                 /* 0 when no CUDA device: callers must fail loudly */
+int am_words_per_row(int width);           /* uint32 words per bit-packed mask row (padded to 4) */
+
+/* ===== 3. Bit-packed masks ==================================================================
+ * bits[f][y][w] bit b <-> pixel x = 32*w + b, ink = 1.  Replaces the uint8 0/255 frames exchanged between
+ * stage 01 and 02 (R/AccessMath/preprocessing/video_worker/FCN_lecturenet_binarizer.py:54-64,
+ * R/AccessMath/preprocessing/content/helper.py:27-34). */
+int am_pack_mask_u8(const uint8_t* d_mask, int width, int height, int batch, uint32_t* d_bits, void* stream);
+int am_unpack_mask_u8(const uint32_t* d_bits, int width, int height, int batch, uint8_t* d_mask, void* stream);
+
+/* ===== 4. CC labeling + statistics + crops ==================================================
+ * Replaces scipy.ndimage.label (labeler.py:126), CC_AgeBoundaries (accessmath_lib.c:357-413) and the
+ * crop loop of Labeler.extractSpatioTemporalContent (labeler.py:171-189) for a batch of frames. */
+typedef struct am_cc_ctx am_cc_ctx;
+am_cc_ctx* am_cc_create(int width, int height, int max_batch, int max_runs, int max_labels, int max_kept,
+                        int crop_words, int min_pixels);
+void am_cc_destroy(am_cc_ctx* ctx);
+/* labels (optional, may be NULL): int32 [batch][H][W], 0 = background, 1..n in raster order of first pixel */
+int am_cc_label_batch(am_cc_ctx* ctx, const uint32_t* d_bits, int batch, int32_t* d_labels, void* stream);
+/* h_counts[batch][4] = n_runs, n_labels, n_kept (count >= min_pixels), crop_words.  Synchronises `stream`. */
+int am_cc_counts(am_cc_ctx* ctx, int batch, int* h_counts, void* stream);
+/* per-label table of one frame (index = label-1), the six CC_AgeBoundaries outputs (age = 0 / -1) */
+int am_cc_read_label_table(am_cc_ctx* ctx, int frame, int n_labels, int* h_min_y, int* h_max_y, int* h_min_x,
+                           int* h_max_x, int* h_count, void* stream);
+/* kept CCs of one frame, ascending label: h_rows[n_kept][8] =
+ *   unique_idx (after am_est_add_frames, else -1), raw_label, min_x, max_x, min_y, max_y, size, crop_offset */
+int am_cc_read_kept(am_cc_ctx* ctx, int frame, int n_kept, int* h_rows, void* stream);
+/* bit-packed crops of one frame (see crop layout in DESIGN.md), crop_words uint32 */
+int am_cc_read_crops(am_cc_ctx* ctx, int frame, int crop_words, uint32_t* h_crops, void* stream);
+/* all kept rows of a batch, compacted: d_rows[sum n_kept][8] (device), d_row_offsets[batch+1] */
+int am_cc_pack_rows(am_cc_ctx* ctx, int batch, int* d_rows, int row_capacity, int* d_row_offsets, void* stream);
+
+/* ===== 5. Temporal matching ==================================================================
+ * Replaces CCStabilityEstimator.__init__/add_frame (R/AccessMath/preprocessing/content/
+ * cc_stability_estimator.py:11-31, 41-155), IntervalIndex.find_matches (R/AccessMath/preprocessing/tools/
+ * interval_index.py:42-99) and ConnectedComponent.getOverlapFMeasure (R/AM_CommonTools/data/
+ * connected_component.py:202-250). */
+typedef struct am_estimator am_estimator;
+am_estimator* am_est_create(int width, int height, double min_recall, double min_precision, int max_gap,
+                            int max_uniques, int max_active, long long arena_words);
+void am_est_destroy(am_estimator* est);
+/* match frames [first, first+n) of ctx, in order, against the active unique CCs; results land in ctx
+ * (am_cc_read_kept / am_cc_pack_rows column 0) */
+int am_est_add_frames(am_estimator* est, am_cc_ctx* ctx, int first, int n, void* stream);
+/* h_state[6] = n_unique, n_active, img_idx, status, tempo_count(lo), tempo_count(hi).  Synchronises. */
+int am_est_state(am_estimator* est, int* h_state, void* stream);
+/* unique CCs [first, first+n): h_rows[n][8] = first_frame, first_label, min_x, max_x, min_y, max_y, size, last_seen */
+int am_est_read_uniques(am_estimator* est, int first, int n, int* h_rows, void* stream);
+/* first-seen crop of one unique CC (bit-packed, word aligned) */
+int am_est_read_unique_crop(am_estimator* est, int unique_idx, int words, uint32_t* h_crop, void* stream);
+/* multi-GPU hand-off of the ACTIVE set between frame shards:
+ *   export: h_sizes[2] = n_active, crop_words (synchronises); then fill d_meta[n_active][10] =
+ *           unique_idx, min_x, max_x, min_y, max_y, size, last_seen, first_frame, first_label, crop_words
+ *           and d_crops[crop_words].
+ *   import: install that set (global unique indices kept) into a fresh estimator. */
+int am_est_export_sizes(am_estimator* est, long long* h_sizes, void* stream);
+int am_est_export(am_estimator* est, int* d_meta, uint32_t* d_crops, void* stream);
+int am_est_import(am_estimator* est, int n_active, int n_unique, int img_idx, unsigned long long tempo_count,
+                  const int* d_meta, const uint32_t* d_crops, long long crop_words, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,72 @@
+"""ctypes binding of libaccessmath_b200.so (include/accessmath_b200.h).
+
+There is NO CPU fallback: if the library is missing or no CUDA device is visible the product raises."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libaccessmath_b200.so")
+
+c_int, c_void_p, c_double, c_ll, c_ull = ctypes.c_int, ctypes.c_void_p, ctypes.c_double, ctypes.c_longlong, ctypes.c_ulonglong
+
+# name -> (restype, argtypes): one entry per symbol declared in include/accessmath_b200.h
+SIGNATURES = {
+    "CC_AgeBoundaries": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int] + [c_void_p] * 6),
+    "am_version": (c_int, []),
+    "am_device_count": (c_int, []),
+    "am_words_per_row": (c_int, [c_int]),
+    "am_pack_mask_u8": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "am_unpack_mask_u8": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "am_cc_create": (c_void_p, [c_int] * 8),
+    "am_cc_destroy": (None, [c_void_p]),
+    "am_cc_label_batch": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "am_cc_counts": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
+    "am_cc_read_label_table": (c_int, [c_void_p, c_int, c_int] + [c_void_p] * 6),
+    "am_cc_read_kept": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "am_cc_read_crops": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "am_cc_pack_rows": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p]),
+    "am_est_create": (c_void_p, [c_int, c_int, c_double, c_double, c_int, c_int, c_int, c_ll]),
+    "am_est_destroy": (None, [c_void_p]),
+    "am_est_add_frames": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "am_est_state": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "am_est_read_uniques": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "am_est_read_unique_crop": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "am_est_export_sizes": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "am_est_export": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "am_est_import": (c_int, [c_void_p, c_int, c_int, c_int, c_ull, c_void_p, c_void_p, c_ll, c_void_p]),
+}
+
+_lib = None
+
+
+class AccessMathB200Error(RuntimeError):
+    pass
+
+
+def load():
+    """dlopen the library and bind every declared symbol (no device needed)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise AccessMathB200Error(
+                "libaccessmath_b200.so is not built (%s); run `python -m lecturemath_b200.build`. "
+                "There is no CPU fallback." % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def lib():
+    """The bound library, after checking that a CUDA device is present."""
+    l = load()
+    if l.am_device_count() <= 0:
+        raise AccessMathB200Error("no CUDA device visible: lecturemath_b200 has no CPU fallback")
+    return l
+
+
+def check(rc, what):
+    if rc != 0:
+        raise AccessMathB200Error("%s failed with code %d (1=CUDA error, 2=bad argument, 3=capacity exceeded)" % (what, rc))

@@ -1,0 +1,172 @@
+"""Device-side CC engine: thin Python over the C ABI (ctx + estimator handles, torch tensors for memory).
+
+One CCEngine owns the scratch for a batch of frames of a fixed size; `label()` runs labeling + stats + crops,
+`match()` runs temporal matching for the frames of the batch, the `read_*` calls bring tables to the host."""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+MIN_CC_PIXELS = 20        # R/AccessMath/preprocessing/content/labeler.py:22
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _np(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+class CCEngine:
+    def __init__(self, width, height, max_batch=1, min_pixels=MIN_CC_PIXELS, max_runs=0, max_labels=0, max_kept=0,
+                 crop_words=0, device=None):
+        self.lib = _lib.lib()
+        self.width, self.height, self.max_batch = int(width), int(height), int(max_batch)
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.wpr = self.lib.am_words_per_row(self.width)
+        with torch.cuda.device(self.device):
+            self.ctx = self.lib.am_cc_create(self.width, self.height, self.max_batch, max_runs, max_labels, max_kept,
+                                             crop_words, min_pixels)
+        if not self.ctx:
+            raise _lib.AccessMathB200Error("am_cc_create failed")
+        self.counts = None
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.am_cc_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- masks ---------------------------------------------------------------------------------
+    def pack(self, masks_u8):
+        """uint8 (B,H,W) device tensor (ink != 0) -> uint32-as-int32 (B,H,WPR) bit-packed tensor."""
+        assert masks_u8.is_cuda and masks_u8.dtype == torch.uint8 and masks_u8.is_contiguous()
+        b = masks_u8.shape[0]
+        bits = torch.empty((b, self.height, self.wpr), dtype=torch.int32, device=masks_u8.device)
+        _lib.check(self.lib.am_pack_mask_u8(_p(masks_u8), self.width, self.height, b, _p(bits), _stream()), "am_pack_mask_u8")
+        return bits
+
+    def unpack(self, bits):
+        b = bits.shape[0]
+        out = torch.empty((b, self.height, self.width), dtype=torch.uint8, device=bits.device)
+        _lib.check(self.lib.am_unpack_mask_u8(_p(bits), self.width, self.height, b, _p(out), _stream()), "am_unpack_mask_u8")
+        return out
+
+    # ---- labeling + stats + crops ------------------------------------------------------------------
+    def label(self, bits, want_labels=False, sync=True):
+        b = bits.shape[0]
+        assert b <= self.max_batch and bits.is_contiguous() and bits.shape[1:] == (self.height, self.wpr)
+        labels = torch.empty((b, self.height, self.width), dtype=torch.int32, device=bits.device) if want_labels else None
+        _lib.check(self.lib.am_cc_label_batch(self.ctx, _p(bits), b, _p(labels) if want_labels else None, _stream()),
+                   "am_cc_label_batch")
+        self.batch = b
+        if sync:
+            self.read_counts()
+        return labels
+
+    def read_counts(self):
+        c = np.zeros((self.batch, 4), dtype=np.int32)
+        _lib.check(self.lib.am_cc_counts(self.ctx, self.batch, _np(c), _stream()), "am_cc_counts")
+        self.counts = c                  # n_runs, n_labels, n_kept, crop_words
+        return c
+
+    def label_table(self, f):
+        n = int(self.counts[f, 1])
+        t = [np.zeros(n, dtype=np.int32) for _ in range(5)]
+        _lib.check(self.lib.am_cc_read_label_table(self.ctx, f, n, *[_np(a) for a in t], _stream()), "am_cc_read_label_table")
+        return t                         # min_y, max_y, min_x, max_x, count
+
+    def kept_rows(self, f):
+        n = int(self.counts[f, 2])
+        rows = np.zeros((n, 8), dtype=np.int32)
+        _lib.check(self.lib.am_cc_read_kept(self.ctx, f, n, _np(rows), _stream()), "am_cc_read_kept")
+        return rows                      # unique, label, min_x, max_x, min_y, max_y, size, crop_off
+
+    def crops(self, f):
+        n = int(self.counts[f, 3])
+        w = np.zeros(n, dtype=np.uint32)
+        _lib.check(self.lib.am_cc_read_crops(self.ctx, f, n, _np(w), _stream()), "am_cc_read_crops")
+        return w
+
+    def packed_rows(self, batch=None):
+        """All kept rows of the batch in one device tensor + offsets (one D2H for the whole batch)."""
+        b = batch or self.batch
+        total_cap = int(self.counts[:b, 2].sum()) if self.counts is not None else 0
+        rows = torch.empty((max(total_cap, 1), 8), dtype=torch.int32, device=self.device)
+        offs = torch.empty((b + 1,), dtype=torch.int32, device=self.device)
+        _lib.check(self.lib.am_cc_pack_rows(self.ctx, b, _p(rows), max(total_cap, 1), _p(offs), _stream()), "am_cc_pack_rows")
+        return rows[:total_cap], offs
+
+
+class Estimator:
+    """Handle on the device-side temporal matcher (am_est_*)."""
+
+    def __init__(self, width, height, min_recall, min_precision, max_gap, max_uniques=0, max_active=0, arena_words=0, device=None):
+        self.lib = _lib.lib()
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        with torch.cuda.device(self.device):
+            self.h = self.lib.am_est_create(int(width), int(height), float(min_recall), float(min_precision), int(max_gap),
+                                            int(max_uniques), int(max_active), int(arena_words))
+        if not self.h:
+            raise _lib.AccessMathB200Error("am_est_create failed")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.am_est_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def add_frames(self, engine, first, n):
+        _lib.check(self.lib.am_est_add_frames(self.h, engine.ctx, first, n, _stream()), "am_est_add_frames")
+
+    def state(self):
+        s = np.zeros(6, dtype=np.int32)
+        _lib.check(self.lib.am_est_state(self.h, _np(s), _stream()), "am_est_state")
+        tempo = (int(s[4]) & 0xffffffff) | ((int(s[5]) & 0xffffffff) << 32)
+        return {"n_unique": int(s[0]), "n_active": int(s[1]), "img_idx": int(s[2]), "tempo_count": tempo}
+
+    def uniques(self, first, n):
+        rows = np.zeros((n, 8), dtype=np.int32)
+        _lib.check(self.lib.am_est_read_uniques(self.h, first, n, _np(rows), _stream()), "am_est_read_uniques")
+        return rows                      # first_frame, first_label, min_x, max_x, min_y, max_y, size, last_seen
+
+    def unique_crop(self, u, words):
+        w = np.zeros(words, dtype=np.uint32)
+        _lib.check(self.lib.am_est_read_unique_crop(self.h, u, words, _np(w), _stream()), "am_est_read_unique_crop")
+        return w
+
+    # ---- frame-shard hand-off ----------------------------------------------------------------------
+    def export_state(self):
+        """-> (header int64[6], meta int32 (n_act,10) device, crops int32 (words,) device)."""
+        sizes = np.zeros(2, dtype=np.int64)
+        _lib.check(self.lib.am_est_export_sizes(self.h, _np(sizes), _stream()), "am_est_export_sizes")
+        n_act, words = int(sizes[0]), int(sizes[1])
+        meta = torch.zeros((max(n_act, 1), 10), dtype=torch.int32, device=self.device)
+        crops = torch.zeros((max(words, 1),), dtype=torch.int32, device=self.device)
+        if n_act:
+            _lib.check(self.lib.am_est_export(self.h, _p(meta), _p(crops), _stream()), "am_est_export")
+        st = self.state()
+        header = torch.tensor([n_act, words, st["n_unique"], st["img_idx"], st["tempo_count"], 0], dtype=torch.int64)
+        return header, meta, crops
+
+    def import_state(self, header, meta, crops):
+        n_act, words, n_unique, img_idx, tempo = [int(v) for v in header[:5]]
+        _lib.check(self.lib.am_est_import(self.h, n_act, n_unique, img_idx, tempo, _p(meta) if n_act else None,
+                                          _p(crops) if n_act else None, words, _stream()), "am_est_import")

@@ -1,0 +1,1008 @@
+// cc_kernels.cu -- connected-component labeling, per-CC statistics, crops and temporal matching
+// on bit-packed masks, hand-written for sm_100a (B200).  HBM/latency-bound integer work: coalesced
+// word loads, warp-aggregated atomics, no tensor cores.
+//
+// Replaces (R/ = reference ACCESS2021_release/):
+//   scipy.ndimage.label                      R/AccessMath/preprocessing/content/labeler.py:126
+//   CC_AgeBoundaries                         R/accessmath_lib.c:357-413
+//   Labeler.extractSpatioTemporalContent     R/AccessMath/preprocessing/content/labeler.py:117-191
+//   IntervalIndex.find_matches + getOverlapFMeasure + CCStabilityEstimator.add_frame
+//        R/AccessMath/preprocessing/tools/interval_index.py:42-99,
+//        R/AM_CommonTools/data/connected_component.py:202-250,
+//        R/AccessMath/preprocessing/content/cc_stability_estimator.py:41-155
+//
+// Data layout (all device, per frame f of a batch):
+//   bits   [H][WPR] uint32, bit b of word w = pixel x = 32*w + b (LSB first), WPR = words/row padded to 4
+//   runs   = maximal horizontal runs of ink, numbered in raster order (row, then x): run id order ==
+//            raster order of first pixels, so the minimum run id of a component is its first raster pixel
+//            and rank(root run) + 1 == the SciPy label.
+//   labels [H][W] int32 (optional output)
+//   label table (by label-1): min_y, max_y, min_x, max_x, count     (CC_AgeBoundaries outputs)
+//   kept table  (CCs with count >= min_pixels, ascending label): raw label, crop offset
+//   crops  : per kept CC a word-aligned bit-packed crop: rows min_y..max_y, words (min_x>>5)..(max_x>>5),
+//            bits at their ABSOLUTE x position, so two crops AND together without shifting.
+#include "am_common.cuh"
+#include "../../include/accessmath_b200.h"
+
+#define NONE_U32 0xFFFFFFFFu
+
+struct CcFrame {                 // device pointers of one frame slot
+    uint32_t* wprefix;           // [H][WPR] runs that start before word w in its row
+    int* rowbase;                // [H+1] exclusive scan of runs per row
+    int* run_parent;             // [MR]
+    int* run_yx;                 // [MR] y<<16 | x_start
+    int* run_xe;                 // [MR] x_end (inclusive)
+    int* run_label;              // [MR]
+    int* blockcnt;               // [MR/1024+1]
+    int* t_min_y; int* t_max_y; int* t_min_x; int* t_max_x; int* t_count;   // [ML]
+    uint32_t* lab_crop_off;      // [ML]
+    int* kept_label;             // [MK]
+    uint32_t* kept_crop_off;     // [MK]
+    uint32_t* crops;             // [CW]
+    int* match_unique;           // [MK] result of temporal matching: unique idx per kept CC
+};
+
+struct am_cc_ctx {
+    int W, H, WPR, B, MR, ML, MK, CW, min_pixels;
+    CcFrame* h_frames;           // host copy of slot descriptors
+    CcFrame* d_frames;           // device copy
+    int* d_counts;               // [B][4]: n_runs, n_labels, n_kept, crop_words
+    int* d_status;               // capacity-overflow flags
+    void* slab;                  // one allocation
+    int* h_counts;               // pinned
+};
+
+// ------------------------------------------------------------------------------------------------
+// K0: uint8 mask -> bit-packed (ink = nonzero)
+__global__ void k_pack_u8(const uint8_t* __restrict__ src, int W, int H, int WPR, uint32_t* __restrict__ bits) {
+    const int f = blockIdx.z, y = blockIdx.y;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint8_t* row = src + ((size_t)f * H + y) * W;
+    bool ink = (x < W) && row[x] != 0;
+    unsigned m = __ballot_sync(0xffffffffu, ink);
+    if ((threadIdx.x & 31) == 0 && (x >> 5) < WPR) bits[((size_t)f * H + y) * WPR + (x >> 5)] = m;
+}
+
+// bit-packed -> uint8 0/255 (used to hand masks back in the reference's format)
+__global__ void k_unpack_u8(const uint32_t* __restrict__ bits, int W, int H, int WPR, uint8_t* __restrict__ dst) {
+    const int f = blockIdx.z, y = blockIdx.y;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= W) return;
+    uint32_t m = bits[((size_t)f * H + y) * WPR + (x >> 5)];
+    dst[((size_t)f * H + y) * W + x] = ((m >> (x & 31)) & 1u) ? 255 : 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: one warp per row: runs starting before each word, runs per row.
+__global__ void k_row_scan(const uint32_t* __restrict__ bits, const CcFrame* __restrict__ frames, int H, int WPR) {
+    const int f = blockIdx.y;
+    const int y = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (y >= H) return;
+    const int lane = threadIdx.x & 31;
+    const uint32_t* row = bits + ((size_t)f * H + y) * WPR;
+    uint32_t* wp = frames[f].wprefix + (size_t)y * WPR;
+    int running = 0;
+    uint32_t carry = 0;                               // bit31 of the word before this chunk
+    for (int w0 = 0; w0 < WPR; w0 += 32) {
+        int w = w0 + lane;
+        uint32_t m = (w < WPR) ? row[w] : 0u;
+        uint32_t prev = __shfl_up_sync(0xffffffffu, m, 1);
+        if (lane == 0) prev = carry;
+        uint32_t starts = m & ~((m << 1) | (prev >> 31));
+        int c = __popc(starts);
+        int inc = warp_incl_scan(c);
+        if (w < WPR) wp[w] = (uint32_t)(running + inc - c);
+        running += __shfl_sync(0xffffffffu, inc, 31);
+        carry = __shfl_sync(0xffffffffu, m, 31);
+    }
+    if (lane == 0) frames[f].rowbase[y + 1] = running;   // counts, scanned in place by k_row_base
+}
+
+// K2: one block per frame: exclusive scan of runs per row -> rowbase[0..H], n_runs
+__global__ void k_row_base(const CcFrame* __restrict__ frames, int H, int MR, int* __restrict__ counts, int* __restrict__ status) {
+    __shared__ int sm[33];
+    const int f = blockIdx.x;
+    int* rb = frames[f].rowbase;
+    int carry = 0;
+    for (int y0 = 0; y0 < H; y0 += blockDim.x) {
+        int y = y0 + threadIdx.x;
+        int v = (y < H) ? rb[y + 1] : 0;
+        int total;
+        int ex = block_excl_scan(v, sm, &total);
+        __syncthreads();
+        if (y < H) rb[y + 1] = carry + ex + v;           // inclusive -> rowbase[y+1]
+        carry += total;
+    }
+    if (threadIdx.x == 0) {
+        rb[0] = 0;
+        if (carry > MR) { atomicOr(status, 1); }
+        counts[f * 4 + 0] = carry;
+    }
+}
+
+__device__ __forceinline__ uint32_t mask_le(int b) { return (2u << b) - 1u; }   // bits 0..b
+
+// K3: one thread per word: write run start / end records, parent = self
+__global__ void k_run_init(const uint32_t* __restrict__ bits, const CcFrame* __restrict__ frames, int H, int WPR, int MR) {
+    const int f = blockIdx.z, y = blockIdx.y;
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= WPR) return;
+    const uint32_t* row = bits + ((size_t)f * H + y) * WPR;
+    const CcFrame fr = frames[f];
+    uint32_t m = row[w];
+    if (m == 0) return;
+    uint32_t cin = (w > 0) ? (row[w - 1] >> 31) : 0u;
+    uint32_t nb0 = (w + 1 < WPR) ? (row[w + 1] & 1u) : 0u;
+    uint32_t starts = m & ~((m << 1) | cin);
+    uint32_t ends = m & ~((m >> 1) | (nb0 << 31));
+    int base = fr.rowbase[y] + (int)fr.wprefix[(size_t)y * WPR + w];
+    uint32_t s = starts;
+    int k = 0;
+    while (s) {
+        int b = __ffs(s) - 1; s &= s - 1;
+        int id = base + k++;
+        if (id < MR) { fr.run_yx[id] = (y << 16) | (w * 32 + b); fr.run_parent[id] = id; }
+    }
+    uint32_t e = ends;
+    while (e) {
+        int b = __ffs(e) - 1; e &= e - 1;
+        int id = base + __popc(starts & mask_le(b)) - 1;
+        if (id >= 0 && id < MR) fr.run_xe[id] = w * 32 + b;
+    }
+}
+
+__device__ __forceinline__ int uf_find(int* parent, int a) {
+    int p;
+    while ((p = ((volatile int*)parent)[a]) != a) a = p;
+    return a;
+}
+__device__ __forceinline__ void uf_union(int* parent, int a, int b) {
+    while (true) {
+        a = uf_find(parent, a); b = uf_find(parent, b);
+        if (a == b) return;
+        if (a < b) { int t = a; a = b; b = t; }        // a > b : link the larger root under the smaller
+        int old = atomicMin(&parent[a], b);
+        if (old == a) return;
+        a = old;
+    }
+}
+
+// K4: one thread per word (rows >= 1): union the runs of vertically adjacent ink
+__global__ void k_run_merge(const uint32_t* __restrict__ bits, const CcFrame* __restrict__ frames, int H, int WPR, int MR) {
+    const int f = blockIdx.z, y = blockIdx.y + 1;
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= WPR || y >= H) return;
+    const uint32_t* row = bits + ((size_t)f * H + y) * WPR;
+    const uint32_t* up = row - WPR;
+    uint32_t m = row[w], u = up[w];
+    uint32_t ov = m & u;
+    if (ov == 0) return;
+    uint32_t mp = (w > 0) ? row[w - 1] : 0u, upv = (w > 0) ? up[w - 1] : 0u;
+    uint32_t ovs = ov & ~(ov << 1);
+    ovs &= ~(((mp & upv) >> 31) & 1u);                  // overlap continuing from the previous word: done there
+    if (ovs == 0) return;
+    const CcFrame fr = frames[f];
+    uint32_t st_m = m & ~((m << 1) | (mp >> 31));
+    uint32_t st_u = u & ~((u << 1) | (upv >> 31));
+    int base_m = fr.rowbase[y] + (int)fr.wprefix[(size_t)y * WPR + w];
+    int base_u = fr.rowbase[y - 1] + (int)fr.wprefix[(size_t)(y - 1) * WPR + w];
+    while (ovs) {
+        int b = __ffs(ovs) - 1; ovs &= ovs - 1;
+        int ia = base_m + __popc(st_m & mask_le(b)) - 1;
+        int ib = base_u + __popc(st_u & mask_le(b)) - 1;
+        if (ia < MR && ib < MR && ia >= 0 && ib >= 0) uf_union(fr.run_parent, ia, ib);
+    }
+}
+
+// K5: flatten + count roots per block of 1024 runs
+__global__ void k_run_flatten(const CcFrame* __restrict__ frames, const int* __restrict__ counts, int MR) {
+    const int f = blockIdx.y;
+    int n = min(counts[f * 4], MR);
+    if ((int)(blockIdx.x * blockDim.x) >= n) return;
+    const CcFrame fr = frames[f];
+    int id = blockIdx.x * blockDim.x + threadIdx.x;
+    int isroot = 0;
+    if (id < n) {
+        int r = uf_find(fr.run_parent, id);
+        fr.run_parent[id] = r;
+        isroot = (r == id);
+    }
+    int c = __syncthreads_count(isroot);
+    if (threadIdx.x == 0) fr.blockcnt[blockIdx.x] = c;
+}
+
+// K6: one block per frame: scan block counts -> block bases, n_labels
+__global__ void k_block_base(const CcFrame* __restrict__ frames, int* __restrict__ counts, int MR, int ML, int* __restrict__ status) {
+    __shared__ int sm[33];
+    const int f = blockIdx.x;
+    int n = min(counts[f * 4], MR);
+    int nb = (n + 1023) >> 10;
+    int* bc = frames[f].blockcnt;
+    int carry = 0;
+    for (int i0 = 0; i0 < nb; i0 += blockDim.x) {
+        int i = i0 + threadIdx.x;
+        int v = (i < nb) ? bc[i] : 0;
+        int total;
+        int ex = block_excl_scan(v, sm, &total);
+        __syncthreads();
+        if (i < nb) bc[i] = carry + ex;
+        carry += total;
+    }
+    if (threadIdx.x == 0) {
+        if (carry > ML) atomicOr(status, 2);
+        counts[f * 4 + 1] = carry;
+    }
+}
+
+// K7: roots get their raster-order label (rank + 1) and initialise their table row
+__global__ void k_root_label(const CcFrame* __restrict__ frames, const int* __restrict__ counts, int MR, int ML, int W, int H) {
+    __shared__ int sm[33];
+    const int f = blockIdx.y;
+    int n = min(counts[f * 4], MR);
+    if ((int)(blockIdx.x * blockDim.x) >= n) return;
+    const CcFrame fr = frames[f];
+    int id = blockIdx.x * blockDim.x + threadIdx.x;
+    int isroot = (id < n) && (fr.run_parent[id] == id);
+    int total;
+    int ex = block_excl_scan(isroot, sm, &total);
+    if (isroot) {
+        int lab = fr.blockcnt[blockIdx.x] + ex;          // 0-based
+        fr.run_label[id] = lab + 1;
+        if (lab < ML) {                                  // accessmath_lib.c:364-374
+            fr.t_min_y[lab] = H; fr.t_max_y[lab] = 0; fr.t_min_x[lab] = W; fr.t_max_x[lab] = 0; fr.t_count[lab] = 0;
+        }
+    }
+}
+
+// K8: every run takes its root's label; warp-aggregated bbox / count reduction (accessmath_lib.c:378-409)
+__global__ void k_run_stats(const CcFrame* __restrict__ frames, const int* __restrict__ counts, int MR, int ML) {
+    const int f = blockIdx.y;
+    int n = min(counts[f * 4], MR);
+    if ((int)(blockIdx.x * blockDim.x) >= n) return;
+    const CcFrame fr = frames[f];
+    int id = blockIdx.x * blockDim.x + threadIdx.x;
+    int lab = 0, y = 0, xs = 0, xe = 0;
+    if (id < n) {
+        lab = fr.run_label[fr.run_parent[id]];
+        fr.run_label[id] = lab;
+        int yx = fr.run_yx[id];
+        y = yx >> 16; xs = yx & 0xffff; xe = fr.run_xe[id];
+        if (lab > ML) lab = 0;
+    }
+    unsigned peers = __match_any_sync(0xffffffffu, lab);
+    int mn_x = __reduce_min_sync(peers, xs), mx_x = __reduce_max_sync(peers, xe);
+    int mn_y = __reduce_min_sync(peers, y), mx_y = __reduce_max_sync(peers, y);
+    int cnt = __reduce_add_sync(peers, xe - xs + 1);
+    if (lab > 0 && (int)(threadIdx.x & 31) == __ffs(peers) - 1) {
+        int l = lab - 1;
+        atomicMin(&fr.t_min_x[l], mn_x); atomicMax(&fr.t_max_x[l], mx_x);
+        atomicMin(&fr.t_min_y[l], mn_y); atomicMax(&fr.t_max_y[l], mx_y);
+        atomicAdd(&fr.t_count[l], cnt);
+    }
+}
+
+// K9: one block per frame: compact labels with count >= min_pixels (labeler.py:177), crop offsets
+__global__ void k_kept_scan(const CcFrame* __restrict__ frames, int* __restrict__ counts, int ML, int MK, int CW,
+                            int min_pixels, int* __restrict__ status) {
+    __shared__ int sm[33];
+    const int f = blockIdx.x;
+    const CcFrame fr = frames[f];
+    int n = min(counts[f * 4 + 1], ML);
+    int kcarry = 0; unsigned wcarry = 0; bool over = false;
+    for (int i0 = 0; i0 < n; i0 += blockDim.x) {
+        int l = i0 + threadIdx.x;
+        int keep = 0, words = 0;
+        if (l < n && fr.t_count[l] >= min_pixels) {
+            keep = 1;
+            words = ((fr.t_max_x[l] >> 5) - (fr.t_min_x[l] >> 5) + 1) * (fr.t_max_y[l] - fr.t_min_y[l] + 1);
+        }
+        int ktot, wtot;
+        int kex = block_excl_scan(keep, sm, &ktot);
+        int wex = block_excl_scan(words, sm, &wtot);
+        __syncthreads();
+        if (l < n) {
+            uint32_t off = NONE_U32;
+            if (keep) {
+                int ki = kcarry + kex;
+                unsigned wo = wcarry + (unsigned)wex;
+                if (ki < MK && wo + (unsigned)words <= (unsigned)CW) {
+                    fr.kept_label[ki] = l + 1; fr.kept_crop_off[ki] = wo; off = wo;
+                } else over = true;
+            }
+            fr.lab_crop_off[l] = off;
+        }
+        kcarry += ktot; wcarry += (unsigned)wtot;
+    }
+    if (__syncthreads_or(over) && threadIdx.x == 0) atomicOr(status, 4);
+    if (threadIdx.x == 0) {
+        counts[f * 4 + 2] = min(kcarry, MK);
+        counts[f * 4 + 3] = (int)min(wcarry, (unsigned)CW);
+    }
+}
+
+__global__ void k_crop_clear(const CcFrame* __restrict__ frames, const int* __restrict__ counts) {
+    const int f = blockIdx.y;
+    int n = counts[f * 4 + 3];
+    uint32_t* c = frames[f].crops;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) c[i] = 0u;
+}
+
+// K10: one thread per run: OR the run's bits into its CC's crop (labeler.py:183, bit-packed)
+__global__ void k_crop_fill(const CcFrame* __restrict__ frames, const int* __restrict__ counts, int MR) {
+    const int f = blockIdx.y;
+    int n = min(counts[f * 4], MR);
+    int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= n) return;
+    const CcFrame fr = frames[f];
+    int lab = fr.run_label[id];
+    if (lab <= 0) return;
+    uint32_t off = fr.lab_crop_off[lab - 1];
+    if (off == NONE_U32) return;
+    int l = lab - 1;
+    int wx0 = fr.t_min_x[l] >> 5, cw = (fr.t_max_x[l] >> 5) - wx0 + 1;
+    int yx = fr.run_yx[id];
+    int y = yx >> 16, xs = yx & 0xffff, xe = fr.run_xe[id];
+    uint32_t* dst = fr.crops + off + (size_t)(y - fr.t_min_y[l]) * cw - wx0;
+    for (int w = xs >> 5; w <= (xe >> 5); ++w) {
+        int lo = max(xs, w * 32) & 31, hi = min(xe, w * 32 + 31) & 31;
+        uint32_t b = mask_le(hi) & ~(mask_le(lo) >> 1);
+        if (lo == 0) b = mask_le(hi);
+        atomicOr(&dst[w], b);
+    }
+}
+
+// K11: label image (int32, 0 = background), one thread per pixel, coalesced stores
+__global__ void k_label_image(const uint32_t* __restrict__ bits, const CcFrame* __restrict__ frames, int W, int H, int WPR, int MR,
+                              int32_t* __restrict__ labels) {
+    const int f = blockIdx.z, y = blockIdx.y;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= W) return;
+    const uint32_t* row = bits + ((size_t)f * H + y) * WPR;
+    int w = x >> 5, b = x & 31;
+    uint32_t m = row[w];
+    int lab = 0;
+    if ((m >> b) & 1u) {
+        const CcFrame fr = frames[f];
+        uint32_t cin = (w > 0) ? (row[w - 1] >> 31) : 0u;
+        uint32_t starts = m & ~((m << 1) | cin);
+        int id = fr.rowbase[y] + (int)fr.wprefix[(size_t)y * WPR + w] + __popc(starts & mask_le(b)) - 1;
+        if (id >= 0 && id < MR) lab = fr.run_label[id];
+    }
+    labels[((size_t)f * H + y) * W + x] = lab;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Legacy operator: CC_AgeBoundaries on an arbitrary int32 label image (+ fp32 ages), R/accessmath_lib.c:357-413
+__device__ __forceinline__ unsigned f32_key(float v) {     // order-preserving float -> unsigned
+    unsigned b = __float_as_uint(v);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float key_f32(unsigned k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+__global__ void k_ageb_init(int n, int W, int H, int* mny, int* mxy, int* mnx, int* mxx, int* cnt, unsigned* agek) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    mny[i] = H; mxy[i] = 0; mnx[i] = W; mxx[i] = 0; cnt[i] = 0; agek[i] = 0xFFFFFFFFu;
+}
+__global__ void k_ageb_scan(const int32_t* __restrict__ labels, const float* __restrict__ ages, int W, int H, int n,
+                            int* mny, int* mxy, int* mnx, int* mxx, int* cnt, unsigned* agek) {
+    const int y = blockIdx.y;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int lab = 0; unsigned ak = 0xFFFFFFFFu;
+    if (x < W) {
+        size_t idx = (size_t)y * W + x;
+        lab = labels[idx];
+        if (lab < 0 || lab > n) lab = 0;                 // the reference would write out of bounds here
+        if (lab > 0 && ages) ak = f32_key(ages[idx]);
+        else if (lab > 0) ak = f32_key(0.0f);
+    }
+    unsigned peers = __match_any_sync(0xffffffffu, lab);
+    int mn_x = __reduce_min_sync(peers, x), mx_x = __reduce_max_sync(peers, x);
+    int c = __popc(peers);
+    unsigned amin = __reduce_min_sync(peers, ak);
+    if (lab > 0 && (int)(threadIdx.x & 31) == __ffs(peers) - 1) {
+        int l = lab - 1;
+        atomicMin(&mnx[l], mn_x); atomicMax(&mxx[l], mx_x);
+        atomicMin(&mny[l], y); atomicMax(&mxy[l], y);
+        atomicAdd(&cnt[l], c);
+        atomicMin(&agek[l], amin);
+    }
+}
+__global__ void k_ageb_finish(int n, const int* cnt, const unsigned* agek, float* out_age) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out_age[i] = (cnt[i] > 0) ? key_f32(agek[i]) : -1.0f;    // accessmath_lib.c:373 "-1 = unset"
+}
+
+// ------------------------------------------------------------------------------------------------
+// Temporal matching (CCStabilityEstimator.add_frame, cc_stability_estimator.py:41-155)
+struct am_estimator {
+    int W, H, max_gap, MU, MA;
+    unsigned long long AW;       // arena capacity in words
+    unsigned long long* tmp_off; // [MA] scratch for export/import
+    double min_recall, min_precision;
+    // unique table (index = global unique idx)
+    int *u_min_x, *u_max_x, *u_min_y, *u_max_y, *u_size, *u_last, *u_first_frame, *u_first_label;
+    unsigned long long* u_crop_off;
+    uint32_t* arena;             // first-seen crops, append only
+    int *act[2];                 // active lists (ascending unique idx), double buffered
+    int cur;                     // which act buffer is current
+    // device scalars: [0]=n_uniq [1]=n_act [2]=img_idx [3]=status ; 64-bit: tested, arena_used
+    int* d_scal; unsigned long long* d_scal64;
+    void* slab;
+    int* h_scal; unsigned long long* h_scal64;   // pinned
+};
+
+// M1: one warp per current CC: scan the active uniques in ascending order, count bbox-overlapping
+// candidates (tempo_count, :85) and take the first one whose pixel overlap passes recall/precision (:94-106)
+__global__ void k_match(const CcFrame* __restrict__ frames, const int* __restrict__ counts, int f,
+                        const int* __restrict__ act, const int* __restrict__ scal,
+                        const int* __restrict__ u_min_x, const int* __restrict__ u_max_x, const int* __restrict__ u_min_y,
+                        const int* __restrict__ u_max_y, const int* __restrict__ u_size, int* __restrict__ u_last,
+                        const unsigned long long* __restrict__ u_crop_off, const uint32_t* __restrict__ arena,
+                        double min_recall, double min_precision, unsigned long long* __restrict__ tested_total) {
+    const CcFrame fr = frames[f];
+    const int n_kept = counts[f * 4 + 2];
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= n_kept) return;
+    const int lane = threadIdx.x & 31;
+    const int img_idx = scal[2], n_act = scal[1];
+    int found = -1;
+    if (img_idx > 0) {                                   // frame 0: every CC becomes a unique CC (:52-69)
+        const int l = fr.kept_label[c] - 1;
+        const int cx0 = fr.t_min_x[l], cx1 = fr.t_max_x[l], cy0 = fr.t_min_y[l], cy1 = fr.t_max_y[l], csz = fr.t_count[l];
+        const int cwx0 = cx0 >> 5, ccw = (cx1 >> 5) - cwx0 + 1;
+        const uint32_t* ccrop = fr.crops + fr.kept_crop_off[c];
+        unsigned tested = 0;
+        for (int a0 = 0; a0 < n_act; a0 += 32) {
+            int u = (a0 + lane < n_act) ? act[a0 + lane] : -1;
+            bool ov = false;
+            if (u >= 0) ov = (cy1 >= u_min_y[u] && u_max_y[u] >= cy0 && cx1 >= u_min_x[u] && u_max_x[u] >= cx0);
+            unsigned bal = __ballot_sync(0xffffffffu, ov);
+            tested += __popc(bal);
+            while (found < 0 && bal) {
+                int j = __ffs(bal) - 1; bal &= bal - 1;
+                int uu = __shfl_sync(0xffffffffu, u, j);
+                int ux0 = u_min_x[uu], ux1 = u_max_x[uu], uy0 = u_min_y[uu], uy1 = u_max_y[uu];
+                int uwx0 = ux0 >> 5, ucw = (ux1 >> 5) - uwx0 + 1;
+                const uint32_t* ucrop = arena + u_crop_off[uu];
+                int y0 = max(cy0, uy0), y1 = min(cy1, uy1);
+                int w0 = max(cwx0, uwx0), w1 = min(cx1 >> 5, ux1 >> 5);
+                int nw = w1 - w0 + 1, tot = nw * (y1 - y0 + 1);
+                int m = 0;
+                for (int i = lane; i < tot; i += 32) {
+                    int yy = y0 + i / nw, ww = w0 + i % nw;
+                    uint32_t a = ccrop[(size_t)(yy - cy0) * ccw + (ww - cwx0)];
+                    uint32_t b = ucrop[(size_t)(yy - uy0) * ucw + (ww - uwx0)];
+                    m += __popc(a & b);
+                }
+                m = __reduce_add_sync(0xffffffffu, m);
+                double recall = (double)m / (double)csz;             // connected_component.py:239-240
+                double precision = (double)m / (double)u_size[uu];
+                if (recall >= min_recall && precision >= min_precision) found = uu;
+            }
+        }
+        if (lane == 0) {
+            if (tested) atomicAdd(tested_total, (unsigned long long)tested);
+            if (found >= 0) u_last[found] = img_idx;     // :104
+        }
+    }
+    if (lane == 0) fr.match_unique[c] = found;
+}
+
+// M2: one block: number the new uniques (ascending current order), copy their crops, expire, append
+__global__ void k_match_update(const CcFrame* __restrict__ frames, const int* __restrict__ counts, int f,
+                               const int* __restrict__ act_in, int* __restrict__ act_out, int* __restrict__ scal,
+                               unsigned long long* __restrict__ scal64,
+                               int* u_min_x, int* u_max_x, int* u_min_y, int* u_max_y, int* u_size, int* u_last,
+                               int* u_first_frame, int* u_first_label, unsigned long long* u_crop_off, uint32_t* arena,
+                               int MU, int MA, unsigned long long AW, int max_gap) {
+    __shared__ int sm[33];
+    __shared__ unsigned long long s_arena;
+    const CcFrame fr = frames[f];
+    const int n_kept = counts[f * 4 + 2];
+    const int img_idx = scal[2], n_uniq0 = scal[0], n_act0 = scal[1];
+    if (threadIdx.x == 0) s_arena = scal64[1];
+    __syncthreads();
+    // 1. expiry of the previously active uniques (:127-145; not on frame 0) -> act_out[0..keep)
+    int kept_act = 0;
+    for (int i0 = 0; i0 < n_act0; i0 += blockDim.x) {
+        int i = i0 + threadIdx.x;
+        int u = (i < n_act0) ? act_in[i] : -1;
+        int keep = (u >= 0) && (img_idx == 0 || img_idx - u_last[u] < max_gap);
+        int tot;
+        int ex = block_excl_scan(keep, sm, &tot);
+        __syncthreads();
+        if (keep) act_out[kept_act + ex] = u;
+        kept_act += tot;
+    }
+    // 2. new uniques (:111-124)
+    int n_new = 0;
+    bool over = false;
+    for (int c0 = 0; c0 < n_kept; c0 += blockDim.x) {
+        int c = c0 + threadIdx.x;
+        int isnew = (c < n_kept) && (fr.match_unique[c] < 0);
+        int words = 0, l = 0;
+        if (isnew) {
+            l = fr.kept_label[c] - 1;
+            words = ((fr.t_max_x[l] >> 5) - (fr.t_min_x[l] >> 5) + 1) * (fr.t_max_y[l] - fr.t_min_y[l] + 1);
+        }
+        int tot, wtot;
+        int ex = block_excl_scan(isnew, sm, &tot);
+        int wex = block_excl_scan(words, sm, &wtot);
+        __syncthreads();
+        if (isnew) {
+            int u = n_uniq0 + n_new + ex;
+            int ai = kept_act + n_new + ex;
+            unsigned long long off = s_arena + (unsigned long long)wex;
+            if (u < MU && ai < MA && off + words <= AW) {
+                u_min_x[u] = fr.t_min_x[l]; u_max_x[u] = fr.t_max_x[l]; u_min_y[u] = fr.t_min_y[l]; u_max_y[u] = fr.t_max_y[l];
+                u_size[u] = fr.t_count[l]; u_last[u] = img_idx; u_first_frame[u] = img_idx; u_first_label[u] = l + 1;
+                u_crop_off[u] = off;
+                act_out[ai] = u;
+                fr.match_unique[c] = u;
+            } else over = true;
+        }
+        __syncthreads();
+        n_new += tot;
+        if (threadIdx.x == 0) s_arena += (unsigned long long)wtot;
+        __syncthreads();
+    }
+    // 3. copy the crops of the new uniques into the arena (first-seen instance, never updated): warp per CC
+    for (int c = threadIdx.x >> 5; c < n_kept; c += (blockDim.x >> 5)) {
+        int u = fr.match_unique[c];
+        if (u < n_uniq0 || u >= MU) continue;
+        int l = fr.kept_label[c] - 1;
+        int words = ((fr.t_max_x[l] >> 5) - (fr.t_min_x[l] >> 5) + 1) * (fr.t_max_y[l] - fr.t_min_y[l] + 1);
+        const uint32_t* src = fr.crops + fr.kept_crop_off[c];
+        uint32_t* dst = arena + u_crop_off[u];
+        for (int i = threadIdx.x & 31; i < words; i += 32) dst[i] = src[i];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (over) atomicOr(&scal[3], 8);
+        scal[0] = min(n_uniq0 + n_new, MU);
+        scal[1] = min(kept_act + n_new, MA);
+        scal[2] = img_idx + 1;
+        scal64[1] = s_arena;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// result rows: unique_idx, raw_label, min_x, max_x, min_y, max_y, size, crop_offset
+__device__ __forceinline__ void write_row(const CcFrame& fr, int c, int* row) {
+    int l = fr.kept_label[c] - 1;
+    row[0] = fr.match_unique[c]; row[1] = l + 1; row[2] = fr.t_min_x[l]; row[3] = fr.t_max_x[l];
+    row[4] = fr.t_min_y[l]; row[5] = fr.t_max_y[l]; row[6] = fr.t_count[l]; row[7] = (int)fr.kept_crop_off[c];
+}
+__global__ void k_rows_one(const CcFrame* __restrict__ frames, int f, int n, int* __restrict__ rows) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < n) write_row(frames[f], c, rows + (size_t)c * 8);
+}
+__global__ void k_row_offsets(const int* __restrict__ counts, int B, int* __restrict__ offs) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        int s = 0;
+        for (int f = 0; f < B; ++f) { offs[f] = s; s += counts[f * 4 + 2]; }
+        offs[B] = s;
+    }
+}
+__global__ void k_rows_all(const CcFrame* __restrict__ frames, const int* __restrict__ counts, const int* __restrict__ offs,
+                           int cap, int* __restrict__ rows) {
+    const int f = blockIdx.y;
+    int n = counts[f * 4 + 2];
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    int r = offs[f] + c;
+    if (r < cap) write_row(frames[f], c, rows + (size_t)r * 8);
+}
+__global__ void k_init_match(const CcFrame* __restrict__ frames, int MK) {
+    int* m = frames[blockIdx.y].match_unique;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < MK; i += gridDim.x * blockDim.x) m[i] = -1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// active-set export / import (frame-shard hand-off)
+__device__ __forceinline__ int crop_words_of(int mnx, int mxx, int mny, int mxy) {
+    return ((mxx >> 5) - (mnx >> 5) + 1) * (mxy - mny + 1);
+}
+__global__ void k_export_sizes(const int* __restrict__ act, const int* __restrict__ scal, const int* u_min_x, const int* u_max_x,
+                               const int* u_min_y, const int* u_max_y, unsigned long long* __restrict__ out) {
+    __shared__ unsigned long long sm[32];
+    int n = scal[1];
+    unsigned long long s = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        int u = act[i];
+        s += (unsigned long long)crop_words_of(u_min_x[u], u_max_x[u], u_min_y[u], u_max_y[u]);
+    }
+    for (int o = 16; o; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += sm[i];
+        out[0] = (unsigned long long)n; out[1] = t;
+    }
+}
+// one block: meta rows + crop offsets (running), then warp-per-unique crop copy
+__global__ void k_export(const int* __restrict__ act, const int* __restrict__ scal, const int* u_min_x, const int* u_max_x,
+                         const int* u_min_y, const int* u_max_y, const int* u_size, const int* u_last, const int* u_ff,
+                         const int* u_fl, const unsigned long long* u_crop_off, const uint32_t* __restrict__ arena,
+                         int* __restrict__ meta, uint32_t* __restrict__ crops, unsigned long long* __restrict__ tmp_off) {
+    __shared__ int sm[33];
+    int n = scal[1];
+    unsigned long long carry = 0;
+    for (int i0 = 0; i0 < n; i0 += blockDim.x) {
+        int i = i0 + threadIdx.x;
+        int words = 0, u = 0;
+        if (i < n) { u = act[i]; words = crop_words_of(u_min_x[u], u_max_x[u], u_min_y[u], u_max_y[u]); }
+        int tot;
+        int ex = block_excl_scan(words, sm, &tot);
+        __syncthreads();
+        if (i < n) {
+            int* m = meta + (size_t)i * 10;
+            m[0] = u; m[1] = u_min_x[u]; m[2] = u_max_x[u]; m[3] = u_min_y[u]; m[4] = u_max_y[u]; m[5] = u_size[u];
+            m[6] = u_last[u]; m[7] = u_ff[u]; m[8] = u_fl[u]; m[9] = words;
+            tmp_off[i] = carry + (unsigned long long)ex;
+        }
+        carry += (unsigned long long)tot;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x >> 5; i < n; i += (blockDim.x >> 5)) {
+        int u = act[i];
+        int words = meta[(size_t)i * 10 + 9];
+        const uint32_t* src = arena + u_crop_off[u];
+        uint32_t* dst = crops + tmp_off[i];
+        for (int k = threadIdx.x & 31; k < words; k += 32) dst[k] = src[k];
+    }
+}
+__global__ void k_import(int n, const int* __restrict__ meta, const uint32_t* __restrict__ crops, int* act, int* u_min_x,
+                         int* u_max_x, int* u_min_y, int* u_max_y, int* u_size, int* u_last, int* u_ff, int* u_fl,
+                         unsigned long long* u_crop_off, uint32_t* arena, unsigned long long* tmp_off, int MU) {
+    __shared__ int sm[33];
+    unsigned long long carry = 0;
+    for (int i0 = 0; i0 < n; i0 += blockDim.x) {
+        int i = i0 + threadIdx.x;
+        int words = (i < n) ? meta[(size_t)i * 10 + 9] : 0;
+        int tot;
+        int ex = block_excl_scan(words, sm, &tot);
+        __syncthreads();
+        if (i < n) {
+            const int* m = meta + (size_t)i * 10;
+            int u = m[0];
+            if (u >= 0 && u < MU) {
+                u_min_x[u] = m[1]; u_max_x[u] = m[2]; u_min_y[u] = m[3]; u_max_y[u] = m[4]; u_size[u] = m[5];
+                u_last[u] = m[6]; u_ff[u] = m[7]; u_fl[u] = m[8];
+                u_crop_off[u] = carry + (unsigned long long)ex;
+            }
+            act[i] = u;
+            tmp_off[i] = carry + (unsigned long long)ex;
+        }
+        carry += (unsigned long long)tot;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < (int)min(carry, (unsigned long long)0x7fffffff); i += blockDim.x) arena[i] = crops[i];
+}
+
+// ================================================================================================
+// Host side: C ABI
+// ================================================================================================
+static inline cudaStream_t S(void* s) { return (cudaStream_t)s; }
+static size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
+
+extern "C" int am_version(void) { return 100; }
+extern "C" int am_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+extern "C" int am_words_per_row(int width) { return am_words_per_row_impl(width); }
+
+extern "C" int am_pack_mask_u8(const uint8_t* d_mask, int width, int height, int batch, uint32_t* d_bits, void* stream) {
+    if (!d_mask || !d_bits || width <= 0 || height <= 0 || batch <= 0) return AM_ERR_ARG;
+    int WPR = am_words_per_row_impl(width);
+    dim3 grid(am_div_up((long long)WPR * 32, 256), height, batch);
+    k_pack_u8<<<grid, 256, 0, S(stream)>>>(d_mask, width, height, WPR, d_bits);
+    AM_CUDA(cudaGetLastError());
+    return AM_OK;
+}
+extern "C" int am_unpack_mask_u8(const uint32_t* d_bits, int width, int height, int batch, uint8_t* d_mask, void* stream) {
+    if (!d_mask || !d_bits || width <= 0 || height <= 0 || batch <= 0) return AM_ERR_ARG;
+    dim3 grid(am_div_up(width, 256), height, batch);
+    k_unpack_u8<<<grid, 256, 0, S(stream)>>>(d_bits, width, height, am_words_per_row_impl(width), d_mask);
+    AM_CUDA(cudaGetLastError());
+    return AM_OK;
+}
+
+extern "C" am_cc_ctx* am_cc_create(int width, int height, int max_batch, int max_runs, int max_labels, int max_kept,
+                                   int crop_words, int min_pixels) {
+    if (width <= 0 || height <= 0 || width > 65535 || height > 32767 || max_batch <= 0) return nullptr;
+    am_cc_ctx* c = new am_cc_ctx();
+    c->W = width; c->H = height; c->WPR = am_words_per_row_impl(width); c->B = max_batch;
+    long long P = (long long)width * height;
+    c->MR = max_runs > 0 ? max_runs : (int)(P / 2 + 64);
+    c->ML = max_labels > 0 ? max_labels : c->MR;
+    if (c->ML > c->MR) c->ML = c->MR;
+    c->MK = max_kept > 0 ? max_kept : (int)(P / 20 + 64);      // a kept CC has >= min_pixels (20) pixels
+    if (c->MK > c->ML) c->MK = c->ML;
+    c->CW = crop_words > 0 ? crop_words : (int)(4 * (long long)c->WPR * height + 1024);
+    c->min_pixels = min_pixels;
+    size_t per = 0;
+    auto add = [&](size_t bytes) { size_t o = per; per += align_up(bytes); return o; };
+    size_t o_wp = add((size_t)height * c->WPR * 4), o_rb = add((size_t)(height + 1) * 4);
+    size_t o_par = add((size_t)c->MR * 4), o_yx = add((size_t)c->MR * 4), o_xe = add((size_t)c->MR * 4), o_rl = add((size_t)c->MR * 4);
+    size_t o_bc = add((size_t)(c->MR / 1024 + 2) * 4);
+    size_t o_t[5]; for (int i = 0; i < 5; ++i) o_t[i] = add((size_t)c->ML * 4);
+    size_t o_lco = add((size_t)c->ML * 4);
+    size_t o_kl = add((size_t)c->MK * 4), o_kco = add((size_t)c->MK * 4), o_mu = add((size_t)c->MK * 4);
+    size_t o_cr = add((size_t)c->CW * 4);
+    size_t head = align_up(sizeof(CcFrame) * max_batch) + align_up((size_t)max_batch * 16) + 256;
+    size_t total = head + per * max_batch;
+    if (cudaMalloc(&c->slab, total) != cudaSuccess) {
+        fprintf(stderr, "[accessmath_b200] am_cc_create: cudaMalloc(%zu) failed\n", total);
+        delete c; return nullptr;
+    }
+    char* base = (char*)c->slab;
+    c->d_frames = (CcFrame*)base;
+    c->d_counts = (int*)(base + align_up(sizeof(CcFrame) * max_batch));
+    c->d_status = (int*)(base + align_up(sizeof(CcFrame) * max_batch) + align_up((size_t)max_batch * 16));
+    c->h_frames = new CcFrame[max_batch];
+    for (int f = 0; f < max_batch; ++f) {
+        char* p = base + head + per * f;
+        CcFrame& fr = c->h_frames[f];
+        fr.wprefix = (uint32_t*)(p + o_wp); fr.rowbase = (int*)(p + o_rb); fr.run_parent = (int*)(p + o_par);
+        fr.run_yx = (int*)(p + o_yx); fr.run_xe = (int*)(p + o_xe); fr.run_label = (int*)(p + o_rl); fr.blockcnt = (int*)(p + o_bc);
+        fr.t_min_y = (int*)(p + o_t[0]); fr.t_max_y = (int*)(p + o_t[1]); fr.t_min_x = (int*)(p + o_t[2]);
+        fr.t_max_x = (int*)(p + o_t[3]); fr.t_count = (int*)(p + o_t[4]); fr.lab_crop_off = (uint32_t*)(p + o_lco);
+        fr.kept_label = (int*)(p + o_kl); fr.kept_crop_off = (uint32_t*)(p + o_kco); fr.match_unique = (int*)(p + o_mu);
+        fr.crops = (uint32_t*)(p + o_cr);
+    }
+    cudaMemcpy(c->d_frames, c->h_frames, sizeof(CcFrame) * max_batch, cudaMemcpyHostToDevice);
+    cudaMemset(c->d_counts, 0, (size_t)max_batch * 16);
+    cudaMemset(c->d_status, 0, 4);
+    cudaMallocHost(&c->h_counts, (size_t)max_batch * 16 + 16);
+    return c;
+}
+extern "C" void am_cc_destroy(am_cc_ctx* c) {
+    if (!c) return;
+    cudaFree(c->slab); cudaFreeHost(c->h_counts); delete[] c->h_frames; delete c;
+}
+
+extern "C" int am_cc_label_batch(am_cc_ctx* c, const uint32_t* d_bits, int batch, int32_t* d_labels, void* stream) {
+    if (!c || !d_bits || batch <= 0 || batch > c->B) return AM_ERR_ARG;
+    cudaStream_t st = S(stream);
+    const int H = c->H, W = c->W, WPR = c->WPR;
+    k_row_scan<<<dim3(am_div_up(H, 4), batch), 128, 0, st>>>(d_bits, c->d_frames, H, WPR);
+    k_row_base<<<batch, 1024, 0, st>>>(c->d_frames, H, c->MR, c->d_counts, c->d_status);
+    dim3 gw(am_div_up(WPR, 64), H, batch);
+    k_run_init<<<gw, 64, 0, st>>>(d_bits, c->d_frames, H, WPR, c->MR);
+    if (H > 1) k_run_merge<<<dim3(gw.x, H - 1, batch), 64, 0, st>>>(d_bits, c->d_frames, H, WPR, c->MR);
+    // run-level kernels: grid sized for the capacity; blocks beyond n_runs exit immediately
+    long long P = (long long)W * H;
+    int run_blocks = am_div_up(c->MR < P / 2 + 64 ? c->MR : P / 2 + 64, 1024);
+    k_run_flatten<<<dim3(run_blocks, batch), 1024, 0, st>>>(c->d_frames, c->d_counts, c->MR);
+    k_block_base<<<batch, 1024, 0, st>>>(c->d_frames, c->d_counts, c->MR, c->ML, c->d_status);
+    k_root_label<<<dim3(run_blocks, batch), 1024, 0, st>>>(c->d_frames, c->d_counts, c->MR, c->ML, W, H);
+    k_run_stats<<<dim3(run_blocks, batch), 1024, 0, st>>>(c->d_frames, c->d_counts, c->MR, c->ML);
+    k_kept_scan<<<batch, 1024, 0, st>>>(c->d_frames, c->d_counts, c->ML, c->MK, c->CW, c->min_pixels, c->d_status);
+    k_crop_clear<<<dim3(64, batch), 256, 0, st>>>(c->d_frames, c->d_counts);
+    k_crop_fill<<<dim3(run_blocks * 4, batch), 256, 0, st>>>(c->d_frames, c->d_counts, c->MR);
+    k_init_match<<<dim3(8, batch), 256, 0, st>>>(c->d_frames, c->MK);
+    if (d_labels) k_label_image<<<dim3(am_div_up(W, 256), H, batch), 256, 0, st>>>(d_bits, c->d_frames, W, H, WPR, c->MR, d_labels);
+    AM_CUDA(cudaGetLastError());
+    return AM_OK;
+}
+
+extern "C" int am_cc_counts(am_cc_ctx* c, int batch, int* h_counts, void* stream) {
+    if (!c || !h_counts || batch <= 0 || batch > c->B) return AM_ERR_ARG;
+    AM_CUDA(cudaMemcpyAsync(c->h_counts, c->d_counts, (size_t)batch * 16, cudaMemcpyDeviceToHost, S(stream)));
+    AM_CUDA(cudaMemcpyAsync(c->h_counts + batch * 4, c->d_status, 4, cudaMemcpyDeviceToHost, S(stream)));
+    AM_CUDA(cudaStreamSynchronize(S(stream)));
+    memcpy(h_counts, c->h_counts, (size_t)batch * 16);
+    if (c->h_counts[batch * 4] != 0) {
+        fprintf(stderr, "[accessmath_b200] CC capacity exceeded (flags 0x%x: 1=runs 2=labels 4=kept/crops)\n", c->h_counts[batch * 4]);
+        return AM_ERR_CAPACITY;
+    }
+    return AM_OK;
+}
+
+extern "C" int am_cc_read_label_table(am_cc_ctx* c, int frame, int n, int* h_min_y, int* h_max_y, int* h_min_x, int* h_max_x,
+                                      int* h_count, void* stream) {
+    if (!c || frame < 0 || frame >= c->B || n < 0 || n > c->ML) return AM_ERR_ARG;
+    const CcFrame& fr = c->h_frames[frame];
+    size_t b = (size_t)n * 4;
+    if (n) {
+        AM_CUDA(cudaMemcpyAsync(h_min_y, fr.t_min_y, b, cudaMemcpyDeviceToHost, S(stream)));
+        AM_CUDA(cudaMemcpyAsync(h_max_y, fr.t_max_y, b, cudaMemcpyDeviceToHost, S(stream)));
+        AM_CUDA(cudaMemcpyAsync(h_min_x, fr.t_min_x, b, cudaMemcpyDeviceToHost, S(stream)));
+        AM_CUDA(cudaMemcpyAsync(h_max_x, fr.t_max_x, b, cudaMemcpyDeviceToHost, S(stream)));
+        AM_CUDA(cudaMemcpyAsync(h_count, fr.t_count, b, cudaMemcpyDeviceToHost, S(stream)));
+    }
+    AM_CUDA(cudaStreamSynchronize(S(stream)));
+    return AM_OK;
+}
+
+extern "C" int am_cc_read_kept(am_cc_ctx* c, int frame, int n_kept, int* h_rows, void* stream) {
+    if (!c || frame < 0 || frame >= c->B || n_kept < 0 || n_kept > c->MK) return AM_ERR_ARG;
+    if (n_kept == 0) return AM_OK;
+    int* d_rows = nullptr;
+    AM_CUDA(cudaMallocAsync(&d_rows, (size_t)n_kept * 32, S(stream)));
+    k_rows_one<<<am_div_up(n_kept, 256), 256, 0, S(stream)>>>(c->d_frames, frame, n_kept, d_rows);
+    AM_CUDA(cudaMemcpyAsync(h_rows, d_rows, (size_t)n_kept * 32, cudaMemcpyDeviceToHost, S(stream)));
+    AM_CUDA(cudaFreeAsync(d_rows, S(stream)));
+    AM_CUDA(cudaStreamSynchronize(S(stream)));
+    return AM_OK;
+}
+
+extern "C" int am_cc_read_crops(am_cc_ctx* c, int frame, int crop_words, uint32_t* h_crops, void* stream) {
+    if (!c || frame < 0 || frame >= c->B || crop_words < 0 || crop_words > c->CW) return AM_ERR_ARG;
+    if (crop_words) AM_CUDA(cudaMemcpyAsync(h_crops, c->h_frames[frame].crops, (size_t)crop_words * 4, cudaMemcpyDeviceToHost, S(stream)));
+    AM_CUDA(cudaStreamSynchronize(S(stream)));
+    return AM_OK;
+}
+
+extern "C" int am_cc_pack_rows(am_cc_ctx* c, int batch, int* d_rows, int row_capacity, int* d_row_offsets, void* stream) {
+    if (!c || !d_rows || !d_row_offsets || batch <= 0 || batch > c->B) return AM_ERR_ARG;
+    k_row_offsets<<<1, 32, 0, S(stream)>>>(c->d_counts, batch, d_row_offsets);
+    k_rows_all<<<dim3(am_div_up(c->MK, 256), batch), 256, 0, S(stream)>>>(c->d_frames, c->d_counts, d_row_offsets, row_capacity, d_rows);
+    AM_CUDA(cudaGetLastError());
+    return AM_OK;
+}
+
+// ---- legacy host-pointer operator -----------------------------------------------------------
+extern "C" int CC_AgeBoundaries(int* labels, float* ages, int width, int height, int count_labels, int* out_mins_y,
+                                int* out_maxs_y, int* out_mins_x, int* out_maxs_x, int* out_counts, float* output_age) {
+    if (count_labels <= 0) return 0;
+    if (!labels || width <= 0 || height <= 0) return AM_ERR_ARG;
+    size_t P = (size_t)width * height, n = (size_t)count_labels;
+    int32_t* d_lab = nullptr; float* d_age = nullptr; int* d_tab = nullptr;
+    AM_CUDA(cudaMalloc(&d_lab, P * 4));
+    if (ages) AM_CUDA(cudaMalloc(&d_age, P * 4));
+    AM_CUDA(cudaMalloc(&d_tab, n * 4 * 7));
+    int *mny = d_tab, *mxy = d_tab + n, *mnx = d_tab + 2 * n, *mxx = d_tab + 3 * n, *cnt = d_tab + 4 * n;
+    unsigned* agek = (unsigned*)(d_tab + 5 * n); float* oage = (float*)(d_tab + 6 * n);
+    AM_CUDA(cudaMemcpy(d_lab, labels, P * 4, cudaMemcpyHostToDevice));
+    if (ages) AM_CUDA(cudaMemcpy(d_age, ages, P * 4, cudaMemcpyHostToDevice));
+    k_ageb_init<<<am_div_up(count_labels, 256), 256>>>(count_labels, width, height, mny, mxy, mnx, mxx, cnt, agek);
+    k_ageb_scan<<<dim3(am_div_up(width, 256), height), 256>>>(d_lab, d_age, width, height, count_labels, mny, mxy, mnx, mxx, cnt, agek);
+    k_ageb_finish<<<am_div_up(count_labels, 256), 256>>>(count_labels, cnt, agek, oage);
+    AM_CUDA(cudaGetLastError());
+    AM_CUDA(cudaMemcpy(out_mins_y, mny, n * 4, cudaMemcpyDeviceToHost));
+    AM_CUDA(cudaMemcpy(out_maxs_y, mxy, n * 4, cudaMemcpyDeviceToHost));
+    AM_CUDA(cudaMemcpy(out_mins_x, mnx, n * 4, cudaMemcpyDeviceToHost));
+    AM_CUDA(cudaMemcpy(out_maxs_x, mxx, n * 4, cudaMemcpyDeviceToHost));
+    AM_CUDA(cudaMemcpy(out_counts, cnt, n * 4, cudaMemcpyDeviceToHost));
+    AM_CUDA(cudaMemcpy(output_age, oage, n * 4, cudaMemcpyDeviceToHost));
+    cudaFree(d_lab); cudaFree(d_age); cudaFree(d_tab);
+    return 0;
+}
+
+// ---- estimator ------------------------------------------------------------------------------
+extern "C" am_estimator* am_est_create(int width, int height, double min_recall, double min_precision, int max_gap,
+                                       int max_uniques, int max_active, long long arena_words) {
+    if (width <= 0 || height <= 0) return nullptr;
+    am_estimator* e = new am_estimator();
+    e->W = width; e->H = height; e->max_gap = max_gap; e->min_recall = min_recall; e->min_precision = min_precision;
+    e->MU = max_uniques > 0 ? max_uniques : (1 << 20);
+    e->MA = max_active > 0 ? max_active : (1 << 18);
+    if (e->MA > e->MU) e->MA = e->MU;
+    unsigned long long aw = arena_words > 0 ? (unsigned long long)arena_words : (64ull << 20);
+    size_t tot = 0;
+    auto add = [&](size_t bytes) { size_t o = tot; tot += align_up(bytes); return o; };
+    size_t o_i[8]; for (int i = 0; i < 8; ++i) o_i[i] = add((size_t)e->MU * 4);
+    size_t o_off = add((size_t)e->MU * 8);
+    size_t o_a0 = add((size_t)e->MA * 4), o_a1 = add((size_t)e->MA * 4);
+    size_t o_tmp = add((size_t)e->MA * 8);
+    size_t o_sc = add(64), o_sc64 = add(64);
+    size_t o_ar = add((size_t)aw * 4);
+    if (cudaMalloc(&e->slab, tot) != cudaSuccess) {
+        fprintf(stderr, "[accessmath_b200] am_est_create: cudaMalloc(%zu) failed\n", tot);
+        delete e; return nullptr;
+    }
+    char* b = (char*)e->slab;
+    e->u_min_x = (int*)(b + o_i[0]); e->u_max_x = (int*)(b + o_i[1]); e->u_min_y = (int*)(b + o_i[2]); e->u_max_y = (int*)(b + o_i[3]);
+    e->u_size = (int*)(b + o_i[4]); e->u_last = (int*)(b + o_i[5]); e->u_first_frame = (int*)(b + o_i[6]); e->u_first_label = (int*)(b + o_i[7]);
+    e->u_crop_off = (unsigned long long*)(b + o_off);
+    e->act[0] = (int*)(b + o_a0); e->act[1] = (int*)(b + o_a1); e->cur = 0;
+    e->d_scal = (int*)(b + o_sc); e->d_scal64 = (unsigned long long*)(b + o_sc64);
+    e->arena = (uint32_t*)(b + o_ar);
+    e->AW = aw; e->tmp_off = (unsigned long long*)(b + o_tmp);
+    cudaMemset(e->d_scal, 0, 64); cudaMemset(e->d_scal64, 0, 64);
+    cudaMallocHost(&e->h_scal, 64); cudaMallocHost(&e->h_scal64, 64);
+    return e;
+}
+extern "C" void am_est_destroy(am_estimator* e) {
+    if (!e) return;
+    cudaFree(e->slab); cudaFreeHost(e->h_scal); cudaFreeHost(e->h_scal64); delete e;
+}
+static inline unsigned long long* est_tmp(am_estimator* e) { return e->tmp_off; }
+
+extern "C" int am_est_add_frames(am_estimator* e, am_cc_ctx* c, int first, int n, void* stream) {
+    if (!e || !c || first < 0 || n <= 0 || first + n > c->B) return AM_ERR_ARG;
+    cudaStream_t st = S(stream);
+    for (int f = first; f < first + n; ++f) {
+        int* a_in = e->act[e->cur]; int* a_out = e->act[e->cur ^ 1];
+        k_match<<<am_div_up(c->MK, 8), 256, 0, st>>>(c->d_frames, c->d_counts, f, a_in, e->d_scal, e->u_min_x, e->u_max_x, e->u_min_y,
+                                                   e->u_max_y, e->u_size, e->u_last, e->u_crop_off, e->arena, e->min_recall,
+                                                   e->min_precision, e->d_scal64);
+        k_match_update<<<1, 1024, 0, st>>>(c->d_frames, c->d_counts, f, a_in, a_out, e->d_scal, e->d_scal64, e->u_min_x, e->u_max_x,
+                                           e->u_min_y, e->u_max_y, e->u_size, e->u_last, e->u_first_frame, e->u_first_label,
+                                           e->u_crop_off, e->arena, e->MU, e->MA, e->AW, e->max_gap);
+        e->cur ^= 1;
+    }
+    AM_CUDA(cudaGetLastError());
+    return AM_OK;
+}
+
+extern "C" int am_est_state(am_estimator* e, int* h_state, void* stream) {
+    if (!e || !h_state) return AM_ERR_ARG;
+    AM_CUDA(cudaMemcpyAsync(e->h_scal, e->d_scal, 16, cudaMemcpyDeviceToHost, S(stream)));
+    AM_CUDA(cudaMemcpyAsync(e->h_scal64, e->d_scal64, 16, cudaMemcpyDeviceToHost, S(stream)));
+    AM_CUDA(cudaStreamSynchronize(S(stream)));
+    h_state[0] = e->h_scal[0]; h_state[1] = e->h_scal[1]; h_state[2] = e->h_scal[2]; h_state[3] = e->h_scal[3];
+    h_state[4] = (int)(e->h_scal64[0] & 0xffffffffull); h_state[5] = (int)(e->h_scal64[0] >> 32);
+    if (e->h_scal[3]) {
+        fprintf(stderr, "[accessmath_b200] estimator capacity exceeded (uniques/active/arena)\n");
+        return AM_ERR_CAPACITY;
+    }
+    return AM_OK;
+}
+
+__global__ void k_uniq_rows(int first, int n, const int* ff, const int* fl, const int* mnx, const int* mxx, const int* mny,
+                            const int* mxy, const int* sz, const int* last, int* rows) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int u = first + i; int* r = rows + (size_t)i * 8;
+    r[0] = ff[u]; r[1] = fl[u]; r[2] = mnx[u]; r[3] = mxx[u]; r[4] = mny[u]; r[5] = mxy[u]; r[6] = sz[u]; r[7] = last[u];
+}
+extern "C" int am_est_read_uniques(am_estimator* e, int first, int n, int* h_rows, void* stream) {
+    if (!e || first < 0 || n < 0 || first + n > e->MU) return AM_ERR_ARG;
+    if (n == 0) return AM_OK;
+    int* d_rows = nullptr;
+    AM_CUDA(cudaMallocAsync(&d_rows, (size_t)n * 32, S(stream)));
+    k_uniq_rows<<<am_div_up(n, 256), 256, 0, S(stream)>>>(first, n, e->u_first_frame, e->u_first_label, e->u_min_x, e->u_max_x,
+                                                        e->u_min_y, e->u_max_y, e->u_size, e->u_last, d_rows);
+    AM_CUDA(cudaMemcpyAsync(h_rows, d_rows, (size_t)n * 32, cudaMemcpyDeviceToHost, S(stream)));
+    AM_CUDA(cudaFreeAsync(d_rows, S(stream)));
+    AM_CUDA(cudaStreamSynchronize(S(stream)));
+    return AM_OK;
+}
+extern "C" int am_est_read_unique_crop(am_estimator* e, int u, int words, uint32_t* h_crop, void* stream) {
+    if (!e || u < 0 || u >= e->MU || words < 0) return AM_ERR_ARG;
+    unsigned long long off = 0;
+    AM_CUDA(cudaMemcpyAsync(&off, e->u_crop_off + u, 8, cudaMemcpyDeviceToHost, S(stream)));
+    AM_CUDA(cudaStreamSynchronize(S(stream)));
+    if (words) AM_CUDA(cudaMemcpyAsync(h_crop, e->arena + off, (size_t)words * 4, cudaMemcpyDeviceToHost, S(stream)));
+    AM_CUDA(cudaStreamSynchronize(S(stream)));
+    return AM_OK;
+}
+
+extern "C" int am_est_export_sizes(am_estimator* e, long long* h_sizes, void* stream) {
+    if (!e || !h_sizes) return AM_ERR_ARG;
+    k_export_sizes<<<1, 1024, 0, S(stream)>>>(e->act[e->cur], e->d_scal, e->u_min_x, e->u_max_x, e->u_min_y, e->u_max_y, e->d_scal64 + 2);
+    AM_CUDA(cudaMemcpyAsync(e->h_scal64 + 2, e->d_scal64 + 2, 16, cudaMemcpyDeviceToHost, S(stream)));
+    AM_CUDA(cudaStreamSynchronize(S(stream)));
+    h_sizes[0] = (long long)e->h_scal64[2]; h_sizes[1] = (long long)e->h_scal64[3];
+    return AM_OK;
+}
+extern "C" int am_est_export(am_estimator* e, int* d_meta, uint32_t* d_crops, void* stream) {
+    if (!e || !d_meta || !d_crops) return AM_ERR_ARG;
+    k_export<<<1, 1024, 0, S(stream)>>>(e->act[e->cur], e->d_scal, e->u_min_x, e->u_max_x, e->u_min_y, e->u_max_y, e->u_size, e->u_last,
+                                        e->u_first_frame, e->u_first_label, e->u_crop_off, e->arena, d_meta, d_crops, est_tmp(e));
+    AM_CUDA(cudaGetLastError());
+    return AM_OK;
+}
+extern "C" int am_est_import(am_estimator* e, int n_active, int n_unique, int img_idx, unsigned long long tempo_count,
+                             const int* d_meta, const uint32_t* d_crops, long long crop_words, void* stream) {
+    if (!e || n_active < 0 || n_active > e->MA || n_unique > e->MU || (unsigned long long)crop_words > e->AW) return AM_ERR_CAPACITY;
+    if (n_active > 0 && (!d_meta || !d_crops)) return AM_ERR_ARG;
+    if (n_active > 0)
+        k_import<<<1, 1024, 0, S(stream)>>>(n_active, d_meta, d_crops, e->act[e->cur], e->u_min_x, e->u_max_x, e->u_min_y, e->u_max_y,
+                                            e->u_size, e->u_last, e->u_first_frame, e->u_first_label, e->u_crop_off, e->arena, est_tmp(e), e->MU);
+    int sc[4] = {n_unique, n_active, img_idx, 0};
+    unsigned long long sc64[2] = {tempo_count, (unsigned long long)crop_words};
+    AM_CUDA(cudaMemcpyAsync(e->d_scal, sc, 16, cudaMemcpyHostToDevice, S(stream)));
+    AM_CUDA(cudaMemcpyAsync(e->d_scal64, sc64, 16, cudaMemcpyHostToDevice, S(stream)));
+    AM_CUDA(cudaStreamSynchronize(S(stream)));
+    return AM_OK;
+}
