@@ -87,6 +87,61 @@ int am_est_export(am_estimator* est, int* d_meta, uint32_t* d_crops, void* strea
 int am_est_import(am_estimator* est, int n_active, int n_unique, int img_idx, unsigned long long tempo_count,
                   const int* d_meta, const uint32_t* d_crops, long long crop_words, void* stream);
 
+/* ===== 6. FCN-LectureNet binarizer (tcgen05 implicit GEMM) ===================================
+ * Replaces the PyTorch arithmetic of FCN_LectureNet.forward / binarize
+ * (R/AccessMath/lecturenet_v1/FCN_lecturenet.py:260-323, 364-403, 430-467) and the frame pre/post
+ * processing of FCN_LectureNet_Binarizer.handleFrame (R/AccessMath/preprocessing/video_worker/
+ * FCN_lecturenet_binarizer.py:47-54).  Activations are NHWC bf16 with physical zero padding in x:
+ * buf[n][y][xp][c], xp in [0, W + 2*pad).  See DESIGN.md for the GEMM formulation. */
+typedef struct am_conv_seg {       /* one K segment = one input tensor of a (concatenated) convolution */
+    const void* ptr;               /* bf16 activation buffer */
+    int C;                         /* channels per pixel in the buffer (multiple of 8) */
+    int Wp;                        /* padded row length in pixels */
+    int Hbuf;                      /* rows per frame in the buffer */
+    int x_off;                     /* buffer pad - conv pad (pixels) */
+    int rowrun;                    /* 1: row-run mode (overlapping rows, S-packing); 0: one load per horizontal tap */
+    int S;                         /* output pixels packed per GEMM row (row-run mode) */
+    int run_len;                   /* (KW + S - 1) * C   (row-run mode) */
+    int KW;                        /* horizontal taps */
+} am_conv_seg;
+
+typedef struct am_conv_desc {
+    int nseg;
+    am_conv_seg seg[2];
+    const void* weights;           /* packed bf16 [chunks*KH*Ntot_pad][64] (fcn_lecturenet.pack_weights) */
+    const float* bias;             /* fp32 [Ntot_pad], BatchNorm folded */
+    int KH, padY;
+    int RT, YT;                    /* tile: RT groups x YT rows = 128 GEMM rows, RT % 8 == 0 */
+    int nR, Hin, batch;            /* GEMM rows per image row, image rows, frames */
+    int NT, Ntot, Ntot_pad;        /* UMMA N per CTA, valid N, padded N (multiple of NT) */
+    void* out; int out_f32;        /* destination (bf16 or fp32), NHWC */
+    int out_H, out_W;
+    long long out_sn, out_sy;      /* element strides: frame, row */
+    int out_sx, out_padx, out_coff;/* pixel stride (channels), left pad (pixels), channel offset */
+    int Cout, Sy, Sx;              /* GEMM column n = ((sy*Sx)+sx)*Cout + co  ->  pixel (Sy*y+sy, Sx*r+sx), channel co */
+    int act;                       /* 0 = none, 1 = exact-erf GELU */
+} am_conv_desc;
+
+int am_conv_gemm(const am_conv_desc* desc, void* stream);
+
+/* uint8 BGR frames [B][H][W][3] -> normalised bf16 RGB (x/255-0.5)/0.5 in buf[B][H][W+2*pad][C] (channels >= 3 zero).
+ * Replaces cv2.cvtColor + TF.to_tensor + TF.normalize (FCN_lecturenet_binarizer.py:50, FCN_lecturenet.py:607-618). */
+int am_fcn_prep_input(const uint8_t* d_bgr, int batch, int height, int width, void* d_out, int C, int pad, void* stream);
+/* MaxPool2d(2) (floor) on padded NHWC bf16 (FCN_lecturenet.py:264-276) */
+int am_fcn_maxpool2(const void* d_in, int batch, int height, int width, int C, int pad_in, void* d_out, int pad_out, void* stream);
+/* fill the rows/columns a k=2,s=2 transposed conv with output_padding leaves untouched (they equal act(bias)):
+ * pixels with y >= y_from or x >= x_from of buf[B][H][W+2*pad][C] get values[c] (bf16[C]) */
+int am_fcn_fill_border(void* d_buf, int batch, int height, int width, int C, int pad, int y_from, int x_from,
+                       const void* d_values, void* stream);
+/* heads: d_heads fp32 [B][H][W][4] = (text logit, rec pre-tanh x3) + the uint8 BGR frame ->
+ *   diff = (x0 - tanh(rec)) * sigmoid(text)  (FCN_lecturenet.py:370-377) into bf16 buf[B][H][W+2*pad][C];
+ *   optional d_text_logit fp32 [B][H][W], d_rec fp32 [B][H][W][3] (RGB, tanh applied) */
+int am_fcn_heads_post(const float* d_heads, const uint8_t* d_bgr, int batch, int height, int width, void* d_diff, int C,
+                      int pad, float* d_text_logit, float* d_rec, void* stream);
+/* final logits fp32 [B][H][W] -> bit-packed INK mask: ink <=> (uint8)(sigmoid(z)*255) < threshold
+ * (FCN_lecturenet.py:452-467 followed by `255 - binary`, FCN_lecturenet_binarizer.py:54) */
+int am_fcn_threshold_pack(const float* d_logits, int batch, int height, int width, int threshold, uint32_t* d_bits, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

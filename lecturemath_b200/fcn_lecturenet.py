@@ -1,0 +1,519 @@
+"""FCN_LectureNet drop-in (R/AccessMath/lecturenet_v1/FCN_lecturenet.py) whose inference runs on hand-written
+sm_100a kernels (csrc/fcn_conv.cu: TMA + tcgen05 implicit GEMM; csrc/fcn_misc.cu: glue) through the C ABI.
+
+Kept from the reference's surface: FCN_LectureNet.CreateFromConfig(config, in_channels, reconstruction_mode)
+(:620-659), state_dict()/load_state_dict() with the reference's parameter names (weight interchange format),
+eval(), cuda(), forward(x) -> (logit, text_logit, rec) (:364-403), binarize(PIL_image, return_others, force_binary,
+binary_treshold, apply_sigmoid) (:430-505), prepare_image (:607-618).
+
+The torch.nn modules below are parameter CONTAINERS only (same construction order as the reference, so the same
+seed yields the same random-init weights); no torch op runs in forward/binarize."""
+import ctypes
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+BN_EPS = 1e-5
+
+
+# ----------------------------------------------------------------------------------------------------
+# parameter container with the reference's names
+def _block(cin, cout, k, act):
+    layers = [nn.Conv2d(cin, cout, stride=1, kernel_size=k, padding=(k - 1) // 2), nn.BatchNorm2d(cout)]
+    if act == "gelu":
+        layers.append(nn.GELU())
+    elif act == "tanh":
+        layers.append(nn.Tanh())
+    seq = nn.Sequential(*layers)
+    nn.init.xavier_normal_(seq[0].weight)
+    return seq
+
+
+class _Params(nn.Module):
+    """Builds parameters in the order FCN_LectureNet.__init__ does (:17-162) so seeds reproduce its init."""
+
+    def __init__(self, ch, down, mid, ups, upc, k, pm1, pm2, pk):
+        super().__init__()
+        cin = ch
+        for i, c in enumerate(down, 1):
+            setattr(self, "conv_down_block_%d" % i, _block(cin, c, k, "gelu"))
+            cin = c
+        self.mid_block = _block(down[4], mid, k, "gelu")
+        cin = mid
+        for lvl in range(5, 0, -1):
+            t = nn.ConvTranspose2d(cin, ups[lvl - 1], 2, padding=0, stride=2)
+            setattr(self, "transposed_conv_%d" % lvl, t)
+            setattr(self, "upsample_block_%d" % lvl, nn.Sequential(nn.BatchNorm2d(ups[lvl - 1]), nn.GELU()))
+            nn.init.xavier_normal_(t.weight)
+            setattr(self, "conv_up_block_%d" % lvl, _block(ups[lvl - 1] + down[lvl - 1], upc[lvl - 1], k, "gelu"))
+            cin = upc[lvl - 1]
+        # set_main_branches (:164-201): pixel branch then text-mask branch, kernel = pixel kernel size
+        self.conv_pixels_1 = _block(ch + upc[0], pm1, pk, "gelu")
+        self.conv_pixels_2 = _block(ch + pm1, pm2, pk, "gelu")
+        self.conv_out = _block(ch + pm2, 1, pk, None)
+        self.conv_text_mask_out = _block(upc[0], 1, pk, None)
+        self.conv_reconstruct = _block(upc[0], 3, k, "tanh")
+
+
+# ----------------------------------------------------------------------------------------------------
+# ctypes mirrors of include/accessmath_b200.h
+class ConvSeg(ctypes.Structure):
+    _fields_ = [("ptr", ctypes.c_void_p), ("C", ctypes.c_int), ("Wp", ctypes.c_int), ("Hbuf", ctypes.c_int), ("x_off", ctypes.c_int),
+                ("rowrun", ctypes.c_int), ("S", ctypes.c_int), ("run_len", ctypes.c_int), ("KW", ctypes.c_int)]
+
+
+class ConvDesc(ctypes.Structure):
+    _fields_ = [("nseg", ctypes.c_int), ("seg", ConvSeg * 2), ("weights", ctypes.c_void_p), ("bias", ctypes.c_void_p),
+                ("KH", ctypes.c_int), ("padY", ctypes.c_int), ("RT", ctypes.c_int), ("YT", ctypes.c_int),
+                ("nR", ctypes.c_int), ("Hin", ctypes.c_int), ("batch", ctypes.c_int),
+                ("NT", ctypes.c_int), ("Ntot", ctypes.c_int), ("Ntot_pad", ctypes.c_int),
+                ("out", ctypes.c_void_p), ("out_f32", ctypes.c_int), ("out_H", ctypes.c_int), ("out_W", ctypes.c_int),
+                ("out_sn", ctypes.c_longlong), ("out_sy", ctypes.c_longlong),
+                ("out_sx", ctypes.c_int), ("out_padx", ctypes.c_int), ("out_coff", ctypes.c_int),
+                ("Cout", ctypes.c_int), ("Sy", ctypes.c_int), ("Sx", ctypes.c_int), ("act", ctypes.c_int)]
+
+
+def fold_bn(w, b, bn_w, bn_b, mean, var, out_dim=0):
+    """Conv + eval BatchNorm -> conv:  w' = w*g/sqrt(v+eps), b' = (b-mu)*g/sqrt(v+eps)+beta  (SURVEY appendix A)."""
+    scale = bn_w.double() / torch.sqrt(var.double() + BN_EPS)
+    shape = [1] * w.dim()
+    shape[out_dim] = -1
+    return (w.double() * scale.view(shape)).float(), ((b.double() - mean.double()) * scale + bn_b.double()).float()
+
+
+def choose_nt(ntot):
+    if ntot <= 256:
+        return ((ntot + 15) // 16) * 16
+    best = None
+    for nt in (256, 192, 128):
+        pad = ((ntot + nt - 1) // nt) * nt
+        if best is None or pad < best[1]:
+            best = (nt, pad)
+    return best[0]
+
+
+def choose_tile(nr, h, kh):
+    best = None
+    for rt, yt in ((8, 16), (16, 8), (32, 4), (64, 2), (128, 1)):
+        area = math.ceil(nr / rt) * rt * math.ceil(h / yt) * yt
+        score = area * (1.0 + 0.25 * (kh - 1) / yt)
+        if best is None or score < best[0]:
+            best = (score, rt, yt)
+    return best[1], best[2]
+
+
+def pack_weights(w, bias, segs, S, rowrun, NT):
+    """Re-pack a folded filter for the row-run implicit GEMM (csrc/fcn_conv.cu header comment).
+
+    w    : fp32 [Nrows][Cin][KH][KW]  (Nrows = Cout, or 4*Cout for the transposed conv's (sy,sx,co))
+    segs : list of (C_buf, index tensor mapping buffer channel -> w input channel, -1 = zero padding)
+    ->   bf16 [chunks*KH*Ntot_pad][64], fp32 bias [Ntot_pad], Ntot, Ntot_pad
+    """
+    nrows, _, KH, KW = w.shape
+    ntot = S * nrows
+    ntot_pad = ((ntot + NT - 1) // NT) * NT
+    blocks = []
+    for C, cmap in segs:
+        cmap = torch.as_tensor(cmap, dtype=torch.long)
+        wseg = torch.zeros((nrows, C, KH, KW), dtype=torch.float32)
+        valid = cmap >= 0
+        wseg[:, valid] = w[:, cmap[valid]]
+        if rowrun:
+            J = KW + S - 1
+            run = torch.zeros((S, nrows, KH, J, C), dtype=torch.float32)
+            for sx in range(S):
+                run[sx, :, :, sx:sx + KW, :] = wseg.permute(0, 2, 3, 1)          # [co][dy][tap][c]
+            K = J * C
+            mat = run.permute(2, 0, 1, 3, 4).reshape(KH, ntot, K)                # [dy][n=(sx,co)][k=(j,c)]
+            nck = (K + 63) // 64
+            full = torch.zeros((KH, ntot_pad, nck * 64), dtype=torch.float32)
+            full[:, :ntot, :K] = mat
+            blocks.append(full.view(KH, ntot_pad, nck, 64).permute(2, 0, 1, 3))  # [ck][dy][n][64]
+        else:
+            assert S == 1
+            nck = (C + 63) // 64
+            full = torch.zeros((KW, KH, ntot_pad, nck * 64), dtype=torch.float32)
+            full[:, :, :ntot, :C] = wseg.permute(3, 2, 0, 1)                     # [kx][dy][co][c]
+            blocks.append(full.view(KW, KH, ntot_pad, nck, 64).permute(0, 3, 1, 2, 4).reshape(KW * nck, KH, ntot_pad, 64))
+    packed = torch.cat(blocks, 0).reshape(-1, 64).to(torch.bfloat16).contiguous()
+    b = torch.zeros(ntot_pad, dtype=torch.float32)
+    b[:ntot] = bias.repeat(S)
+    return packed, b, ntot, ntot_pad
+
+
+class _Buf:
+    """NHWC bf16 activation buffer with physical zero padding in x."""
+
+    def __init__(self, B, H, W, C, pad, device, dtype=torch.bfloat16):
+        self.B, self.H, self.W, self.C, self.pad = B, H, W, C, pad
+        self.Wp = W + 2 * pad
+        n = B * H * self.Wp * C
+        self.t = torch.zeros(n + 256, dtype=dtype, device=device)      # slack: TMA boxes never leave the allocation
+        self.ptr = self.t.data_ptr()
+
+    def view(self):
+        return self.t[:self.B * self.H * self.Wp * self.C].view(self.B, self.H, self.Wp, self.C)[:, :, self.pad:self.pad + self.W]
+
+
+class FCNPlan:
+    """All device buffers, packed weights and kernel descriptors for one (batch, H, W)."""
+
+    def __init__(self, net, B, H, W, device, rowrun=True):
+        self.lib = _lib.load()          # building a plan needs no device; run() does (and fails loudly without one)
+        self.B, self.H, self.W, self.device, self.rowrun = B, H, W, device, rowrun
+        sd = {k: v.detach().float().cpu() for k, v in net.state_dict().items()}
+        k = sd["conv_down_block_1.0.weight"].shape[-1]
+        pk = sd["conv_pixels_1.0.weight"].shape[-1]
+        p3, p7 = (k - 1) // 2, (pk - 1) // 2
+        down = [sd["conv_down_block_%d.0.weight" % i].shape[0] for i in range(1, 6)]
+        mid = sd["mid_block.0.weight"].shape[0]
+        ups = [sd["transposed_conv_%d.weight" % i].shape[1] for i in range(1, 6)]
+        upc = [sd["conv_up_block_%d.0.weight" % i].shape[0] for i in range(1, 6)]
+        pm1, pm2 = sd["conv_pixels_1.0.weight"].shape[0], sd["conv_pixels_2.0.weight"].shape[0]
+        for c in down + [mid] + ups + upc + [pm1, pm2]:
+            if c % 8:
+                raise ValueError("channel widths must be multiples of 8 for the NHWC bf16 kernels (got %d)" % c)
+        hs, ws = [H], [W]
+        for _ in range(5):
+            hs.append(hs[-1] // 2); ws.append(ws[-1] // 2)
+        if hs[5] < 1 or ws[5] < 1:
+            raise ValueError("image too small for five pooling levels")
+        mk = lambda lvl, C, pad: _Buf(B, hs[lvl], ws[lvl], C, pad, device)
+        self.frames = torch.zeros((B, H, W, 3), dtype=torch.uint8, device=device)
+        self.x0 = mk(0, 8, p3)
+        self.d = [mk(i, down[i], p3) for i in range(5)]                  # conv_down outputs (skip connections)
+        self.p = [mk(i + 1, down[i], p3) for i in range(5)]              # pooled
+        self.mid = mk(5, mid, 0)
+        self.t = [mk(i, ups[i], p3) for i in range(5)]                   # transposed-conv outputs (level i)
+        self.u = [mk(i, upc[i], 0 if i > 0 else p7) for i in range(5)]   # conv_up outputs; u[0] = x_up1
+        self.heads = torch.zeros((B, H, W, 4), dtype=torch.float32, device=device)
+        self.diff = mk(0, 8, p7)
+        self.px1, self.px2 = mk(0, pm1, p7), mk(0, pm2, p7)
+        self.logits = torch.zeros((B, H, W), dtype=torch.float32, device=device)
+        self.text_logit = torch.zeros((B, H, W), dtype=torch.float32, device=device)
+        self.rec = torch.zeros((B, H, W, 3), dtype=torch.float32, device=device)
+        self.wpr = self.lib.am_words_per_row(W)
+        self.bits = torch.zeros((B, H, self.wpr), dtype=torch.int32, device=device)
+        self.keep = []          # keeps packed weights alive
+        self.ops = []           # (kind, payload)
+        self.flops = 0
+
+        def cbn(name):
+            return fold_bn(sd[name + ".0.weight"], sd[name + ".0.bias"], sd[name + ".1.weight"], sd[name + ".1.bias"],
+                           sd[name + ".1.running_mean"], sd[name + ".1.running_var"])
+
+        ident = lambda c: list(range(c))
+        # encoder
+        src = self.x0
+        for i in range(5):
+            w, b = cbn("conv_down_block_%d" % (i + 1))
+            cmap = [0, 1, 2] + [-1] * 5 if i == 0 else ident(src.C)
+            self._conv(w, b, [(src, cmap)], self.d[i], act=1, S=self._pick_s(ws[i], w.shape[0], src.C))
+            self.ops.append(("pool", (self.d[i], self.p[i])))
+            src = self.p[i]
+        w, b = cbn("mid_block")
+        self._conv(w, b, [(src, ident(src.C))], self.mid, act=1, S=1)
+        # decoder
+        src = self.mid
+        for lvl in range(4, -1, -1):
+            name = "transposed_conv_%d" % (lvl + 1)
+            bn = "upsample_block_%d.0" % (lvl + 1)
+            wt, bt = fold_bn(sd[name + ".weight"], sd[name + ".bias"], sd[bn + ".weight"], sd[bn + ".bias"],
+                             sd[bn + ".running_mean"], sd[bn + ".running_var"], out_dim=1)
+            self._tconv(wt, bt, src, self.t[lvl])
+            w, b = cbn("conv_up_block_%d" % (lvl + 1))
+            cu = self.t[lvl].C
+            self._conv(w, b, [(self.t[lvl], ident(cu)), (self.d[lvl], [cu + c for c in range(self.d[lvl].C)])], self.u[lvl], act=1,
+                       S=self._pick_s(ws[lvl], w.shape[0], cu))
+            src = self.u[lvl]
+        # heads: text mask (pk x pk, 1 ch) and reconstruction (k x k, 3 ch) share one pk x pk GEMM with 4 columns
+        wt_, bt_ = cbn("conv_text_mask_out")
+        wr_, br_ = cbn("conv_reconstruct")
+        wh = torch.zeros((4, upc[0], pk, pk))
+        wh[0] = wt_[0]
+        o = (pk - k) // 2
+        wh[1:4, :, o:o + k, o:o + k] = wr_
+        f0 = self.flops
+        self._conv(wh, torch.cat([bt_, br_]), [(self.u[0], ident(upc[0]))], None, act=0, S=self._pick_s(W, 4, upc[0], cap=8), f32_out=self.heads)
+        self.flops = f0 + 2 * H * W * upc[0] * (pk * pk + 3 * k * k)     # algorithmic: 7x7x1 + 3x3x3, not the padded GEMM
+        self.ops.append(("heads_post", None))
+        dmap = [0, 1, 2] + [-1] * 5
+        w, b = cbn("conv_pixels_1")       # reference input order: (diff 0..2, x_up1)  (:383)
+        self._conv(w, b, [(self.u[0], [3 + c for c in range(upc[0])]), (self.diff, dmap)], self.px1, act=1, S=self._pick_s(W, pm1, upc[0]))
+        w, b = cbn("conv_pixels_2")
+        self._conv(w, b, [(self.px1, [3 + c for c in range(pm1)]), (self.diff, dmap)], self.px2, act=1, S=self._pick_s(W, pm2, pm1))
+        w, b = cbn("conv_out")
+        self._conv(w, b, [(self.px2, [3 + c for c in range(pm2)]), (self.diff, dmap)], None, act=0, S=self._pick_s(W, 1, pm2, cap=16),
+                   f32_out=self.logits)
+        self.ops.append(("threshold", None))
+
+    @staticmethod
+    def count_flops(net, H, W):
+        """Algorithmic FLOPs per frame: 2 x MACs of the 16 conv + 5 transposed-conv layers, no padding."""
+        sd = net.state_dict()
+        hs, ws = [H], [W]
+        for _ in range(5):
+            hs.append(hs[-1] // 2); ws.append(ws[-1] // 2)
+        macs = 0
+        for i in range(1, 6):
+            macs += hs[i - 1] * ws[i - 1] * sd["conv_down_block_%d.0.weight" % i][0].numel() * sd["conv_down_block_%d.0.weight" % i].shape[0]
+            macs += hs[i - 1] * ws[i - 1] * sd["conv_up_block_%d.0.weight" % i].numel()
+            macs += hs[i] * ws[i] * sd["transposed_conv_%d.weight" % i].numel()
+        macs += hs[5] * ws[5] * sd["mid_block.0.weight"].numel()
+        for n in ("conv_text_mask_out", "conv_reconstruct", "conv_pixels_1", "conv_pixels_2", "conv_out"):
+            macs += H * W * sd[n + ".0.weight"].numel()
+        return 2 * macs
+
+    # -------------------------------------------------------------------------------------------------
+    def _pick_s(self, width, cout, cin, cap=None):
+        """x-packing factor: fill the UMMA N dimension (target N = S*Cout up to 128) for narrow layers."""
+        if not self.rowrun:
+            return 1
+        s = 1
+        while s * 2 * cout <= 128 and width % (s * 2) == 0 and (cap is None or s * 2 <= cap) and s * 2 <= 16:
+            s *= 2
+        return s
+
+    def _conv(self, w, b, srcs, dst, act, S, f32_out=None):
+        nrows, cin_total, KH, KW = w.shape
+        first = srcs[0][0]
+        Hin, Win = first.H, first.W
+        if Win % S:
+            S = 1
+        NT = choose_nt(S * nrows)
+        packed, bias, ntot, ntot_pad = pack_weights(w, b, [(buf.C, cmap) for buf, cmap in srcs], S, self.rowrun, NT)
+        packed, bias = packed.to(self.device), bias.to(self.device)
+        self.keep += [packed, bias]
+        d = ConvDesc()
+        d.nseg = len(srcs)
+        for i, (buf, _) in enumerate(srcs):
+            g = d.seg[i]
+            g.ptr, g.C, g.Wp, g.Hbuf = buf.ptr, buf.C, buf.Wp, buf.H
+            g.x_off = buf.pad - (KW - 1) // 2
+            assert g.x_off >= 0
+            g.rowrun, g.S, g.run_len, g.KW = int(self.rowrun), S, (KW + S - 1) * buf.C, KW
+        d.weights, d.bias = packed.data_ptr(), bias.data_ptr()
+        d.KH, d.padY = KH, (KH - 1) // 2
+        d.nR, d.Hin, d.batch = Win // S, Hin, self.B
+        d.RT, d.YT = choose_tile(d.nR, Hin, KH)
+        d.NT, d.Ntot, d.Ntot_pad = NT, ntot, ntot_pad
+        if f32_out is not None:
+            d.out, d.out_f32 = f32_out.data_ptr(), 1
+            d.out_H, d.out_W = Hin, Win
+            d.out_sx = nrows
+            d.out_sy = Win * nrows
+            d.out_sn = Hin * Win * nrows
+            d.out_padx, d.out_coff = 0, 0
+        else:
+            d.out, d.out_f32 = dst.ptr, 0
+            d.out_H, d.out_W = dst.H, dst.W
+            d.out_sx, d.out_sy, d.out_sn = dst.C, dst.Wp * dst.C, dst.H * dst.Wp * dst.C
+            d.out_padx, d.out_coff = dst.pad, 0
+        d.Cout, d.Sy, d.Sx, d.act = nrows, 1, S, act
+        self.ops.append(("conv", d))
+        self.flops += 2 * Hin * Win * nrows * cin_total * KH * KW
+
+    def _tconv(self, wt, bt, src, dst):
+        """ConvTranspose2d(k=2,s=2) + BN + GELU as a 1x1 GEMM with N = (sy,sx,co); odd output sizes get the
+        bias-only row/column (output_padding, FCN_lecturenet.py:280) from a border fill."""
+        cin, cout = wt.shape[0], wt.shape[1]
+        w = wt.permute(2, 3, 1, 0).reshape(4 * cout, cin, 1, 1).contiguous()      # n = (sy*2+sx)*Cout + co
+        NT = choose_nt(4 * cout)
+        packed, bias, ntot, ntot_pad = pack_weights(w, bt.repeat(4), [(src.C, list(range(src.C)))], 1, self.rowrun, NT)
+        packed, bias = packed.to(self.device), bias.to(self.device)
+        d = ConvDesc()
+        d.nseg = 1
+        g = d.seg[0]
+        g.ptr, g.C, g.Wp, g.Hbuf, g.x_off = src.ptr, src.C, src.Wp, src.H, src.pad
+        g.rowrun, g.S, g.run_len, g.KW = int(self.rowrun), 1, src.C, 1
+        d.weights, d.bias = packed.data_ptr(), bias.data_ptr()
+        d.KH, d.padY = 1, 0
+        d.nR, d.Hin, d.batch = src.W, src.H, self.B
+        d.RT, d.YT = choose_tile(src.W, src.H, 1)
+        d.NT, d.Ntot, d.Ntot_pad = NT, ntot, ntot_pad
+        d.out, d.out_f32 = dst.ptr, 0
+        d.out_H, d.out_W = dst.H, dst.W
+        d.out_sx, d.out_sy, d.out_sn = dst.C, dst.Wp * dst.C, dst.H * dst.Wp * dst.C
+        d.out_padx, d.out_coff = dst.pad, 0
+        d.Cout, d.Sy, d.Sx, d.act = cout, 2, 2, 1
+        self.ops.append(("conv", d))
+        gelu_b = (0.5 * bt.double() * (1.0 + torch.erf(bt.double() / math.sqrt(2.0)))).float().to(torch.bfloat16).to(self.device)
+        self.keep += [packed, bias, gelu_b]
+        if dst.H > 2 * src.H or dst.W > 2 * src.W:
+            self.ops.append(("border", (dst, 2 * src.H, 2 * src.W, gelu_b)))
+        self.flops += 2 * src.H * src.W * 4 * cout * cin
+
+    # -------------------------------------------------------------------------------------------------
+    def run(self, stream, want_others=False, threshold=128):
+        """frames (self.frames, uint8 BGR) -> self.logits / self.bits (and text_logit / rec when asked)."""
+        lib, B, H, W = _lib.lib(), self.B, self.H, self.W
+        st = ctypes.c_void_p(stream)
+        chk = _lib.check
+        chk(lib.am_fcn_prep_input(self.frames.data_ptr(), B, H, W, self.x0.ptr, self.x0.C, self.x0.pad, st), "am_fcn_prep_input")
+        for kind, a in self.ops:
+            if kind == "conv":
+                chk(lib.am_conv_gemm(ctypes.byref(a), st), "am_conv_gemm")
+            elif kind == "pool":
+                src, dst = a
+                chk(lib.am_fcn_maxpool2(src.ptr, B, src.H, src.W, src.C, src.pad, dst.ptr, dst.pad, st), "am_fcn_maxpool2")
+            elif kind == "border":
+                dst, yf, xf, vals = a
+                chk(lib.am_fcn_fill_border(dst.ptr, B, dst.H, dst.W, dst.C, dst.pad, yf, xf, vals.data_ptr(), st), "am_fcn_fill_border")
+            elif kind == "heads_post":
+                chk(lib.am_fcn_heads_post(self.heads.data_ptr(), self.frames.data_ptr(), B, H, W, self.diff.ptr, self.diff.C, self.diff.pad,
+                                          self.text_logit.data_ptr() if want_others else None,
+                                          self.rec.data_ptr() if want_others else None, st), "am_fcn_heads_post")
+            elif kind == "threshold":
+                chk(lib.am_fcn_threshold_pack(self.logits.data_ptr(), B, H, W, int(threshold), self.bits.data_ptr(), st), "am_fcn_threshold_pack")
+
+
+# ----------------------------------------------------------------------------------------------------
+class FCN_LectureNet:
+    """Drop-in for the reference class (inference only; the training branches are out of scope)."""
+
+    def __init__(self, channels, n_conv_down_1, n_conv_down_2, n_conv_down_3, n_conv_down_4, n_conv_down_5, mid_block,
+                 n_upsample_5, n_conv_up_5, n_upsample_4, n_conv_up_4, n_upsample_3, n_conv_up_3,
+                 n_upsample_2, n_conv_up_2, n_upsample_1, n_conv_up_1, kernel_size,
+                 n_pmaps_1, n_pmaps_2, pixel_kernel_size, reconstruction_mode):
+        if channels != 3 or reconstruction_mode:
+            raise NotImplementedError("only the 3-channel binarizer branch (reconstruction_mode=False) is on the hot path")
+        self.params = _Params(channels, [n_conv_down_1, n_conv_down_2, n_conv_down_3, n_conv_down_4, n_conv_down_5], mid_block,
+                              [n_upsample_1, n_upsample_2, n_upsample_3, n_upsample_4, n_upsample_5],
+                              [n_conv_up_1, n_conv_up_2, n_conv_up_3, n_conv_up_4, n_conv_up_5], kernel_size,
+                              n_pmaps_1, n_pmaps_2, pixel_kernel_size)
+        self.reconstruction_mode = reconstruction_mode
+        self._plans = {}
+        self._device = None
+        self.rowrun = True
+
+    # ---- reference-compatible plumbing ---------------------------------------------------------------
+    @staticmethod
+    def CreateFromConfig(config, in_channels, reconstruction_mode):
+        g = config.get
+        return FCN_LectureNet(
+            in_channels,
+            g("FCN_BINARIZER_NET_DOWN_CONV_FILTERS_1", 16), g("FCN_BINARIZER_NET_DOWN_CONV_FILTERS_2", 32),
+            g("FCN_BINARIZER_NET_DOWN_CONV_FILTERS_3", 64), g("FCN_BINARIZER_NET_DOWN_CONV_FILTERS_4", 128),
+            g("FCN_BINARIZER_NET_DOWN_CONV_FILTERS_5", 256), g("FCN_BINARIZER_NET_MIDDLE_CONV_FILTERS_MIDDLE", 512),
+            g("FCN_BINARIZER_NET_UPSAMPLE_FILTERS_5", 256), g("FCN_BINARIZER_NET_UP_CONV_FILTERS_5", 256),
+            g("FCN_BINARIZER_NET_UPSAMPLE_FILTERS_4", 128), g("FCN_BINARIZER_NET_UP_CONV_FILTERS_4", 128),
+            g("FCN_BINARIZER_NET_UPSAMPLE_FILTERS_3", 64), g("FCN_BINARIZER_NET_UP_CONV_FILTERS_3", 64),
+            g("FCN_BINARIZER_NET_UPSAMPLE_FILTERS_2", 32), g("FCN_BINARIZER_NET_UP_CONV_FILTERS_2", 32),
+            g("FCN_BINARIZER_NET_UPSAMPLE_FILTERS_1", 16), g("FCN_BINARIZER_NET_UP_CONV_FILTERS_1", 16),
+            g("FCN_BINARIZER_NET_KERNEL_SIZE", 3),
+            g("FCN_BINARIZER_NET_PIXEL_FEATURES_1", 32), g("FCN_BINARIZER_NET_PIXEL_FEATURES_2", 16),
+            g("FCN_BINARIZER_NET_PIXEL_KERNEL_SIZE", 3), reconstruction_mode)
+
+    def state_dict(self):
+        return self.params.state_dict()
+
+    def load_state_dict(self, sd, strict=True):
+        self._plans.clear()
+        return self.params.load_state_dict(sd, strict=strict)
+
+    def parameters(self):
+        return self.params.parameters()
+
+    def eval(self):
+        self.params.eval()
+        return self
+
+    def cuda(self, device=None):
+        self._device = torch.device("cuda:%d" % (torch.cuda.current_device() if device is None else int(device)))
+        return self
+
+    def to(self, device):
+        return self.cuda(torch.device(device).index)
+
+    def __call__(self, x0):
+        return self.forward(x0)
+
+    # ---- device plans ------------------------------------------------------------------------------------
+    def plan(self, B, H, W):
+        if self._device is None:
+            _lib.lib()      # raises loudly without a GPU: there is no CPU path
+            self.cuda()
+        key = (B, H, W, self.rowrun)
+        if key not in self._plans:
+            with torch.cuda.device(self._device):
+                self._plans[key] = FCNPlan(self.params, B, H, W, self._device, self.rowrun)
+        return self._plans[key]
+
+    def binarize_frames(self, frames_bgr, want_others=False, threshold=128):
+        """uint8 BGR frames (B,H,W,3) (numpy, pinned/CPU tensor or CUDA tensor) -> the plan holding
+        logits (B,H,W) fp32 and the bit-packed INK mask (B,H,WPR), all on the device.  The fused fast path."""
+        t = torch.from_numpy(frames_bgr) if isinstance(frames_bgr, np.ndarray) else frames_bgr
+        B, H, W, _ = t.shape
+        plan = self.plan(B, H, W)
+        plan.frames.copy_(t, non_blocking=True)
+        plan.run(torch.cuda.current_stream().cuda_stream, want_others, threshold)
+        return plan
+
+    def masks_from_plan(self, plan, f, want_others=True, threshold=128):
+        """Reference-format host outputs of frame f: ink mask uint8 (ink = 255, i.e. after `255 - binary`),
+        text mask uint8 0/255, reconstructed image uint8 BGR  (FCN_lecturenet.py:461-479)."""
+        from .cc_engine import _p, _stream
+        ink = torch.empty((1, plan.H, plan.W), dtype=torch.uint8, device=plan.device)
+        _lib.check(plan.lib.am_unpack_mask_u8(_p(plan.bits[f:f + 1]), plan.W, plan.H, 1, _p(ink), _stream()), "am_unpack_mask_u8")
+        binary = ink[0].cpu().numpy()
+        if not want_others:
+            return binary, None, None
+        t = (torch.sigmoid(plan.text_logit[f]).cpu().numpy() * 255).astype(np.uint8)
+        text_mask = np.where(t >= threshold, 255, 0).astype(np.uint8)
+        rec = plan.rec[f].cpu().numpy() * 0.5 + 0.5
+        return binary, text_mask, np.clip(rec[:, :, ::-1] * 255, 0, 255).astype(np.uint8)
+
+    @staticmethod
+    def prepare_image(PIL_image):
+        """(1,3,H,W) fp32 in [-1,1]  (:607-618)"""
+        a = np.asarray(PIL_image.convert("RGB"), dtype=np.uint8)
+        t = torch.from_numpy(a.copy()).permute(2, 0, 1).float().div(255.0)
+        return ((t - 0.5) / 0.5).unsqueeze(0)
+
+    def forward(self, x0):
+        """x0: (N,3,H,W) fp32 normalised as prepare_image does -> (output_logit, text_mask_logit, rec_img) CUDA fp32.
+        The kernels start from the uint8 frame, so x0 is mapped back to its uint8 pixels (exact for prepare_image output)."""
+        u8 = torch.round((x0.detach().float().cpu() * 0.5 + 0.5) * 255.0).clamp(0, 255).to(torch.uint8)
+        bgr = u8.permute(0, 2, 3, 1).flip(-1).contiguous()
+        plan = self.binarize_frames(bgr, want_others=True)
+        return (plan.logits.unsqueeze(1).clone(), plan.text_logit.unsqueeze(1).clone(), plan.rec.permute(0, 3, 1, 2).contiguous())
+
+    def binarize(self, PIL_image, return_others=False, force_binary=False, binary_treshold=128, apply_sigmoid=True):
+        import cv2
+        import PIL.Image
+        o_width, o_height = PIL_image.size
+        width, height = o_width, o_height
+        while width * height > 2500000:                                  # :434-437 (host PIL, as the reference)
+            PIL_image = PIL_image.resize((int(width / 2), int(height / 2)), PIL.Image.LANCZOS)
+            width, height = PIL_image.size
+        rgb = np.asarray(PIL_image.convert("RGB"), dtype=np.uint8)
+        plan = self.binarize_frames(np.ascontiguousarray(rgb[None, :, :, ::-1]), want_others=return_others)
+        res = plan.logits[0]
+        text = plan.text_logit[0] if return_others else None
+        if apply_sigmoid:                                                # :452-454
+            res = torch.sigmoid(res)
+            text = torch.sigmoid(text) if return_others else None
+        binary = (res.cpu().numpy() * 255).astype(np.uint8)              # :461-462
+        if force_binary:
+            binary[binary >= binary_treshold] = 255
+            binary[binary < binary_treshold] = 0
+        if return_others:
+            text_mask = (text.cpu().numpy() * 255).astype(np.uint8)
+            if force_binary:
+                text_mask[text_mask >= binary_treshold] = 255
+                text_mask[text_mask < binary_treshold] = 0
+            rec = plan.rec[0].cpu().numpy() * 0.5 + 0.5                  # from_img_space_to_cv2 (:532-554)
+            rec_img = np.clip(rec[:, :, ::-1] * 255, 0, 255).astype(np.uint8)
+        if o_width != width:                                             # :481-494
+            interp = cv2.INTER_NEAREST if force_binary else cv2.INTER_CUBIC
+            binary = cv2.resize(binary, (o_width, o_height), interpolation=interp)
+            if return_others:
+                text_mask = cv2.resize(text_mask, (o_width, o_height), interpolation=interp)
+                rec_img = cv2.resize(rec_img, (o_width, o_height), interpolation=cv2.INTER_NEAREST)
+        if return_others:
+            return binary, text_mask, rec_img
+        return binary

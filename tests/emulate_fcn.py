@@ -1,0 +1,111 @@
+"""Test infrastructure: a torch/CPU emulation of what csrc/fcn_conv.cu + fcn_misc.cu compute from an FCNPlan
+(same packed weights, same descriptors, same buffer layout, TMA out-of-bounds zero fill, K-step masking, epilogue
+scatter).  It checks the HOST logic (weight packing, S-packing, K segments, tile/epilogue index math) on the CPU
+tier; the GPU tier then only has the PTX itself left to prove."""
+import math
+
+import torch
+
+
+def _flat_of(plan):
+    m = {}
+    for b in [plan.x0, plan.mid, plan.diff, plan.px1, plan.px2] + plan.d + plan.p + plan.t + plan.u:
+        m[b.ptr] = b.t
+    for t in plan.keep + [plan.heads, plan.logits]:
+        m[t.data_ptr()] = t.view(-1)
+    return m
+
+
+def emulate_conv(d, mem):
+    B, Hin, nR, KH = d.batch, d.Hin, d.nR, d.KH
+    Wmat = mem[d.weights].float().view(-1, KH, d.Ntot_pad, 64)           # [chunk][dy][n][64]
+    bias = mem[d.bias].float()
+    acc = torch.zeros((B, Hin, nR, d.Ntot_pad), dtype=torch.float32)
+    chunk = 0
+    n_i = torch.arange(B).view(B, 1, 1, 1)
+    y_i = torch.arange(Hin).view(1, Hin, 1, 1)
+    r_i = torch.arange(nR).view(1, 1, nR, 1)
+    kk = torch.arange(64).view(1, 1, 1, 64)
+    for s in range(d.nseg):
+        g = d.seg[s]
+        flat = mem[g.ptr].float()
+        base = g.x_off * g.C
+        if g.rowrun:
+            nkx, nck, dim0 = 1, (g.run_len + 63) // 64, g.run_len
+            klast = ((g.run_len - (nck - 1) * 64) + 15) // 16 * 16
+        else:
+            nkx, nck, dim0 = g.KW, (g.C + 63) // 64, g.C
+            klast = ((g.C - (nck - 1) * 64) + 15) // 16 * 16
+        for kx in range(nkx):
+            for ck in range(nck):
+                kvalid = klast if ck == nck - 1 else 64
+                for dy in range(KH):
+                    yy = y_i + dy - d.padY
+                    k = ck * 64 + kk
+                    if g.rowrun:
+                        idx = base + ((n_i * g.Hbuf + yy) * g.Wp) * g.C + r_i * g.S * g.C + k
+                        ok = (yy >= 0) & (yy < Hin) & (k < dim0)
+                    else:
+                        x = r_i + kx
+                        idx = base + ((n_i * g.Hbuf + yy) * g.Wp + x) * g.C + k
+                        ok = (yy >= 0) & (yy < Hin) & (k < dim0) & (x < g.Wp)
+                    ok = ok & (kk < kvalid)
+                    idx = torch.where(ok, idx, torch.zeros_like(idx))
+                    a = torch.where(ok, flat[idx.reshape(-1)].view(idx.shape), torch.zeros(()))
+                    acc += torch.einsum("byrk,nk->byrn", a, Wmat[chunk, dy])
+                chunk += 1
+    out = mem[d.out]
+    x = acc + bias.view(1, 1, 1, -1)
+    if d.act == 1:
+        x = 0.5 * x * (1.0 + torch.erf(x / math.sqrt(2.0)))
+    n = torch.arange(d.Ntot)
+    grp, co = n // d.Cout, n % d.Cout
+    sy, sx = grp // d.Sx, grp % d.Sx
+    for j in range(d.Ntot):
+        oy = d.Sy * torch.arange(Hin) + int(sy[j])
+        ox = d.Sx * torch.arange(nR) + int(sx[j])
+        vy, vx = oy < d.out_H, ox < d.out_W
+        off = (torch.arange(B).view(B, 1, 1) * d.out_sn + oy[vy].view(1, -1, 1) * d.out_sy +
+               (ox[vx].view(1, 1, -1) + d.out_padx) * d.out_sx + d.out_coff + int(co[j]))
+        vals = x[:, vy][:, :, vx][..., j]
+        out[off.reshape(-1)] = vals.reshape(-1).to(out.dtype)
+
+
+def _norm(u8):
+    return (u8.float() / 255.0 - 0.5) / 0.5
+
+
+def emulate_plan(plan, frames_bgr):
+    """Run the whole plan on the CPU; returns (logits, text_logit, rec, ink)."""
+    mem = _flat_of(plan)
+    B, H, W = plan.B, plan.H, plan.W
+    fr = torch.as_tensor(frames_bgr)
+    rgb = _norm(fr.flip(-1))
+    plan.x0.view()[..., :3] = rgb.to(torch.bfloat16)
+    text = rec = None
+    for kind, a in plan.ops:
+        if kind == "conv":
+            emulate_conv(a, mem)
+        elif kind == "pool":
+            src, dst = a
+            v = src.view().float()
+            Ho, Wo = src.H // 2, src.W // 2
+            v = v[:, :Ho * 2, :Wo * 2].reshape(B, Ho, 2, Wo, 2, src.C).amax(dim=(2, 4))
+            dst.view()[:] = v.to(torch.bfloat16)
+        elif kind == "border":
+            dst, yf, xf, vals = a
+            v = dst.view()
+            v[:, yf:, :, :] = vals
+            v[:, :, xf:, :] = vals
+        elif kind == "heads_post":
+            h = plan.heads
+            text = h[..., 0].clone()
+            rec = torch.tanh(h[..., 1:4])
+            diff = (rgb - rec) * torch.sigmoid(text).unsqueeze(-1)
+            plan.diff.view()[..., :3] = diff.to(torch.bfloat16)
+        elif kind == "threshold":
+            pass
+    logits = plan.logits.clone()
+    u8 = (torch.sigmoid(logits).numpy() * 255).astype("uint8")
+    ink = (u8 < 128)
+    return logits, text, rec, ink

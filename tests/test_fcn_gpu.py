@@ -1,0 +1,96 @@
+"""GPU parity tests for the FCN binarizer (tcgen05 implicit-GEMM kernels, through the C ABI).
+
+Floating point: bf16 operands, fp32 accumulation.  Stated tolerance (BASELINE.json north_star): probability maps
+within 1e-2 absolute of the fp32 reference, mask disagreement <= 0.1 % of pixels."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import fcn_oracle as FO
+from tests.test_fcn_host_logic import golden_net
+
+pytestmark = pytest.mark.gpu
+
+PROB_TOL = 1e-2
+MASK_TOL = 1e-3
+
+
+def _sig(a):
+    return 1.0 / (1.0 + np.exp(-a))
+
+
+@pytest.mark.parametrize("tag", ["tiny", "full"])
+@pytest.mark.parametrize("rowrun", [True, False])
+def test_forward_vs_reference_golden(golden, tag, rowrun):
+    z = golden("fcn_forward.npz")
+    net = golden_net(tag, z).cuda()
+    net.rowrun = rowrun
+    frame = z["frame_bgr"]
+    plan = net.binarize_frames(frame[None], want_others=True)
+    torch.cuda.synchronize()
+    p = _sig(plan.logits[0].cpu().numpy())
+    assert np.abs(p - _sig(z[tag + "_logit"])).max() < PROB_TOL
+    assert np.abs(_sig(plan.text_logit[0].cpu().numpy()) - _sig(z[tag + "_text_logit"])).max() < PROB_TOL
+    assert np.abs(plan.rec[0].permute(2, 0, 1).cpu().numpy() - z[tag + "_rec_raw"]).max() < 2e-2
+    ink, text_m, rec = net.masks_from_plan(plan, 0)
+    assert (ink != z[tag + "_binary"]).mean() <= 2 * MASK_TOL          # 10k-pixel image: 0.1 % = 10 pixels
+    assert np.abs(rec.astype(int) - z[tag + "_rec"].astype(int)).max() <= 3
+
+
+def test_binarize_and_worker_api_vs_oracle(golden):
+    from PIL import Image
+    import cv2
+    from lecturemath_b200.fcn_binarizer_worker import FCN_LectureNet_Binarizer
+    z = golden("fcn_forward.npz")
+    net = golden_net("tiny", z).cuda()
+    frame = z["frame_bgr"]
+    pil = Image.fromarray(cv2.cvtColor(frame, cv2.COLOR_RGB2BGR))
+    binary, text_m, rec = net.binarize(pil, return_others=True, force_binary=True)
+    assert ((255 - binary) != z["tiny_binary"]).mean() <= 2 * MASK_TOL
+    soft = net.binarize(pil)
+    sd = {k: v for k, v in net.state_dict().items()}
+    ref_soft, _, _ = FO.binarize(sd, frame[:, :, ::-1], force_binary=False)
+    assert np.abs(soft.astype(int) - ref_soft.astype(int)).max() <= 3
+    worker = FCN_LectureNet_Binarizer(net)
+    worker.initialize(frame.shape[1], frame.shape[0])
+    worker.handleFrame(frame, None, 0, 40.0, 40.0, 7)
+    assert worker.frame_indices == [7] and worker.frame_times == [40.0] and worker.getWorkName()
+    decoded = cv2.imdecode(worker.compressed_frames[0], cv2.IMREAD_GRAYSCALE)
+    np.testing.assert_array_equal(decoded, worker.last_binary)
+    assert (decoded != z["tiny_binary"]).mean() <= 2 * MASK_TOL
+    lg, tx, rc = net.forward(net.prepare_image(pil))
+    assert lg.shape == (1, 1) + frame.shape[:2] and rc.shape == (1, 3) + frame.shape[:2]
+    assert np.abs(_sig(lg[0, 0].cpu().numpy()) - _sig(z["tiny_logit"])).max() < PROB_TOL
+
+
+@pytest.mark.parametrize("hw", [(720, 1280), (1080, 1920)])
+def test_full_size_random_init_vs_fp32_oracle_on_gpu(hw):
+    """BASELINE configs 1/2 shapes with the reference's seed-0 random init: compare with the fp32 oracle run on the
+    same GPU (torch/cuDNN fp32, TF32 off).  Also a size-independent property: batch invariance."""
+    from lecturemath_b200 import synth
+    from lecturemath_b200.configuration import Configuration
+    from lecturemath_b200.fcn_lecturenet import FCN_LectureNet
+    from tests.conftest import GOLDEN
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    h, w = hw
+    torch.manual_seed(0)
+    net = FCN_LectureNet.CreateFromConfig(Configuration.from_file(GOLDEN + "/fcn_full.conf"), 3, False).eval().cuda()
+    frames = np.stack(list(synth.whiteboard_frames(2, h, w, seed=1234)))
+    plan = net.binarize_frames(frames)
+    torch.cuda.synchronize()
+    logits = plan.logits.clone()
+    bits = plan.bits.clone()
+    sd = {k: v.cuda() for k, v in net.state_dict().items()}
+    for f in range(2):
+        x0 = FO.prepare_image(frames[f][:, :, ::-1]).cuda()
+        ref, _, _ = FO.forward(sd, x0)
+        p, pr = torch.sigmoid(logits[f]), torch.sigmoid(ref[0, 0])
+        assert (p - pr).abs().max().item() < PROB_TOL
+        ink = ((p * 255).to(torch.uint8) < 128)
+        ink_ref = ((pr * 255).to(torch.uint8) < 128)
+        dis = (ink != ink_ref).float().mean().item()
+        assert dis <= MASK_TOL, "mask disagreement %.4f%%" % (100 * dis)
+    single = net.binarize_frames(frames[1:2])
+    torch.cuda.synchronize()
+    assert torch.equal(single.bits[0], bits[1])                          # batch invariance (bit-exact)

@@ -1,0 +1,71 @@
+"""CPU: host-side logic of the FCN path -- seeded init equals the reference's, BN folding, weight packing and
+the row-run GEMM formulation (emulated in torch from the very descriptors the CUDA kernel receives) reproduce
+the reference's logits within bf16 tolerance."""
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+from lecturemath_b200.configuration import Configuration
+from lecturemath_b200.fcn_lecturenet import FCN_LectureNet, FCNPlan
+from tests.conftest import GOLDEN
+from tests.emulate_fcn import emulate_plan
+
+
+def _state_hash(sd):
+    h = hashlib.sha256()
+    for k in sd:
+        h.update(k.encode()); h.update(sd[k].detach().cpu().numpy().tobytes())
+    return h.hexdigest()
+
+
+def golden_net(tag, z):
+    """Rebuild the exact weights oracle/gen_golden.py gave the reference (seed 0 + perturbed BatchNorm)."""
+    path = GOLDEN + ("/fcn_tiny.conf" if tag == "tiny" else "/fcn_full.conf")
+    cfg = Configuration.from_file(path)
+    torch.manual_seed(0)
+    net = FCN_LectureNet.CreateFromConfig(cfg, 3, False)
+    g = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        for _, mod in net.params.named_modules():
+            if isinstance(mod, torch.nn.BatchNorm2d):
+                mod.running_mean.copy_(torch.randn(mod.num_features, generator=g) * 0.1)
+                mod.running_var.copy_(torch.rand(mod.num_features, generator=g) * 0.5 + 0.75)
+                mod.weight.copy_(torch.rand(mod.num_features, generator=g) * 0.5 + 0.75)
+                mod.bias.copy_(torch.randn(mod.num_features, generator=g) * 0.1)
+    return net.eval()
+
+
+def test_seeded_init_reproduces_reference_weights(golden):
+    z = golden("fcn_forward.npz")
+    net = golden_net("tiny", z)
+    assert _state_hash(net.state_dict()) == str(z["tiny_sd_hash"])
+    for k, v in net.state_dict().items():
+        np.testing.assert_array_equal(v.numpy(), z["tiny_sd/" + k])
+
+
+@pytest.mark.parametrize("rowrun", [True, False])
+def test_emulated_kernel_plan_matches_reference_logits(golden, rowrun):
+    z = golden("fcn_forward.npz")
+    net = golden_net("tiny", z)
+    frame = z["frame_bgr"]
+    plan = FCNPlan(net.params, 1, frame.shape[0], frame.shape[1], torch.device("cpu"), rowrun=rowrun)
+    logits, text, rec, ink = emulate_plan(plan, frame[None])
+    # bf16 activations/weights with fp32 accumulation: stated tolerance 1e-2 on probabilities (BASELINE north_star)
+    p, p_ref = torch.sigmoid(logits[0]).numpy(), 1 / (1 + np.exp(-z["tiny_logit"]))
+    assert np.abs(p - p_ref).max() < 1e-2
+    assert np.abs(torch.sigmoid(text[0]).numpy() - 1 / (1 + np.exp(-z["tiny_text_logit"]))).max() < 1e-2
+    assert np.abs(rec[0].permute(2, 0, 1).numpy() - z["tiny_rec_raw"]).max() < 2e-2
+    ref_ink = z["tiny_binary"] > 0
+    assert (ink[0] != ref_ink).mean() <= 2e-3
+    assert plan.flops > 0
+
+
+def test_full_config_flops_match_survey():
+    cfg = Configuration.from_file(GOLDEN + "/fcn_full.conf")
+    net = FCN_LectureNet.CreateFromConfig(cfg, 3, False)
+    assert sum(p.numel() for p in net.parameters()) == 15815538
+    for (h, w, gf) in ((720, 1280, 414.5), (1080, 1920, 931.8)):
+        plan = FCNPlan.__new__(FCNPlan)                                    # flop count only: no buffers
+        assert abs(FCNPlan.count_flops(net.params, h, w) / 1e9 - gf) < 0.5
