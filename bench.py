@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark: 1080p frames/s for (FCN binarize + CC label/stats + temporal match).
+
+  python bench.py --gpus N --steps K --warmup W            this repo on N B200s (torchrun launches N>1)
+  python bench.py --impl reference --steps K --warmup W     the reference's CPU algorithm (oracle port) on host cores
+
+A "step" = one pass of the hot path over one batch of synthetic 1080p whiteboard frames (BASELINE.json
+configs[1]).  `value` = whole-job frames/s with the frames already resident in HBM; `e2e` = the same metric
+through ContentExtractor.process_batch with HOST buffers (H2D of the frames and D2H of the result rows inside the
+timed region).  Multi-GPU: contiguous frame ranges per rank (weak scaling), temporal matching chained rank to
+rank with the active unique-CC set sent over NCCL (lecturemath_b200/pipeline.py).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+H, W = 1080, 1920
+CONF = os.path.join(REPO, "tests", "golden", "fcn_full.conf")
+METRIC = "1080p frames/s (FCN binarize + CC label/stats/match)"
+
+
+def measured_peaks():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples if len(s) > 2 + i)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.samples[0][1]) if self.samples[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def make_net():
+    import torch
+    from lecturemath_b200.configuration import Configuration
+    from lecturemath_b200.fcn_lecturenet import FCN_LectureNet
+    torch.manual_seed(0)                                  # the reference's random init under seed 0 (no trained weights on the box)
+    return FCN_LectureNet.CreateFromConfig(Configuration.from_file(CONF), 3, False).eval()
+
+
+def frame_pool(n, seed):
+    from lecturemath_b200 import synth
+    return np.stack(list(synth.whiteboard_frames(n, H, W, seed=seed)))
+
+
+# ------------------------------------------------------------------------------------------------------------
+def cpu_reference_pass(frames, sd, est):
+    """The reference's CPU algorithm (oracle port) for a few frames: torch-CPU fp32 FCN + oracle CC stage."""
+    from oracle import fcn_oracle as FO
+    t0 = time.perf_counter()
+    for fr in frames:
+        ink, _, _ = FO.handle_frame(sd, fr)
+        est.add_frame(ink)
+    return time.perf_counter() - t0
+
+
+def run_reference(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import cc_oracle as CO
+    torch.set_num_threads(os.cpu_count())
+    net = make_net()
+    sd = net.state_dict()
+    n_timed = max(1, min(args.steps, 24))
+    n_warm = max(1, min(args.warmup, 2))
+    frames = frame_pool(n_timed + n_warm, 1234)
+    est = CO.StabilityOracle(W, H, 0.85, 0.85, 85, use_ref_lib=CO.ref_lib() is not None)
+    cpu_reference_pass(frames[:n_warm], sd, est)
+    dt = cpu_reference_pass(frames[n_warm:], sd, est)
+    fps = n_timed / dt
+    kind = "port"
+    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1000.0 * dt / n_timed, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "config": {"workload": "1080p synthetic whiteboard video, binarize + CC label/stats + temporal match (BASELINE configs[1]); "
+                                   "one frame per step", "weights": "random-init seed 0"},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": os.cpu_count(), "kind": kind,
+                             "sample": "%d timed 1080p frames (torch-CPU fp32 FCN + scipy-equivalent label + %s CC_AgeBoundaries + "
+                                       "Python matching), %d warm-up" % (n_timed, "reference-compiled" if CO.ref_lib() is not None else "ported", n_warm)},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from lecturemath_b200.pipeline import ContentExtractor
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    B, K, Wm = args.batch, args.steps, args.warmup
+    net = make_net()
+    ex = ContentExtractor(net, W, H, 0.85, 0.85, 85, batch=B, device=dev)
+    pool_n = max(2 * B, 16)
+    pool_h = torch.from_numpy(frame_pool(pool_n, 1234 + rank)).pin_memory()
+    pool_d = pool_h.to(dev)
+    l2_flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def batch_dev(i):
+        s = (i % (pool_n // B)) * B
+        return pool_d[s:s + B]
+
+    def batch_host(i):                                    # contiguous slice of the pinned host pool (no staging copy)
+        s = (i % (pool_n // B)) * B
+        return pool_h[s:s + B]
+
+    # ---------------- device-resident throughput: K steps, then the shard chain -------------------------
+    def timed_device(n_steps, timing=None, bits_store=None):
+        for i in range(n_steps):
+            l2_flush.fill_(i & 0xff)                      # L2 flush between timed iterations (also: activations >> L2)
+            fr = batch_dev(i)
+            if rank == 0:
+                ex.step_device(fr, match=True, timing=timing)
+            else:                                         # phase 1 only; masks are kept for the chained phase 2
+                ex.step_device(fr, match=False, timing=timing)
+                bits_store.append(ex.plan.bits.clone())
+
+    def chain(bits_store):
+        if world == 1:
+            return
+        if rank > 0:
+            ex.recv_state(rank - 1)
+            for bits in bits_store:
+                ex.engine.label(bits, want_labels=False, sync=False)
+                ex.est.add_frames(ex.engine, 0, B)
+                ex.launches += 12 + 2 * B
+        if rank + 1 < world:
+            ex.send_state(rank + 1)
+
+    # warm-up
+    store = []
+    timed_device(max(Wm, 3), None, store)
+    chain(store)
+    barrier()
+    # fresh temporal state for the timed region
+    from lecturemath_b200.cc_engine import Estimator
+    ex.est = Estimator(W, H, 0.85, 0.85, 85, device=dev)
+    ex.launches = 0
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    timing, store = [], []
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    timed_device(K, timing, store)
+    chain(store)
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    launches = ex.launches
+    state = ex.est.state()
+    conv_ms = sum(a.elapsed_time(b) for _, a, b in timing)
+    per_op = {}
+    for i, a, b in timing:
+        per_op.setdefault(i, []).append(a.elapsed_time(b))
+
+    # ---------------- end-to-end through the public API with host buffers ----------------------------------
+    ex.est = Estimator(W, H, 0.85, 0.85, 85, device=dev)
+    for i in range(2):
+        ex.process_batch(batch_host(i))
+    ex.est = Estimator(W, H, 0.85, 0.85, 85, device=dev)
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    d2h = 0
+    n_cc = 0
+    for i in range(K):
+        rows = ex.process_batch(batch_host(i))
+        d2h += sum(r.nbytes for r in rows) + B * 16
+        n_cc += sum(len(r) for r in rows)
+    e1.record()
+    barrier()
+    e2e_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_ms = float(e2e_ms.item())
+    masks = ex.masks_host()
+    ink_pct = 100.0 * float((masks != 0).mean())
+    if rank == 0:
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+
+    if rank == 0:
+        peaks, peak_kind = measured_peaks()
+        frames_total = world * K * B
+        fps = frames_total / (ms_total / 1000.0)
+        flops_step = ex.plan.flops * B
+        conv_ms_step = conv_ms / max(K, 1)
+        achieved = flops_step / (conv_ms_step / 1000.0) / 1e12
+        n_conv = len(per_op)
+        peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
+        roof = {"bound": "tensor", "kernel": "k_conv_gemm (%d launches/step: 16 conv + 5 transposed conv; text-mask and reconstruct "
+                                             "heads share one launch)" % n_conv,
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "peak_kind": peak_kind + " bf16_tflops_sustained (kernel timed inside a long step)",
+                "traffic": None, "flop_per_step": flops_step, "conv_ms_per_step": conv_ms_step,
+                "conv_share_of_step": conv_ms_step / (ms_total / K)}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import cc_oracle as CO
+            torch.set_num_threads(os.cpu_count())
+            sd = net.state_dict()
+            est = CO.StabilityOracle(W, H, 0.85, 0.85, 85, use_ref_lib=CO.ref_lib() is not None)
+            fr = pool_h[:4].numpy()
+            cpu_reference_pass(fr[:1], sd, est)
+            dt = cpu_reference_pass(fr[1:4], sd, est)
+            cpu = {"value": 3 / dt, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+                   "sample": "3 timed 1080p frames of this workload after 1 warm-up frame (torch-CPU fp32 FCN, oracle CC stage)"}
+        line = {"metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": max(Wm, 3),
+                "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": "1080p synthetic whiteboard video, binarize + CC label/stats + temporal match on B200 "
+                                       "(BASELINE configs[1])", "frames_per_step_per_gpu": B, "frame": [H, W],
+                           "weights": "random-init seed 0 (FCN_LectureNet.conf widths)", "l2": "256 MB flush write between steps",
+                           "parallelism": "frame-range shards x%d, chained temporal matching" % world,
+                           "ink_pct": round(ink_pct, 2), "ccs_per_frame": round(n_cc / max(K * B, 1), 1),
+                           "unique_ccs": state["n_unique"], "tempo_count": state["tempo_count"]},
+                "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu,
+                "e2e": {"value": world * K * B / (e2e_ms / 1000.0), "unit": "frames/s", "h2d_bytes_per_step": B * H * W * 3,
+                        "d2h_bytes_per_step": int(d2h / max(K, 1))},
+                "gpu_launches": launches}
+        print(json.dumps(line))
+        if args.layer_table:
+            names = {}
+            rows = []
+            for i in sorted(per_op):
+                d = ex.plan.ops[i][1]
+                t = float(np.mean(per_op[i]))
+                fl = ex.plan.op_flops.get(i, 0) * B
+                rows.append({"op": i, "N": d.NT, "Ntot": d.Ntot, "KH": d.KH, "S": d.Sx if d.Sy == 1 else 1, "RT": d.RT, "YT": d.YT,
+                             "ms": round(t, 4), "tflops": round(fl / (t / 1000.0) / 1e12, 1)})
+            with open(args.layer_table, "w") as f:
+                json.dump(rows, f, indent=1)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=8, help="frames per step per GPU")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--layer-table", default=None, help="write per-layer conv timings (json) here")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

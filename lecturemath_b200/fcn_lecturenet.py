@@ -200,6 +200,7 @@ class FCNPlan:
         self.bits = torch.zeros((B, H, self.wpr), dtype=torch.int32, device=device)
         self.keep = []          # keeps packed weights alive
         self.ops = []           # (kind, payload)
+        self.op_flops = {}      # op index -> algorithmic FLOPs per frame of that conv launch
         self.flops = 0
 
         def cbn(name):
@@ -240,6 +241,7 @@ class FCNPlan:
         f0 = self.flops
         self._conv(wh, torch.cat([bt_, br_]), [(self.u[0], ident(upc[0]))], None, act=0, S=self._pick_s(W, 4, upc[0], cap=8), f32_out=self.heads)
         self.flops = f0 + 2 * H * W * upc[0] * (pk * pk + 3 * k * k)     # algorithmic: 7x7x1 + 3x3x3, not the padded GEMM
+        self.op_flops[len(self.ops) - 1] = self.flops - f0
         self.ops.append(("heads_post", None))
         dmap = [0, 1, 2] + [-1] * 5
         w, b = cbn("conv_pixels_1")       # reference input order: (diff 0..2, x_up1)  (:383)
@@ -315,6 +317,7 @@ class FCNPlan:
             d.out_padx, d.out_coff = dst.pad, 0
         d.Cout, d.Sy, d.Sx, d.act = nrows, 1, S, act
         self.ops.append(("conv", d))
+        self.op_flops[len(self.ops) - 1] = 2 * Hin * Win * nrows * cin_total * KH * KW
         self.flops += 2 * Hin * Win * nrows * cin_total * KH * KW
 
     def _tconv(self, wt, bt, src, dst):
@@ -343,20 +346,33 @@ class FCNPlan:
         self.ops.append(("conv", d))
         gelu_b = (0.5 * bt.double() * (1.0 + torch.erf(bt.double() / math.sqrt(2.0)))).float().to(torch.bfloat16).to(self.device)
         self.keep += [packed, bias, gelu_b]
+        self.op_flops[len(self.ops) - 1] = 2 * src.H * src.W * 4 * cout * cin
         if dst.H > 2 * src.H or dst.W > 2 * src.W:
             self.ops.append(("border", (dst, 2 * src.H, 2 * src.W, gelu_b)))
         self.flops += 2 * src.H * src.W * 4 * cout * cin
 
     # -------------------------------------------------------------------------------------------------
-    def run(self, stream, want_others=False, threshold=128):
-        """frames (self.frames, uint8 BGR) -> self.logits / self.bits (and text_logit / rec when asked)."""
+    @property
+    def launches_per_run(self):
+        return 1 + len(self.ops)
+
+    def run(self, stream, want_others=False, threshold=128, timing=None):
+        """frames (self.frames, uint8 BGR) -> self.logits / self.bits (and text_logit / rec when asked).
+        timing: optional list; gets (op_index, start_event, end_event) per conv GEMM launch (CUDA events on the
+        launching stream, which must be torch's current stream)."""
         lib, B, H, W = _lib.lib(), self.B, self.H, self.W
         st = ctypes.c_void_p(stream)
         chk = _lib.check
         chk(lib.am_fcn_prep_input(self.frames.data_ptr(), B, H, W, self.x0.ptr, self.x0.C, self.x0.pad, st), "am_fcn_prep_input")
-        for kind, a in self.ops:
+        for i, (kind, a) in enumerate(self.ops):
             if kind == "conv":
+                if timing is not None:
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
                 chk(lib.am_conv_gemm(ctypes.byref(a), st), "am_conv_gemm")
+                if timing is not None:
+                    e1.record()
+                    timing.append((i, e0, e1))
             elif kind == "pool":
                 src, dst = a
                 chk(lib.am_fcn_maxpool2(src.ptr, B, src.H, src.W, src.C, src.pad, dst.ptr, dst.pad, st), "am_fcn_maxpool2")
