@@ -120,9 +120,20 @@ typedef struct am_conv_desc {
     int out_sx, out_padx, out_coff;/* pixel stride (channels), left pad (pixels), channel offset */
     int Cout, Sy, Sx;              /* GEMM column n = ((sy*Sx)+sx)*Cout + co  ->  pixel (Sy*y+sy, Sx*r+sx), channel co */
     int act;                       /* 0 = none, 1 = exact-erf GELU */
+    int flags;                     /* AM_CONV_* tuning overrides (0 = let the library choose) */
 } am_conv_desc;
+#define AM_CONV_NO_RESIDENT 1      /* always stream the weights through the B ring */
+#define AM_CONV_NO_MT2 2           /* one M-tile per work item even when two would share the weight tiles */
 
+/* one launch: encodes the tensor maps, picks the tiling and runs the persistent tcgen05 kernel */
 int am_conv_gemm(const am_conv_desc* desc, void* stream);
+/* prepared form: tensor maps / tiling computed once per layer (needs a CUDA device), then launched many times */
+typedef struct am_conv_plan am_conv_plan;
+am_conv_plan* am_conv_plan_create(const am_conv_desc* desc);
+void am_conv_plan_destroy(am_conv_plan* plan);
+int am_conv_plan_launch(const am_conv_plan* plan, void* stream);
+/* info[8] = M-tiles per work item, resident weights (0/1), accumulator stages, A stages, B stages, grid, smem bytes, work items */
+int am_conv_plan_info(const am_conv_plan* plan, int* info);
 
 /* uint8 BGR frames [B][H][W][3] -> normalised bf16 RGB (x/255-0.5)/0.5 in buf[B][H][W+2*pad][C] (channels >= 3 zero).
  * Replaces cv2.cvtColor + TF.to_tensor + TF.normalize (FCN_lecturenet_binarizer.py:50, FCN_lecturenet.py:607-618). */

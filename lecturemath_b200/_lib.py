@@ -35,6 +35,10 @@ SIGNATURES = {
     "am_est_export": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "am_est_import": (c_int, [c_void_p, c_int, c_int, c_int, c_ull, c_void_p, c_void_p, c_ll, c_void_p]),
     "am_conv_gemm": (c_int, [c_void_p, c_void_p]),
+    "am_conv_plan_create": (c_void_p, [c_void_p]),
+    "am_conv_plan_destroy": (None, [c_void_p]),
+    "am_conv_plan_launch": (c_int, [c_void_p, c_void_p]),
+    "am_conv_plan_info": (c_int, [c_void_p, c_void_p]),
     "am_fcn_prep_input": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
     "am_fcn_maxpool2": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "am_fcn_fill_border": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),

@@ -14,6 +14,17 @@ def unpack_crop(words, min_x, max_x, min_y, max_y):
     return np.ascontiguousarray(bits[:, x0:x0 + (max_x - min_x + 1)]) * np.uint8(255)
 
 
+def pack_crop(img, min_x, max_x, min_y, max_y):
+    """uint8 (h, w) crop (nonzero = ink) -> bit-packed word-aligned uint32[h*cw], bits at their absolute x position
+    (the layout K-crop writes and K-match ANDs, csrc/cc_kernels.cu)."""
+    h = max_y - min_y + 1
+    cw = (max_x >> 5) - (min_x >> 5) + 1
+    bits = np.zeros((h, cw * 32), dtype=np.uint8)
+    x0 = min_x - ((min_x >> 5) << 5)
+    bits[:, x0:x0 + (max_x - min_x + 1)] = (np.asarray(img) != 0)
+    return np.packbits(bits, axis=1, bitorder="little").view("<u4").reshape(-1).copy()
+
+
 class ConnectedComponent:
     def __init__(self, cc_id, min_x, max_x, min_y, max_y, size, img=None, packed=None):
         self.cc_id = cc_id

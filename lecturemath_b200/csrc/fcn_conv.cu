@@ -18,12 +18,21 @@
 //   The vertical halo is loaded once per K chunk: the A box has YT+KH-1 rows and tap dy just offsets the
 //   UMMA descriptor by dy*RT rows (RT multiple of 8 keeps the 1024-byte swizzle atom aligned).
 //
-// CTA = 6 warps: warp0 TMA producer, warp1 TMEM owner + MMA issuer, warps2-5 epilogue (one TMEM lane
-// quarter each).  Two smem rings: A boxes (per K chunk) and B tiles (per K chunk x dy).
+// Execution model (v2): PERSISTENT CTAs (grid = min(work items, SM count)), 10 warps:
+//   warp 0      TMA producer (A boxes per K chunk; B tiles per (chunk, dy) unless the weights are resident)
+//   warp 1      TMEM owner + single-thread tcgen05.mma issuer
+//   warps 2..9  epilogue: two warps per TMEM lane quarter, alternating 16-column groups
+// A work item = MT (1 or 2) M-tiles of 128 GEMM rows x one N block of NT columns.  MT = 2 shares every B tile
+// between two accumulators (halves the L2->smem weight traffic of the streamed mode).  Weights that fit in
+// shared memory are loaded ONCE per CTA ("resident B") and the B ring disappears.  Accumulators are double
+// buffered in TMEM when 2*MT*NTc <= 512 columns so the epilogue of tile i overlaps the main loop of tile i+1.
 #include "am_common.cuh"
 #include "../../include/accessmath_b200.h"
 #include <cuda.h>
 #include <cuda_bf16.h>
+
+#define CONV_THREADS 320
+#define EPI_WARPS 8
 
 struct alignas(64) ConvParams {
     CUtensorMap tmA[2];
@@ -34,11 +43,13 @@ struct alignas(64) ConvParams {
     int seg_klast[2];    // valid K (multiple of 16) of the last chunk
     int seg_c1step[2];   // coordinate-1 step per kx (0 in row-run mode)
     int seg_c1off[2];    // coordinate-1 offset
-    int KH, RT, YT, padY;
-    int nRT, nYT;        // tiles per row / per frame column
+    int KH, RT, YT, padY, logRT;
+    int nRT, nYT, batch; // tiles per row / per frame column, frames
     int nR, Hin;         // valid groups per row, valid rows
-    int NT;              // UMMA N of this launch
-    int Ntot_pad;        // rows per (chunk,dy) block of the packed weights
+    int NT, NTc;         // UMMA N of this launch, TMEM columns per accumulator (power of two >= NT)
+    int Ntot_pad, nNB;   // rows per (chunk,dy) block of the packed weights, N blocks
+    int MT, acc_stages, residentB, total_chunks;
+    int n_mtiles, n_work;
     int tmem_cols;
     int stagesA, stagesB;
     // epilogue
@@ -46,6 +57,7 @@ struct alignas(64) ConvParams {
     int out_H, out_W;
     long long out_sn, out_sy; int out_sx, out_padx, out_coff;
     int Cout, Sy, Sx, Ntot, act;
+    unsigned cout_magic;  // floor(2^32 / Cout) + 1 (Cout >= 2)
     const float* bias;
 };
 
@@ -57,6 +69,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
     for (uint32_t it = 0; !done; ++it) {
@@ -65,7 +80,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.b32 %0, 1, 0, p;\n\t}"
             : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        if (it > (1u << 26)) { printf("[accessmath_b200] mbarrier timeout (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x); __trap(); }
+        if (it > (1u << 26)) { printf("[accessmath_b200] mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
     }
 }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
@@ -77,6 +92,9 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(dst), "l"((unsigned long long)tm), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((unsigned long long)tm) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -99,45 +117,77 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
     d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
     return d;
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+// 16 consecutive fp32 accumulator columns of this thread's TMEM lane (asynchronous: tmem_wait before use)
+__device__ __forceinline__ void tmem_ld16_async(uint32_t taddr, uint32_t* v) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
           "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
         : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// wait for outstanding tcgen05.ld; the registers are in/out operands so no use of them can be hoisted above the wait
+__device__ __forceinline__ void tmem_wait16(uint32_t* v) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+                   "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+                 :: "memory");
+}
 
-__global__ void __launch_bounds__(192, 1) k_conv_gemm(const __grid_constant__ ConvParams p) {
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // carve: [A ring][B ring][barriers][tmem ptr]
-    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t bytesA = (uint32_t)(p.YT + p.KH - 1) * p.RT * 128u;
-    const uint32_t bytesB = (uint32_t)p.NT * 128u;
-    const uint32_t sA0 = smem_base;
-    const uint32_t sB0 = sA0 + bytesA * p.stagesA;             // bytesA multiple of 1024 (RT % 8 == 0)
-    const uint32_t bar0 = sB0 + ((bytesB * p.stagesB + 1023u) & ~1023u);
-    // barriers: fullA[sA], emptyA[sA], fullB[sB], emptyB[sB], accum
-    const uint32_t fullA = bar0, emptyA = fullA + 8 * p.stagesA, fullB = emptyA + 8 * p.stagesA, emptyB = fullB + 8 * p.stagesB;
-    const uint32_t accum = emptyB + 8 * p.stagesB;
-    const uint32_t tmem_slot = accum + 8;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+// nn.GELU() (exact-erf form): 0.5*x*(1+erf(x/sqrt 2)).  erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far
+// below the bf16 rounding of the stored activation); branch free, two MUFU ops (rcp, ex2).
+__device__ __forceinline__ float gelu_erf(float x) {
+    const float ax = fabsf(x) * 0.70710678118654752f;
+    float t;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.0f)));
+    float pl = fmaf(1.061405429f, t, -1.453152027f);
+    pl = fmaf(pl, t, 1.421413741f);
+    pl = fmaf(pl, t, -0.284496736f);
+    pl = fmaf(pl, t, 0.254829592f);
+    pl *= t;
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(ax * ax * -1.4426950408889634f));
+    const float erf_abs = fmaf(-pl, e, 1.0f);
+    const float hx = 0.5f * x;
+    return fmaf(fabsf(hx), erf_abs, hx);             // 0.5x + 0.5|x| erf(|x|/sqrt2) == 0.5x(1 + erf(x/sqrt2))
+}
 
-    // tile coordinates
-    int t = blockIdx.x;
+struct TileCoord { int frame, y0, r0; bool valid; };
+__device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int t) {
+    TileCoord c;
+    c.valid = t < p.n_mtiles;
+    if (!c.valid) t = p.n_mtiles - 1;                // duplicate the last tile: loads stay in bounds, stores are skipped
     const int rt = t % p.nRT; t /= p.nRT;
-    const int yt = t % p.nYT; const int frame = t / p.nYT;
-    const int r0 = rt * p.RT, y0 = yt * p.YT, n0 = blockIdx.y * p.NT;
+    const int yt = t % p.nYT;
+    c.frame = t / p.nYT; c.y0 = yt * p.YT; c.r0 = rt * p.RT;
+    return c;
+}
 
-    int total_chunks = 0;
-    for (int s = 0; s < p.nseg; ++s) total_chunks += p.seg_nkx[s] * p.seg_nck[s];
+__global__ void __launch_bounds__(CONV_THREADS, 1) k_conv_gemm(const __grid_constant__ ConvParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // carve: [A ring][B ring | resident B][bias][barriers][tmem ptr]
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bytesA1 = (uint32_t)(p.YT + p.KH - 1) * p.RT * 128u;    // one M-tile box (multiple of 1024: RT % 8 == 0)
+    const uint32_t bytesA = bytesA1 * p.MT;
+    const uint32_t bytesB = (uint32_t)p.NT * 128u;
+    const uint32_t nB = p.residentB ? (uint32_t)(p.total_chunks * p.KH) : (uint32_t)p.stagesB;
+    const uint32_t sA0 = smem_base;
+    const uint32_t sB0 = sA0 + bytesA * p.stagesA;
+    const uint32_t sBias = sB0 + ((bytesB * nB + 1023u) & ~1023u);
+    const uint32_t bar0 = sBias + (((uint32_t)p.NT * 4u + 127u) & ~127u);
+    // barriers: fullA[sA], emptyA[sA], fullB[sB], emptyB[sB], accFull[2], accEmpty[2]
+    const uint32_t fullA = bar0, emptyA = fullA + 8 * p.stagesA, fullB = emptyA + 8 * p.stagesA, emptyB = fullB + 8 * p.stagesB;
+    const uint32_t accFull = emptyB + 8 * p.stagesB, accEmpty = accFull + 16;
+    const uint32_t tmem_slot = accEmpty + 16;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < p.stagesA; ++i) { mbar_init(fullA + 8 * i, 1); mbar_init(emptyA + 8 * i, 1); }
         for (int i = 0; i < p.stagesB; ++i) { mbar_init(fullB + 8 * i, 1); mbar_init(emptyB + 8 * i, 1); }
-        mbar_init(accum, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(accFull + 8 * i, 1); mbar_init(accEmpty + 8 * i, EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        tma_prefetch_desc(&p.tmA[0]);
+        if (p.nseg > 1) tma_prefetch_desc(&p.tmA[1]);
+        tma_prefetch_desc(&p.tmB);
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)p.tmem_cols) : "memory");
@@ -153,21 +203,35 @@ __global__ void __launch_bounds__(192, 1) k_conv_gemm(const __grid_constant__ Co
         // ===================== TMA producer =====================
         if (lane == 0) {
             int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
-            int chunk = 0;
-            for (int s = 0; s < p.nseg; ++s) {
-                const CUtensorMap* tm = &p.tmA[s];
-                for (int kx = 0; kx < p.seg_nkx[s]; ++kx) {
-                    for (int ck = 0; ck < p.seg_nck[s]; ++ck, ++chunk) {
-                        mbar_wait(emptyA + 8 * sa, pa ^ 1);
-                        mbar_expect_tx(fullA + 8 * sa, bytesA);
-                        tma_load_4d(sA0 + bytesA * sa, tm, fullA + 8 * sa, ck * 64, r0 + p.seg_c1off[s] + kx * p.seg_c1step[s],
-                                    y0 - p.padY, frame);
-                        if (++sa == p.stagesA) { sa = 0; pa ^= 1; }
-                        for (int dy = 0; dy < p.KH; ++dy) {
-                            mbar_wait(emptyB + 8 * sb, pb ^ 1);
-                            mbar_expect_tx(fullB + 8 * sb, bytesB);
-                            tma_load_2d(sB0 + bytesB * sb, &p.tmB, fullB + 8 * sb, 0, (chunk * p.KH + dy) * p.Ntot_pad + n0);
-                            if (++sb == p.stagesB) { sb = 0; pb ^= 1; }
+            if (p.residentB) {                           // all weight tiles once (single N block): fullB[0] collects them
+                mbar_expect_tx(fullB, bytesB * nB);
+                for (uint32_t i = 0; i < nB; ++i) tma_load_2d(sB0 + bytesB * i, &p.tmB, fullB, 0, (int)i * p.Ntot_pad);
+            }
+            for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
+                const int st = w / p.nNB, nb = w - st * p.nNB;
+                const int n0 = nb * p.NT;
+                TileCoord tc[2];
+                tc[0] = decode_tile(p, st * p.MT);
+                tc[1] = decode_tile(p, st * p.MT + (p.MT - 1));
+                int chunk = 0;
+                for (int s = 0; s < p.nseg; ++s) {
+                    const CUtensorMap* tm = &p.tmA[s];
+                    for (int kx = 0; kx < p.seg_nkx[s]; ++kx) {
+                        for (int ck = 0; ck < p.seg_nck[s]; ++ck, ++chunk) {
+                            mbar_wait(emptyA + 8 * sa, pa ^ 1);
+                            mbar_expect_tx(fullA + 8 * sa, bytesA);
+                            for (int mt = 0; mt < p.MT; ++mt)
+                                tma_load_4d(sA0 + bytesA * sa + bytesA1 * mt, tm, fullA + 8 * sa, ck * 64,
+                                            tc[mt].r0 + p.seg_c1off[s] + kx * p.seg_c1step[s], tc[mt].y0 - p.padY, tc[mt].frame);
+                            if (++sa == p.stagesA) { sa = 0; pa ^= 1; }
+                            if (!p.residentB) {
+                                for (int dy = 0; dy < p.KH; ++dy) {
+                                    mbar_wait(emptyB + 8 * sb, pb ^ 1);
+                                    mbar_expect_tx(fullB + 8 * sb, bytesB);
+                                    tma_load_2d(sB0 + bytesB * sb, &p.tmB, fullB + 8 * sb, 0, (chunk * p.KH + dy) * p.Ntot_pad + n0);
+                                    if (++sb == p.stagesB) { sb = 0; pb ^= 1; }
+                                }
+                            }
                         }
                     }
                 }
@@ -178,87 +242,155 @@ __global__ void __launch_bounds__(192, 1) k_conv_gemm(const __grid_constant__ Co
         if (lane == 0) {
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NT >> 3) << 17) | ((128u >> 4) << 24);
             int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
-            uint32_t acc = 0;
-            for (int s = 0; s < p.nseg; ++s) {
-                for (int kx = 0; kx < p.seg_nkx[s]; ++kx) {
-                    for (int ck = 0; ck < p.seg_nck[s]; ++ck) {
-                        const int ksteps = ((ck == p.seg_nck[s] - 1) ? p.seg_klast[s] : 64) >> 4;
-                        mbar_wait(fullA + 8 * sa, pa);
-                        for (int dy = 0; dy < p.KH; ++dy) {
-                            mbar_wait(fullB + 8 * sb, pb);
+            int as = 0; uint32_t pacc = 0;
+            if (p.residentB) { mbar_wait(fullB, 0); tc_fence_after(); }
+            for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
+                mbar_wait(accEmpty + 8 * as, pacc ^ 1);                  // epilogue drained this accumulator stage
+                tc_fence_after();
+                const uint32_t tacc = tmem_base + (uint32_t)(as * p.MT * p.NTc);
+                uint32_t acc = 0;
+                int chunk = 0;
+                for (int s = 0; s < p.nseg; ++s) {
+                    for (int kx = 0; kx < p.seg_nkx[s]; ++kx) {
+                        for (int ck = 0; ck < p.seg_nck[s]; ++ck, ++chunk) {
+                            const int ksteps = ((ck == p.seg_nck[s] - 1) ? p.seg_klast[s] : 64) >> 4;
+                            mbar_wait(fullA + 8 * sa, pa);
                             tc_fence_after();
-                            const uint32_t a_addr = sA0 + bytesA * sa + (uint32_t)dy * p.RT * 128u;
-                            const uint32_t b_addr = sB0 + bytesB * sb;
-                            for (int k = 0; k < ksteps; ++k) {
-                                tc_mma_bf16(tmem_base, make_desc_sw128(a_addr + k * 32), make_desc_sw128(b_addr + k * 32), idesc, acc);
+                            for (int dy = 0; dy < p.KH; ++dy) {
+                                uint32_t b_addr;
+                                if (p.residentB) b_addr = sB0 + bytesB * (uint32_t)(chunk * p.KH + dy);
+                                else { mbar_wait(fullB + 8 * sb, pb); tc_fence_after(); b_addr = sB0 + bytesB * sb; }
+                                for (int mt = 0; mt < p.MT; ++mt) {
+                                    const uint32_t a_addr = sA0 + bytesA * sa + bytesA1 * mt + (uint32_t)dy * p.RT * 128u;
+                                    for (int k = 0; k < ksteps; ++k)
+                                        tc_mma_bf16(tacc + (uint32_t)(mt * p.NTc), make_desc_sw128(a_addr + k * 32), make_desc_sw128(b_addr + k * 32),
+                                                    idesc, acc | (uint32_t)k);
+                                }
                                 acc = 1;
+                                if (!p.residentB) { tc_commit(emptyB + 8 * sb); if (++sb == p.stagesB) { sb = 0; pb ^= 1; } }
                             }
-                            tc_commit(emptyB + 8 * sb);
-                            if (++sb == p.stagesB) { sb = 0; pb ^= 1; }
+                            tc_commit(emptyA + 8 * sa);
+                            if (++sa == p.stagesA) { sa = 0; pa ^= 1; }
                         }
-                        tc_commit(emptyA + 8 * sa);
-                        if (++sa == p.stagesA) { sa = 0; pa ^= 1; }
                     }
                 }
+                tc_commit(accFull + 8 * as);
+                if (++as == p.acc_stages) { as = 0; pacc ^= 1; }
             }
-            tc_commit(accum);
         }
     } else {
-        // ===================== epilogue (warps 2..5) =====================
+        // ===================== epilogue (warps 2..9) =====================
         const int q = warp & 3;                          // TMEM lane quarter this warp may access
+        const int h = (warp - 2) >> 2;                   // which half of the 16-column groups
         const int m = q * 32 + lane;
-        const int yy = m / p.RT, rr = m % p.RT;
-        const int y = y0 + yy, r = r0 + rr;
-        const bool row_ok = (y < p.Hin) && (r < p.nR);
-        mbar_wait(accum, 0);
-        tc_fence_after();
-        const bool vec8 = (p.Cout % 8) == 0;
-        for (int j0 = 0; j0 < p.NT; j0 += 16) {
-            uint32_t v[16];
-            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)j0, v);
-            if (!row_ok) continue;
-            if (vec8) {
+        const int yy = m >> p.logRT, rr = m & (p.RT - 1);
+        // bias of this CTA's N block -> smem (reloaded per work item only when there are several N blocks)
+        float* sbias = (float*)(smem_raw + (sBias - smem_u32(smem_raw)));
+        int bias_nb = -1;
+        int as = 0; uint32_t pacc = 0;
+        const int units_per_tile = p.NT >> 4;
+        const int units = units_per_tile * p.MT;
+        const bool vec8 = (p.Cout & 7) == 0 && !p.out_f32;
+        for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
+            const int st = w / p.nNB, nb = w - st * p.nNB;
+            const int n0 = nb * p.NT;
+            if (nb != bias_nb) {
+                asm volatile("bar.sync 1, %0;" ::"r"(EPI_WARPS * 32));     // everyone finished reading the previous bias
+                for (int i = threadIdx.x - 64; i < p.NT; i += EPI_WARPS * 32) sbias[i] = __ldg(p.bias + n0 + i);
+                asm volatile("bar.sync 1, %0;" ::"r"(EPI_WARPS * 32));
+                bias_nb = nb;
+            }
+            mbar_wait(accFull + 8 * as, pacc);
+            tc_fence_after();
+            const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.MT * p.NTc);
+            uint32_t va[16], vb[16];
+            int g = h;
+            if (g < units) {
+                const int mt = g / units_per_tile, u = g - mt * units_per_tile;
+                tmem_ld16_async(tacc + (uint32_t)(mt * p.NTc + u * 16), va);
+            }
+            int cur_mt = -1;
+            bool row_ok = false;
+            long long base = 0;
+            for (; g < units; g += 2) {
+                const int mt = g / units_per_tile, u = g - mt * units_per_tile;
+                tmem_wait16(va);
 #pragma unroll
-                for (int g = 0; g < 2; ++g) {
-                    const int n = n0 + j0 + g * 8;
-                    if (n >= p.Ntot) continue;
-                    const int grp = n / p.Cout, co = n - grp * p.Cout;
-                    const int sy = grp / p.Sx, sx = grp - sy * p.Sx;
-                    const int oy = p.Sy * y + sy, ox = p.Sx * r + sx;
-                    if (oy >= p.out_H || ox >= p.out_W) continue;
-                    const long long off = (long long)frame * p.out_sn + (long long)oy * p.out_sy + (long long)(ox + p.out_padx) * p.out_sx + p.out_coff + co;
-                    float f[8];
+                for (int i = 0; i < 16; ++i) vb[i] = va[i];
+                if (g + 2 < units) {
+                    const int mt2 = (g + 2) / units_per_tile, u2 = (g + 2) - mt2 * units_per_tile;
+                    tmem_ld16_async(tacc + (uint32_t)(mt2 * p.NTc + u2 * 16), va);
+                }
+                if (mt != cur_mt) {
+                    cur_mt = mt;
+                    const TileCoord tc = decode_tile(p, st * p.MT + mt);
+                    const int y = tc.y0 + yy, r = tc.r0 + rr;
+                    row_ok = tc.valid && (y < p.Hin) && (r < p.nR);
+                    base = (long long)tc.frame * p.out_sn + (long long)(p.Sy * y) * p.out_sy + (long long)(p.Sx * r + p.out_padx) * p.out_sx + p.out_coff;
+                    if (p.Sy * y + p.Sy > p.out_H || p.Sx * r + p.Sx > p.out_W) row_ok = false;   // never true for the FCN's shapes
+                }
+                if (!row_ok) continue;
+                const int j0 = u * 16;
+                if (vec8) {
+                    // two 8-channel groups; a group never straddles a pixel because Cout % 8 == 0
+                    uint4 pk[2]; long long offs[2]; bool ok[2];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        float x = __uint_as_float(v[g * 8 + i]) + __ldg(p.bias + n + i);
-                        f[i] = p.act == 1 ? gelu_erf(x) : x;
-                    }
-                    if (p.out_f32) {
-                        float4* o = (float4*)((float*)p.out + off);
-                        o[0] = make_float4(f[0], f[1], f[2], f[3]); o[1] = make_float4(f[4], f[5], f[6], f[7]);
-                    } else {
+                    for (int gg = 0; gg < 2; ++gg) {
+                        const int n = n0 + j0 + gg * 8;
+                        ok[gg] = n < p.Ntot;
+                        const int grp = (int)__umulhi((unsigned)n, p.cout_magic), co = n - grp * p.Cout;
+                        const int sy = (p.Sy == 2 && grp >= p.Sx) ? 1 : 0, sx = grp - sy * p.Sx;
+                        offs[gg] = base + (long long)sy * p.out_sy + (long long)sx * p.out_sx + co;
+                        float f[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            float x = __uint_as_float(vb[gg * 8 + i]) + sbias[j0 + gg * 8 + i];
+                            f[i] = p.act == 1 ? gelu_erf(x) : x;
+                        }
                         __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]), h1 = __floats2bfloat162_rn(f[2], f[3]);
                         __nv_bfloat162 h2 = __floats2bfloat162_rn(f[4], f[5]), h3 = __floats2bfloat162_rn(f[6], f[7]);
-                        uint4 u;
-                        u.x = *(uint32_t*)&h0; u.y = *(uint32_t*)&h1; u.z = *(uint32_t*)&h2; u.w = *(uint32_t*)&h3;
-                        *(uint4*)((__nv_bfloat16*)p.out + off) = u;
+                        pk[gg].x = *(uint32_t*)&h0; pk[gg].y = *(uint32_t*)&h1; pk[gg].z = *(uint32_t*)&h2; pk[gg].w = *(uint32_t*)&h3;
+                    }
+                    __nv_bfloat16* o = (__nv_bfloat16*)p.out;
+                    if (ok[0] && ok[1] && offs[1] == offs[0] + 8 && ((offs[0] & 15) == 0)) {
+                        // 32 contiguous, 32-byte aligned bytes: one full sector per thread (STG.256)
+                        asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(o + offs[0]), "r"(pk[0].x), "r"(pk[0].y), "r"(pk[0].z),
+                                     "r"(pk[0].w), "r"(pk[1].x), "r"(pk[1].y), "r"(pk[1].z), "r"(pk[1].w) : "memory");
+                    } else {
+                        if (ok[0]) *(uint4*)(o + offs[0]) = pk[0];
+                        if (ok[1]) *(uint4*)(o + offs[1]) = pk[1];
+                    }
+                } else if (p.out_f32 && p.out_sx == p.Cout && p.Sy == 1 && p.out_coff == 0 && ((p.Ntot | (int)p.out_sy | (int)p.out_sn) & 3) == 0) {
+                    // fp32 heads / logits: the row's N columns are contiguous in memory (n = sx*Cout + co)
+                    float* o = (float*)p.out + base + n0 + j0;
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4) {
+                        if (n0 + j0 + i >= p.Ntot) break;
+                        float4 f;
+                        f.x = __uint_as_float(vb[i]) + sbias[j0 + i]; f.y = __uint_as_float(vb[i + 1]) + sbias[j0 + i + 1];
+                        f.z = __uint_as_float(vb[i + 2]) + sbias[j0 + i + 2]; f.w = __uint_as_float(vb[i + 3]) + sbias[j0 + i + 3];
+                        if (p.act == 1) { f.x = gelu_erf(f.x); f.y = gelu_erf(f.y); f.z = gelu_erf(f.z); f.w = gelu_erf(f.w); }
+                        *(float4*)(o + i) = f;
+                    }
+                } else {
+                    for (int i = 0; i < 16; ++i) {
+                        const int n = n0 + j0 + i;
+                        if (n >= p.Ntot) break;
+                        const int grp = n / p.Cout, co = n - grp * p.Cout;
+                        const int sy = grp / p.Sx, sx = grp - sy * p.Sx;
+                        const long long off = base + (long long)sy * p.out_sy + (long long)sx * p.out_sx + co;
+                        float x = __uint_as_float(vb[i]) + sbias[j0 + i];
+                        x = p.act == 1 ? gelu_erf(x) : x;
+                        if (p.out_f32) ((float*)p.out)[off] = x;
+                        else ((__nv_bfloat16*)p.out)[off] = __float2bfloat16_rn(x);
                     }
                 }
-            } else {
-                for (int i = 0; i < 16; ++i) {
-                    const int n = n0 + j0 + i;
-                    if (n >= p.Ntot) break;
-                    const int grp = n / p.Cout, co = n - grp * p.Cout;
-                    const int sy = grp / p.Sx, sx = grp - sy * p.Sx;
-                    const int oy = p.Sy * y + sy, ox = p.Sx * r + sx;
-                    if (oy >= p.out_H || ox >= p.out_W) continue;
-                    const long long off = (long long)frame * p.out_sn + (long long)oy * p.out_sy + (long long)(ox + p.out_padx) * p.out_sx + p.out_coff + co;
-                    float x = __uint_as_float(v[i]) + __ldg(p.bias + n);
-                    x = p.act == 1 ? gelu_erf(x) : x;
-                    if (p.out_f32) ((float*)p.out)[off] = x;
-                    else ((__nv_bfloat16*)p.out)[off] = __float2bfloat16_rn(x);
-                }
             }
+            // all tcgen05.ld of this stage have completed (tmem_wait16 in the last iteration): hand the stage back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(accEmpty + 8 * as);
+            if (++as == p.acc_stages) { as = 0; pacc ^= 1; }
         }
         tc_fence_before();
     }
@@ -303,11 +435,27 @@ static int encode_map(CUtensorMap* tm, void* base, int rank, const unsigned long
     return AM_OK;
 }
 
-// One convolution-as-GEMM launch.  Everything the kernel needs is in this plain-C descriptor (see header).
-extern "C" int am_conv_gemm(const am_conv_desc* d, void* stream) {
-    if (!d || d->nseg < 1 || d->nseg > 2 || d->RT % 8 != 0 || d->RT * d->YT != 128 || d->NT % 16 != 0 || d->NT < 16 || d->NT > 256)
-        return AM_ERR_ARG;
+struct am_conv_plan {
     ConvParams p;
+    size_t smem;
+    int grid;
+};
+
+static int sm_count() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
+// Fills a launch plan from the plain-C descriptor: tensor maps, tiling, smem/TMEM budget.
+static int conv_prepare(const am_conv_desc* d, am_conv_plan* plan) {
+    if (!d || d->nseg < 1 || d->nseg > 2 || d->RT % 8 != 0 || (d->RT & (d->RT - 1)) != 0 || d->RT * d->YT != 128 || d->NT % 16 != 0 ||
+        d->NT < 16 || d->NT > 256 || d->batch <= 0 || d->Ntot_pad % d->NT != 0)
+        return AM_ERR_ARG;
+    ConvParams& p = plan->p;
     memset(&p, 0, sizeof(p));
     p.nseg = d->nseg;
     const int box_rows = d->YT + d->KH - 1;
@@ -345,32 +493,89 @@ extern "C" int am_conv_gemm(const am_conv_desc* d, void* stream) {
         if (rc) return rc;
     }
     p.KH = d->KH; p.RT = d->RT; p.YT = d->YT; p.padY = d->padY;
-    p.nRT = (d->nR + d->RT - 1) / d->RT; p.nYT = (d->Hin + d->YT - 1) / d->YT;
-    p.nR = d->nR; p.Hin = d->Hin; p.NT = d->NT; p.Ntot_pad = d->Ntot_pad;
-    p.tmem_cols = 32; while (p.tmem_cols < d->NT) p.tmem_cols <<= 1;
+    p.logRT = 0; while ((1 << p.logRT) < d->RT) ++p.logRT;
+    p.nRT = (d->nR + d->RT - 1) / d->RT; p.nYT = (d->Hin + d->YT - 1) / d->YT; p.batch = d->batch;
+    p.nR = d->nR; p.Hin = d->Hin; p.NT = d->NT; p.Ntot_pad = d->Ntot_pad; p.nNB = d->Ntot_pad / d->NT;
+    p.NTc = 32; while (p.NTc < d->NT) p.NTc <<= 1;
+    p.total_chunks = total_chunks;
+    p.n_mtiles = p.nRT * p.nYT * d->batch;
     p.out = d->out; p.out_f32 = d->out_f32; p.out_H = d->out_H; p.out_W = d->out_W;
     p.out_sn = d->out_sn; p.out_sy = d->out_sy; p.out_sx = d->out_sx; p.out_padx = d->out_padx; p.out_coff = d->out_coff;
     p.Cout = d->Cout; p.Sy = d->Sy; p.Sx = d->Sx; p.Ntot = d->Ntot; p.act = d->act; p.bias = d->bias;
-    // shared memory budget: A ring + B ring + barriers
-    const size_t bytesA = (size_t)box_rows * d->RT * 128, bytesB = (size_t)d->NT * 128;
-    const size_t budget = 200 * 1024;
-    int sa = 2, sb = 2;
-    while (true) {      // grow the rings alternately while they fit; B stages are consumed KH times faster
-        bool grew = false;
-        if (sb < 3 * d->KH && sb < 12 && bytesA * sa + bytesB * (sb + 1) + 2048 <= budget) { ++sb; grew = true; }
-        if (sa < 4 && bytesA * (sa + 1) + bytesB * sb + 2048 <= budget) { ++sa; grew = true; }
-        if (!grew) break;
+    p.cout_magic = d->Cout >= 2 ? (unsigned)((1ull << 32) / (unsigned long long)d->Cout) + 1u : 0u;
+    if (d->Sy < 1 || d->Sy > 2 || d->Sx < 1) return AM_ERR_ARG;
+
+    // ---- shared-memory / TMEM budget -------------------------------------------------------------------
+    const size_t bytesA1 = (size_t)box_rows * d->RT * 128, bytesB = (size_t)d->NT * 128;
+    const size_t fixed = 1024 /*align*/ + 1024 /*bias (<= 256 floats)*/ + 512 /*barriers*/;
+    const size_t budget = 226 * 1024;
+    const size_t allB = bytesB * (size_t)total_chunks * d->KH;
+    // resident weights: single N block and the whole packed filter + >= 3 A stages fit
+    int resident = (d->flags & AM_CONV_NO_RESIDENT) ? 0 : (p.nNB == 1 && fixed + allB + 3 * bytesA1 <= budget);
+    int MT = 1;
+    if (!resident && !(d->flags & AM_CONV_NO_MT2) && p.n_mtiles * p.nNB >= 2 * sm_count() * 2 && 2 * p.NTc <= 512) MT = 2;
+    int sa, sb;
+    if (resident) {
+        sb = 1; sa = 3;
+        while (sa < 8 && fixed + allB + (size_t)(sa + 1) * bytesA1 <= budget) ++sa;
+    } else {
+        sa = 2; sb = 2;
+        while (true) {      // grow the rings alternately while they fit; B stages are consumed KH times faster
+            bool grew = false;
+            if (sb < 3 * d->KH && sb < 12 && fixed + bytesA1 * MT * sa + bytesB * (sb + 1) <= budget) { ++sb; grew = true; }
+            if (sa < 4 && fixed + bytesA1 * MT * (sa + 1) + bytesB * sb <= budget) { ++sa; grew = true; }
+            if (!grew) break;
+        }
+        if (fixed + bytesA1 * MT * sa + bytesB * sb > budget) {
+            if (MT == 2) { MT = 1; sa = 2; sb = 2; }
+            if (fixed + bytesA1 * sa + bytesB * sb > budget) return AM_ERR_ARG;
+        }
     }
-    if (bytesA * sa + bytesB * sb + 2048 > 227 * 1024) return AM_ERR_ARG;
-    p.stagesA = sa; p.stagesB = sb;
-    const size_t smem = 1024 + bytesA * sa + ((bytesB * sb + 1023) & ~(size_t)1023) + 1024;
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
+    p.residentB = resident; p.MT = MT; p.stagesA = sa; p.stagesB = sb;
+    p.acc_stages = (2 * MT * p.NTc <= 512) ? 2 : 1;
+    p.tmem_cols = 32; while (p.tmem_cols < p.acc_stages * MT * p.NTc) p.tmem_cols <<= 1;
+    p.n_work = ((p.n_mtiles + MT - 1) / MT) * p.nNB;
+    const size_t nB = resident ? (size_t)total_chunks * d->KH : (size_t)sb;
+    plan->smem = 1024 + bytesA1 * MT * sa + ((bytesB * nB + 1023) & ~(size_t)1023) + 1024 + 512;
+    if (plan->smem > 227 * 1024) return AM_ERR_ARG;
+    plan->grid = p.n_work < sm_count() ? p.n_work : sm_count();
+    return AM_OK;
+}
+
+static int conv_launch(const am_conv_plan* plan, void* stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
         AM_CUDA(cudaFuncSetAttribute(k_conv_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
-        smem_set = 227 * 1024;
+        attr_set = true;
     }
-    dim3 grid((unsigned)(p.nRT * p.nYT * d->batch), (unsigned)(d->Ntot_pad / d->NT));
-    k_conv_gemm<<<grid, 192, smem, (cudaStream_t)stream>>>(p);
+    k_conv_gemm<<<plan->grid, CONV_THREADS, plan->smem, (cudaStream_t)stream>>>(plan->p);
     AM_CUDA(cudaGetLastError());
+    return AM_OK;
+}
+
+// One convolution-as-GEMM launch.  Everything the kernel needs is in this plain-C descriptor (see header).
+extern "C" int am_conv_gemm(const am_conv_desc* d, void* stream) {
+    am_conv_plan plan;
+    int rc = conv_prepare(d, &plan);
+    if (rc) return rc;
+    return conv_launch(&plan, stream);
+}
+
+// Prepared form: tensor maps and tiling are computed once per layer, launches reuse them.
+extern "C" am_conv_plan* am_conv_plan_create(const am_conv_desc* d) {
+    am_conv_plan* plan = new am_conv_plan();
+    if (conv_prepare(d, plan) != AM_OK) { delete plan; return nullptr; }
+    return plan;
+}
+extern "C" void am_conv_plan_destroy(am_conv_plan* plan) { delete plan; }
+extern "C" int am_conv_plan_launch(const am_conv_plan* plan, void* stream) {
+    if (!plan) return AM_ERR_ARG;
+    return conv_launch(plan, stream);
+}
+// info[8] = MT, residentB, acc_stages, stagesA, stagesB, grid, smem bytes, n_work
+extern "C" int am_conv_plan_info(const am_conv_plan* plan, int* info) {
+    if (!plan || !info) return AM_ERR_ARG;
+    info[0] = plan->p.MT; info[1] = plan->p.residentB; info[2] = plan->p.acc_stages; info[3] = plan->p.stagesA;
+    info[4] = plan->p.stagesB; info[5] = plan->grid; info[6] = (int)plan->smem; info[7] = plan->p.n_work;
     return AM_OK;
 }

@@ -74,7 +74,7 @@ class ConvDesc(ctypes.Structure):
                 ("out", ctypes.c_void_p), ("out_f32", ctypes.c_int), ("out_H", ctypes.c_int), ("out_W", ctypes.c_int),
                 ("out_sn", ctypes.c_longlong), ("out_sy", ctypes.c_longlong),
                 ("out_sx", ctypes.c_int), ("out_padx", ctypes.c_int), ("out_coff", ctypes.c_int),
-                ("Cout", ctypes.c_int), ("Sy", ctypes.c_int), ("Sx", ctypes.c_int), ("act", ctypes.c_int)]
+                ("Cout", ctypes.c_int), ("Sy", ctypes.c_int), ("Sx", ctypes.c_int), ("act", ctypes.c_int), ("flags", ctypes.c_int)]
 
 
 def fold_bn(w, b, bn_w, bn_b, mean, var, out_dim=0):
@@ -145,6 +145,35 @@ def pack_weights(w, bias, segs, S, rowrun, NT):
     return packed, b, ntot, ntot_pad
 
 
+SMEM_BUDGET = 226 * 1024
+L2_BYTES_PER_CLK_SM = 42.0        # ~6300 B/clk chip-wide L2->SM throughput / 148 SMs (B300_MICROARCH.md)
+EPI_CLK_PER_COL = 30.0            # epilogue cycles per accumulator column of a 128-row tile (8 warps, GELU)
+
+
+def layer_cost(nr, h, ntot, runs, kh, batch, n_sm=148):
+    """Cycle model of one 128-row M-tile of k_conv_gemm (see csrc/fcn_conv.cu) for GEMM width ntot and per-segment run
+    lengths `runs` (elements of K per vertical tap).  Mirrors conv_prepare()'s choices of resident weights / MT."""
+    nt = choose_nt(ntot)
+    ntot_pad = ((ntot + nt - 1) // nt) * nt
+    nnb = ntot_pad // nt
+    rt, yt = choose_tile(nr, h, kh)
+    chunks = sum((r + 63) // 64 for r in runs)
+    k16 = sum((r + 15) // 16 for r in runs) * kh
+    bytes_a = (yt + kh - 1) * rt * 128
+    bytes_b_all = chunks * kh * nt * 128
+    fixed = 2560
+    resident = nnb == 1 and fixed + bytes_b_all + 3 * bytes_a <= SMEM_BUDGET
+    n_mtiles = math.ceil(nr / rt) * math.ceil(h / yt) * batch
+    ntc = 32
+    while ntc < nt:
+        ntc *= 2
+    mt = 2 if (not resident and n_mtiles * nnb >= 4 * n_sm and 2 * ntc <= 512) else 1
+    mma = k16 * max(nt / 2.0, (4096 + 32 * nt) / 128.0)
+    l2 = (chunks * bytes_a + (0 if resident else chunks * kh * nt * 128 / mt)) / L2_BYTES_PER_CLK_SM
+    epi = EPI_CLK_PER_COL * nt
+    return {"clk": max(mma, l2, epi) * nnb, "mma": mma, "l2": l2, "epi": epi, "resident": resident, "mt": mt, "nt": nt}
+
+
 class _Buf:
     """NHWC bf16 activation buffer with physical zero padding in x."""
 
@@ -198,6 +227,7 @@ class FCNPlan:
         self.rec = torch.zeros((B, H, W, 3), dtype=torch.float32, device=device)
         self.wpr = self.lib.am_words_per_row(W)
         self.bits = torch.zeros((B, H, self.wpr), dtype=torch.int32, device=device)
+        self._cplans = {}       # op index -> am_conv_plan handle
         self.keep = []          # keeps packed weights alive
         self.ops = []           # (kind, payload)
         self.op_flops = {}      # op index -> algorithmic FLOPs per frame of that conv launch
@@ -213,11 +243,11 @@ class FCNPlan:
         for i in range(5):
             w, b = cbn("conv_down_block_%d" % (i + 1))
             cmap = [0, 1, 2] + [-1] * 5 if i == 0 else ident(src.C)
-            self._conv(w, b, [(src, cmap)], self.d[i], act=1, S=self._pick_s(ws[i], w.shape[0], src.C))
+            self._conv(w, b, [(src, cmap)], self.d[i], act=1)
             self.ops.append(("pool", (self.d[i], self.p[i])))
             src = self.p[i]
         w, b = cbn("mid_block")
-        self._conv(w, b, [(src, ident(src.C))], self.mid, act=1, S=1)
+        self._conv(w, b, [(src, ident(src.C))], self.mid, act=1)
         # decoder
         src = self.mid
         for lvl in range(4, -1, -1):
@@ -228,8 +258,7 @@ class FCNPlan:
             self._tconv(wt, bt, src, self.t[lvl])
             w, b = cbn("conv_up_block_%d" % (lvl + 1))
             cu = self.t[lvl].C
-            self._conv(w, b, [(self.t[lvl], ident(cu)), (self.d[lvl], [cu + c for c in range(self.d[lvl].C)])], self.u[lvl], act=1,
-                       S=self._pick_s(ws[lvl], w.shape[0], cu))
+            self._conv(w, b, [(self.t[lvl], ident(cu)), (self.d[lvl], [cu + c for c in range(self.d[lvl].C)])], self.u[lvl], act=1)
             src = self.u[lvl]
         # heads: text mask (pk x pk, 1 ch) and reconstruction (k x k, 3 ch) share one pk x pk GEMM with 4 columns
         wt_, bt_ = cbn("conv_text_mask_out")
@@ -239,18 +268,17 @@ class FCNPlan:
         o = (pk - k) // 2
         wh[1:4, :, o:o + k, o:o + k] = wr_
         f0 = self.flops
-        self._conv(wh, torch.cat([bt_, br_]), [(self.u[0], ident(upc[0]))], None, act=0, S=self._pick_s(W, 4, upc[0], cap=8), f32_out=self.heads)
+        self._conv(wh, torch.cat([bt_, br_]), [(self.u[0], ident(upc[0]))], None, act=0, cap=8, f32_out=self.heads)
         self.flops = f0 + 2 * H * W * upc[0] * (pk * pk + 3 * k * k)     # algorithmic: 7x7x1 + 3x3x3, not the padded GEMM
         self.op_flops[len(self.ops) - 1] = self.flops - f0
         self.ops.append(("heads_post", None))
         dmap = [0, 1, 2] + [-1] * 5
         w, b = cbn("conv_pixels_1")       # reference input order: (diff 0..2, x_up1)  (:383)
-        self._conv(w, b, [(self.u[0], [3 + c for c in range(upc[0])]), (self.diff, dmap)], self.px1, act=1, S=self._pick_s(W, pm1, upc[0]))
+        self._conv(w, b, [(self.u[0], [3 + c for c in range(upc[0])]), (self.diff, dmap)], self.px1, act=1)
         w, b = cbn("conv_pixels_2")
-        self._conv(w, b, [(self.px1, [3 + c for c in range(pm1)]), (self.diff, dmap)], self.px2, act=1, S=self._pick_s(W, pm2, pm1))
+        self._conv(w, b, [(self.px1, [3 + c for c in range(pm1)]), (self.diff, dmap)], self.px2, act=1)
         w, b = cbn("conv_out")
-        self._conv(w, b, [(self.px2, [3 + c for c in range(pm2)]), (self.diff, dmap)], None, act=0, S=self._pick_s(W, 1, pm2, cap=16),
-                   f32_out=self.logits)
+        self._conv(w, b, [(self.px2, [3 + c for c in range(pm2)]), (self.diff, dmap)], None, act=0, cap=16, f32_out=self.logits)
         self.ops.append(("threshold", None))
 
     @staticmethod
@@ -271,21 +299,28 @@ class FCNPlan:
         return 2 * macs
 
     # -------------------------------------------------------------------------------------------------
-    def _pick_s(self, width, cout, cin, cap=None):
-        """x-packing factor: fill the UMMA N dimension (target N = S*Cout up to 128) for narrow layers."""
+    def _pick_s(self, width, height, cout, seg_cs, KW, KH, cap=None):
+        """x-packing factor S (output pixels per GEMM row) from a per-tile cycle model of csrc/fcn_conv.cu:
+        the slowest of MMA issue (tcgen05 floor N/2 clk per K=16 step, or the smem operand read (4 KB + 32 N B) at
+        128 B/clk), L2->smem traffic (A boxes + streamed weight tiles at ~42 B/clk/SM) and the epilogue."""
         if not self.rowrun:
             return 1
+        best = None
         s = 1
-        while s * 2 * cout <= 128 and width % (s * 2) == 0 and (cap is None or s * 2 <= cap) and s * 2 <= 16:
+        while s <= 16 and (cap is None or s <= cap):
+            if s == 1 or (width % s == 0 and s * cout <= 256):
+                c = layer_cost(width // s, height, s * cout, [(KW + s - 1) * c_ for c_ in seg_cs], KH, self.B)
+                cost = c["clk"] / (128.0 * s)
+                if best is None or cost < best[0] * 0.97:      # prefer the smaller S on near ties (less padding work)
+                    best = (cost, s)
             s *= 2
-        return s
+        return best[1]
 
-    def _conv(self, w, b, srcs, dst, act, S, f32_out=None):
+    def _conv(self, w, b, srcs, dst, act, cap=None, f32_out=None):
         nrows, cin_total, KH, KW = w.shape
         first = srcs[0][0]
         Hin, Win = first.H, first.W
-        if Win % S:
-            S = 1
+        S = self._pick_s(Win, Hin, nrows, [buf.C for buf, _ in srcs], KW, KH, cap)
         NT = choose_nt(S * nrows)
         packed, bias, ntot, ntot_pad = pack_weights(w, b, [(buf.C, cmap) for buf, cmap in srcs], S, self.rowrun, NT)
         packed, bias = packed.to(self.device), bias.to(self.device)
@@ -352,6 +387,30 @@ class FCNPlan:
         self.flops += 2 * src.H * src.W * 4 * cout * cin
 
     # -------------------------------------------------------------------------------------------------
+    def _conv_plan(self, i, desc):
+        """Prepared launch (tensor maps + tiling) of conv op i, created on first use (needs the device)."""
+        h = self._cplans.get(i)
+        if h is None:
+            h = self.lib.am_conv_plan_create(ctypes.byref(desc))
+            if not h:
+                raise _lib.AccessMathB200Error("am_conv_plan_create failed for op %d" % i)
+            self._cplans[i] = h
+        return h
+
+    def conv_plan_info(self, i):
+        """[MT, resident weights, accumulator stages, A stages, B stages, grid, smem bytes, work items] of conv op i."""
+        info = (ctypes.c_int * 8)()
+        _lib.check(self.lib.am_conv_plan_info(self._conv_plan(i, self.ops[i][1]), info), "am_conv_plan_info")
+        return list(info)
+
+    def __del__(self):
+        try:
+            for h in self._cplans.values():
+                self.lib.am_conv_plan_destroy(h)
+            self._cplans = {}
+        except Exception:
+            pass
+
     @property
     def launches_per_run(self):
         return 1 + len(self.ops)
@@ -369,7 +428,7 @@ class FCNPlan:
                 if timing is not None:
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     e0.record()
-                chk(lib.am_conv_gemm(ctypes.byref(a), st), "am_conv_gemm")
+                chk(lib.am_conv_plan_launch(self._conv_plan(i, a), st), "am_conv_plan_launch")
                 if timing is not None:
                     e1.record()
                     timing.append((i, e0, e1))

@@ -69,23 +69,39 @@ class ContentExtractor:
 
     # ---- frame-shard chain ------------------------------------------------------------------------------
     def recv_state(self, src):
-        import torch.distributed as dist
-        header = torch.zeros(6, dtype=torch.int64, device=self.device)
-        dist.recv(header, src=src)
-        h = header.cpu()
-        n_act, words = int(h[0]), int(h[1])
-        meta = torch.zeros((max(n_act, 1), 10), dtype=torch.int32, device=self.device)
-        crops = torch.zeros((max(words, 1),), dtype=torch.int32, device=self.device)
-        dist.recv(meta, src=src)
-        dist.recv(crops, src=src)
+        h, meta, crops = recv_active_set(src, self.device)
         self.est.import_state(h, meta, crops)
 
     def send_state(self, dst):
-        import torch.distributed as dist
         header, meta, crops = self.est.export_state()
-        dist.send(header.to(self.device), dst=dst)
-        dist.send(meta, dst=dst)
-        dist.send(crops, dst=dst)
+        send_active_set(header, meta, crops, dst, self.device)
+
+
+# Wire format of the hand-off between frame shards (the only data-path exchange):
+#   header int64[6] = n_active, crop_words, n_unique, img_idx, tempo_count, 0
+#   meta   int32[n_active][10] = unique_idx, min_x, max_x, min_y, max_y, size, last_seen, first_frame, first_label, crop_words
+#   crops  int32[crop_words]   = the first-seen bit-packed crops of the active uniques, concatenated in meta order
+def send_active_set(header, meta, crops, dst, device=None):
+    """Point-to-point send of the active unique-CC set (NCCL over NVLink on the GPU box, gloo in the CPU tests)."""
+    import torch.distributed as dist
+    dev = device if device is not None else torch.device("cpu")
+    dist.send(header.to(dev), dst=dst)
+    dist.send(meta.to(dev).contiguous(), dst=dst)
+    dist.send(crops.to(dev).contiguous(), dst=dst)
+
+
+def recv_active_set(src, device=None):
+    import torch.distributed as dist
+    dev = device if device is not None else torch.device("cpu")
+    header = torch.zeros(6, dtype=torch.int64, device=dev)
+    dist.recv(header, src=src)
+    h = header.cpu()
+    n_act, words = int(h[0]), int(h[1])
+    meta = torch.zeros((max(n_act, 1), 10), dtype=torch.int32, device=dev)
+    crops = torch.zeros((max(words, 1),), dtype=torch.int32, device=dev)
+    dist.recv(meta, src=src)
+    dist.recv(crops, src=src)
+    return h, meta, crops
 
 
 def shard_ranges(n_frames, world):
