@@ -175,7 +175,7 @@ def run_ours(args):
             for bits in bits_store:
                 ex.engine.label(bits, want_labels=False, sync=False)
                 ex.est.add_frames(ex.engine, 0, B)
-                ex.launches += 12 + 2 * B
+                ex.launches += 12 + 4 * B
         if rank + 1 < world:
             ex.send_state(rank + 1)
 

@@ -5,7 +5,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libaccessmath_b200.so")
+LIB_PATH = os.environ.get("AM_B200_LIB") or os.path.join(_HERE, "libaccessmath_b200.so")      # AM_B200_LIB: tuning variants only
 
 c_int, c_void_p, c_double, c_ll, c_ull = ctypes.c_int, ctypes.c_void_p, ctypes.c_double, ctypes.c_longlong, ctypes.c_ulonglong
 

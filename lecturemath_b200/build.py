@@ -24,19 +24,27 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not _stale():
-        return OUT
+def build(force=False, verbose=False, variant=None, defines=()):
+    """variant/defines: tuning experiments only (e.g. variant="e16", defines=["-DEPI_WARPS=16"]) -> a second library
+    libaccessmath_b200_<variant>.so that AM_B200_LIB can point the binding at."""
+    out = OUT if not variant else OUT[:-3] + "_" + variant + ".so"
+    if not force and not variant and not _stale():
+        return out
     objs = []
-    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    bdir = os.path.join(HERE, "build" + ("_" + variant if variant else ""))
+    os.makedirs(bdir, exist_ok=True)
     for src in sources():
-        obj = os.path.join(HERE, "build", os.path.basename(src)[:-3] + ".o")
-        cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        obj = os.path.join(bdir, os.path.basename(src)[:-3] + ".o")
+        cmd = [NVCC] + FLAGS + list(defines) + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
         subprocess.check_call(cmd)
         objs.append(obj)
-    subprocess.check_call([NVCC, "-shared", "-o", OUT] + objs + ["-lcudart_static", "-ldl", "-lpthread", "-lrt"])
-    return OUT
+    subprocess.check_call([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", out] + objs + ["-lcudart_static", "-ldl", "-lpthread", "-lrt"])
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    args = [a for a in sys.argv[1:]]
+    variant = None
+    if "--variant" in args:
+        variant = args[args.index("--variant") + 1]
+    print(build(force="--force" in args, verbose="-v" in args, variant=variant, defines=[a for a in args if a.startswith("-D")]))

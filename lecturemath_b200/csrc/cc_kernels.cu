@@ -430,65 +430,127 @@ struct am_estimator {
     int cur;                     // which act buffer is current
     // device scalars: [0]=n_uniq [1]=n_act [2]=img_idx [3]=status ; 64-bit: tested, arena_used
     int* d_scal; unsigned long long* d_scal64;
+    // per-frame candidate work lists (reset by k_match_update): scal[4] = n_pairs, scal[5] = n_items
+    int MP, MI;                  // capacities
+    int2* pair_cu;               // [MP] (current kept index, unique index) of every bbox-overlapping candidate
+    int* pair_m;                 // [MP] pixel overlap of the pair (popcount of AND), accumulated by k_match_overlap
+    int2* items;                 // [MI] (pair index, chunk of MATCH_CHUNK words) -- large overlaps are split over warps
     void* slab;
     int* h_scal; unsigned long long* h_scal64;   // pinned
 };
+#define MATCH_CHUNK 2048
+#define MATCH_NONE 0x7fffffff
 
-// M1: one warp per current CC: scan the active uniques in ascending order, count bbox-overlapping
-// candidates (tempo_count, :85) and take the first one whose pixel overlap passes recall/precision (:94-106)
-__global__ void k_match(const CcFrame* __restrict__ frames, const int* __restrict__ counts, int f,
-                        const int* __restrict__ act, const int* __restrict__ scal,
-                        const int* __restrict__ u_min_x, const int* __restrict__ u_max_x, const int* __restrict__ u_min_y,
-                        const int* __restrict__ u_max_y, const int* __restrict__ u_size, int* __restrict__ u_last,
-                        const unsigned long long* __restrict__ u_crop_off, const uint32_t* __restrict__ arena,
-                        double min_recall, double min_precision, unsigned long long* __restrict__ tested_total) {
+// Temporal matching is pair-parallel.  The reference tests a CC's candidates in ascending unique index and stops
+// computing at the first one that passes (cc_stability_estimator.py:90-108) while still COUNTING every candidate
+// (tempo_count, :85).  Equivalent and parallel: compute the overlap of every candidate pair, then take the MINIMUM
+// unique index among the passing ones.  Large overlaps (a board-sized CC) are split into MATCH_CHUNK-word items so
+// that one giant pair does not serialise on a single warp.
+//
+// M1a: one warp per current CC: scan the active uniques, append every bbox-overlapping pair (+ its work items)
+__global__ void k_match_pairs(const CcFrame* __restrict__ frames, const int* __restrict__ counts, int f,
+                              const int* __restrict__ act, int* __restrict__ scal,
+                              const int* __restrict__ u_min_x, const int* __restrict__ u_max_x, const int* __restrict__ u_min_y,
+                              const int* __restrict__ u_max_y, int2* __restrict__ pair_cu, int* __restrict__ pair_m,
+                              int2* __restrict__ items, int MP, int MI, unsigned long long* __restrict__ tested_total) {
     const CcFrame fr = frames[f];
     const int n_kept = counts[f * 4 + 2];
     const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (c >= n_kept) return;
     const int lane = threadIdx.x & 31;
     const int img_idx = scal[2], n_act = scal[1];
-    int found = -1;
-    if (img_idx > 0) {                                   // frame 0: every CC becomes a unique CC (:52-69)
-        const int l = fr.kept_label[c] - 1;
-        const int cx0 = fr.t_min_x[l], cx1 = fr.t_max_x[l], cy0 = fr.t_min_y[l], cy1 = fr.t_max_y[l], csz = fr.t_count[l];
-        const int cwx0 = cx0 >> 5, ccw = (cx1 >> 5) - cwx0 + 1;
-        const uint32_t* ccrop = fr.crops + fr.kept_crop_off[c];
-        unsigned tested = 0;
-        for (int a0 = 0; a0 < n_act; a0 += 32) {
-            int u = (a0 + lane < n_act) ? act[a0 + lane] : -1;
-            bool ov = false;
-            if (u >= 0) ov = (cy1 >= u_min_y[u] && u_max_y[u] >= cy0 && cx1 >= u_min_x[u] && u_max_x[u] >= cx0);
-            unsigned bal = __ballot_sync(0xffffffffu, ov);
-            tested += __popc(bal);
-            while (found < 0 && bal) {
-                int j = __ffs(bal) - 1; bal &= bal - 1;
-                int uu = __shfl_sync(0xffffffffu, u, j);
-                int ux0 = u_min_x[uu], ux1 = u_max_x[uu], uy0 = u_min_y[uu], uy1 = u_max_y[uu];
-                int uwx0 = ux0 >> 5, ucw = (ux1 >> 5) - uwx0 + 1;
-                const uint32_t* ucrop = arena + u_crop_off[uu];
-                int y0 = max(cy0, uy0), y1 = min(cy1, uy1);
-                int w0 = max(cwx0, uwx0), w1 = min(cx1 >> 5, ux1 >> 5);
-                int nw = w1 - w0 + 1, tot = nw * (y1 - y0 + 1);
-                int m = 0;
-                for (int i = lane; i < tot; i += 32) {
-                    int yy = y0 + i / nw, ww = w0 + i % nw;
-                    uint32_t a = ccrop[(size_t)(yy - cy0) * ccw + (ww - cwx0)];
-                    uint32_t b = ucrop[(size_t)(yy - uy0) * ucw + (ww - uwx0)];
-                    m += __popc(a & b);
-                }
-                m = __reduce_add_sync(0xffffffffu, m);
-                double recall = (double)m / (double)csz;             // connected_component.py:239-240
-                double precision = (double)m / (double)u_size[uu];
-                if (recall >= min_recall && precision >= min_precision) found = uu;
+    if (lane == 0) fr.match_unique[c] = MATCH_NONE;
+    if (img_idx == 0) return;                            // frame 0: every CC becomes a unique CC (:52-69)
+    const int l = fr.kept_label[c] - 1;
+    const int cx0 = fr.t_min_x[l], cx1 = fr.t_max_x[l], cy0 = fr.t_min_y[l], cy1 = fr.t_max_y[l];
+    unsigned tested = 0;
+    for (int a0 = 0; a0 < n_act; a0 += 32) {
+        const int u = (a0 + lane < n_act) ? act[a0 + lane] : -1;
+        bool ov = false;
+        int n_items = 0;
+        if (u >= 0) {
+            const int ux0 = u_min_x[u], ux1 = u_max_x[u], uy0 = u_min_y[u], uy1 = u_max_y[u];
+            ov = (cy1 >= uy0 && uy1 >= cy0 && cx1 >= ux0 && ux1 >= cx0);      // inclusive bbox overlap (interval_index.py:42-99)
+            if (ov) {
+                const int nw = (min(cx1, ux1) >> 5) - (max(cx0, ux0) >> 5) + 1;
+                const int tot = nw * (min(cy1, uy1) - max(cy0, uy0) + 1);
+                n_items = (tot + MATCH_CHUNK - 1) / MATCH_CHUNK;
             }
         }
-        if (lane == 0) {
-            if (tested) atomicAdd(tested_total, (unsigned long long)tested);
-            if (found >= 0) u_last[found] = img_idx;     // :104
+        const unsigned bal = __ballot_sync(0xffffffffu, ov);
+        if (bal == 0) continue;
+        tested += __popc(bal);
+        const int my_items_incl = warp_incl_scan(n_items);
+        const int tot_items = __shfl_sync(0xffffffffu, my_items_incl, 31);
+        int pbase = 0, ibase = 0;
+        if (lane == 0) { pbase = atomicAdd(&scal[4], __popc(bal)); ibase = atomicAdd(&scal[5], tot_items); }
+        pbase = __shfl_sync(0xffffffffu, pbase, 0); ibase = __shfl_sync(0xffffffffu, ibase, 0);
+        if (ov) {
+            const int pi = pbase + __popc(bal & ((1u << lane) - 1u));
+            if (pi < MP) {
+                pair_cu[pi] = make_int2(c, u); pair_m[pi] = 0;
+                int ii = ibase + my_items_incl - n_items;
+                for (int k = 0; k < n_items; ++k, ++ii)
+                    if (ii < MI) items[ii] = make_int2(pi, k);
+            }
         }
     }
-    if (lane == 0) fr.match_unique[c] = found;
+    if (lane == 0 && tested) atomicAdd(tested_total, (unsigned long long)tested);
+}
+
+// M1b: persistent warps over the work items: popcount(cc.mask & unique.mask) on the bit-packed crops, which sit at
+// their ABSOLUTE x position so the AND needs no shifting (connected_component.py:211-228)
+__global__ void k_match_overlap(const CcFrame* __restrict__ frames, int f, int* __restrict__ scal,
+                                const int* __restrict__ u_min_x, const int* __restrict__ u_max_x, const int* __restrict__ u_min_y,
+                                const int* __restrict__ u_max_y, const unsigned long long* __restrict__ u_crop_off,
+                                const uint32_t* __restrict__ arena, const int2* __restrict__ pair_cu, int* __restrict__ pair_m,
+                                const int2* __restrict__ items, int MP, int MI) {
+    const CcFrame fr = frames[f];
+    const int lane = threadIdx.x & 31;
+    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int n_items = min(scal[5], MI);
+    for (int it = wid; it < n_items; it += nwarps) {
+        const int2 item = items[it];
+        if (item.x >= MP) continue;
+        const int2 cu = pair_cu[item.x];
+        const int l = fr.kept_label[cu.x] - 1;
+        const int cx0 = fr.t_min_x[l], cx1 = fr.t_max_x[l], cy0 = fr.t_min_y[l], cy1 = fr.t_max_y[l];
+        const int ux0 = u_min_x[cu.y], ux1 = u_max_x[cu.y], uy0 = u_min_y[cu.y], uy1 = u_max_y[cu.y];
+        const int cwx0 = cx0 >> 5, ccw = (cx1 >> 5) - cwx0 + 1;
+        const int uwx0 = ux0 >> 5, ucw = (ux1 >> 5) - uwx0 + 1;
+        const uint32_t* ccrop = fr.crops + fr.kept_crop_off[cu.x];
+        const uint32_t* ucrop = arena + u_crop_off[cu.y];
+        const int y0 = max(cy0, uy0), y1 = min(cy1, uy1);
+        const int w0 = max(cwx0, uwx0), w1 = min(cx1 >> 5, ux1 >> 5);
+        const int nw = w1 - w0 + 1, tot = nw * (y1 - y0 + 1);
+        const int i0 = item.y * MATCH_CHUNK, i1 = min(tot, i0 + MATCH_CHUNK);
+        int m = 0;
+#pragma unroll 4
+        for (int i = i0 + lane; i < i1; i += 32) {
+            const int ry = i / nw, ww = w0 + (i - ry * nw), yy = y0 + ry;
+            const uint32_t a = ccrop[(size_t)(yy - cy0) * ccw + (ww - cwx0)];
+            const uint32_t b = ucrop[(size_t)(yy - uy0) * ucw + (ww - uwx0)];
+            m += __popc(a & b);
+        }
+        m = __reduce_add_sync(0xffffffffu, m);
+        if (lane == 0 && m) atomicAdd(&pair_m[item.x], m);
+    }
+}
+
+// M1c: per pair: recall / precision in IEEE fp64 (connected_component.py:239-240), lowest passing unique index wins
+__global__ void k_match_select(const CcFrame* __restrict__ frames, int f, const int* __restrict__ scal, const int* __restrict__ u_size,
+                               const int2* __restrict__ pair_cu, const int* __restrict__ pair_m, int MP,
+                               double min_recall, double min_precision) {
+    const CcFrame fr = frames[f];
+    const int n_pairs = min(scal[4], MP);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pairs; i += gridDim.x * blockDim.x) {
+        const int2 cu = pair_cu[i];
+        const int m = pair_m[i];
+        const int csz = fr.t_count[fr.kept_label[cu.x] - 1];
+        const double recall = (double)m / (double)csz;
+        const double precision = (double)m / (double)u_size[cu.y];
+        if (recall >= min_recall && precision >= min_precision) atomicMin(&fr.match_unique[cu.x], cu.y);
+    }
 }
 
 // M2: one block: number the new uniques (ascending current order), copy their crops, expire, append
@@ -497,13 +559,21 @@ __global__ void k_match_update(const CcFrame* __restrict__ frames, const int* __
                                unsigned long long* __restrict__ scal64,
                                int* u_min_x, int* u_max_x, int* u_min_y, int* u_max_y, int* u_size, int* u_last,
                                int* u_first_frame, int* u_first_label, unsigned long long* u_crop_off, uint32_t* arena,
-                               int MU, int MA, unsigned long long AW, int max_gap) {
+                               int MU, int MA, unsigned long long AW, int max_gap, int MP, int MI) {
     __shared__ int sm[33];
     __shared__ unsigned long long s_arena;
     const CcFrame fr = frames[f];
     const int n_kept = counts[f * 4 + 2];
     const int img_idx = scal[2], n_uniq0 = scal[0], n_act0 = scal[1];
-    if (threadIdx.x == 0) s_arena = scal64[1];
+    if (threadIdx.x == 0) {
+        s_arena = scal64[1];
+        if (scal[4] > MP || scal[5] > MI) atomicOr(&scal[3], 16);       // candidate work lists overflowed
+    }
+    // 0. matched CCs refresh their unique's last-seen frame (:104) before the expiry pass reads it
+    for (int c = threadIdx.x; c < n_kept; c += blockDim.x) {
+        const int u = fr.match_unique[c];
+        if (u != MATCH_NONE) u_last[u] = img_idx;
+    }
     __syncthreads();
     // 1. expiry of the previously active uniques (:127-145; not on frame 0) -> act_out[0..keep)
     int kept_act = 0;
@@ -522,7 +592,7 @@ __global__ void k_match_update(const CcFrame* __restrict__ frames, const int* __
     bool over = false;
     for (int c0 = 0; c0 < n_kept; c0 += blockDim.x) {
         int c = c0 + threadIdx.x;
-        int isnew = (c < n_kept) && (fr.match_unique[c] < 0);
+        int isnew = (c < n_kept) && (fr.match_unique[c] == MATCH_NONE);
         int words = 0, l = 0;
         if (isnew) {
             l = fr.kept_label[c] - 1;
@@ -565,6 +635,7 @@ __global__ void k_match_update(const CcFrame* __restrict__ frames, const int* __
         scal[0] = min(n_uniq0 + n_new, MU);
         scal[1] = min(kept_act + n_new, MA);
         scal[2] = img_idx + 1;
+        scal[4] = 0; scal[5] = 0;                        // empty work lists for the next frame
         scal64[1] = s_arena;
     }
 }
@@ -894,6 +965,8 @@ extern "C" am_estimator* am_est_create(int width, int height, double min_recall,
     size_t o_a0 = add((size_t)e->MA * 4), o_a1 = add((size_t)e->MA * 4);
     size_t o_tmp = add((size_t)e->MA * 8);
     size_t o_sc = add(64), o_sc64 = add(64);
+    e->MP = 1 << 20; e->MI = 1 << 21;
+    size_t o_pcu = add((size_t)e->MP * 8), o_pm = add((size_t)e->MP * 4), o_it = add((size_t)e->MI * 8);
     size_t o_ar = add((size_t)aw * 4);
     if (cudaMalloc(&e->slab, tot) != cudaSuccess) {
         fprintf(stderr, "[accessmath_b200] am_est_create: cudaMalloc(%zu) failed\n", tot);
@@ -906,6 +979,7 @@ extern "C" am_estimator* am_est_create(int width, int height, double min_recall,
     e->act[0] = (int*)(b + o_a0); e->act[1] = (int*)(b + o_a1); e->cur = 0;
     e->d_scal = (int*)(b + o_sc); e->d_scal64 = (unsigned long long*)(b + o_sc64);
     e->arena = (uint32_t*)(b + o_ar);
+    e->pair_cu = (int2*)(b + o_pcu); e->pair_m = (int*)(b + o_pm); e->items = (int2*)(b + o_it);
     e->AW = aw; e->tmp_off = (unsigned long long*)(b + o_tmp);
     cudaMemset(e->d_scal, 0, 64); cudaMemset(e->d_scal64, 0, 64);
     cudaMallocHost(&e->h_scal, 64); cudaMallocHost(&e->h_scal64, 64);
@@ -922,12 +996,14 @@ extern "C" int am_est_add_frames(am_estimator* e, am_cc_ctx* c, int first, int n
     cudaStream_t st = S(stream);
     for (int f = first; f < first + n; ++f) {
         int* a_in = e->act[e->cur]; int* a_out = e->act[e->cur ^ 1];
-        k_match<<<am_div_up(c->MK, 8), 256, 0, st>>>(c->d_frames, c->d_counts, f, a_in, e->d_scal, e->u_min_x, e->u_max_x, e->u_min_y,
-                                                   e->u_max_y, e->u_size, e->u_last, e->u_crop_off, e->arena, e->min_recall,
-                                                   e->min_precision, e->d_scal64);
+        k_match_pairs<<<am_div_up(c->MK, 8), 256, 0, st>>>(c->d_frames, c->d_counts, f, a_in, e->d_scal, e->u_min_x, e->u_max_x, e->u_min_y,
+                                                         e->u_max_y, e->pair_cu, e->pair_m, e->items, e->MP, e->MI, e->d_scal64);
+        k_match_overlap<<<148 * 4, 256, 0, st>>>(c->d_frames, f, e->d_scal, e->u_min_x, e->u_max_x, e->u_min_y, e->u_max_y, e->u_crop_off,
+                                                 e->arena, e->pair_cu, e->pair_m, e->items, e->MP, e->MI);
+        k_match_select<<<148, 256, 0, st>>>(c->d_frames, f, e->d_scal, e->u_size, e->pair_cu, e->pair_m, e->MP, e->min_recall, e->min_precision);
         k_match_update<<<1, 1024, 0, st>>>(c->d_frames, c->d_counts, f, a_in, a_out, e->d_scal, e->d_scal64, e->u_min_x, e->u_max_x,
                                            e->u_min_y, e->u_max_y, e->u_size, e->u_last, e->u_first_frame, e->u_first_label,
-                                           e->u_crop_off, e->arena, e->MU, e->MA, e->AW, e->max_gap);
+                                           e->u_crop_off, e->arena, e->MU, e->MA, e->AW, e->max_gap, e->MP, e->MI);
         e->cur ^= 1;
     }
     AM_CUDA(cudaGetLastError());
@@ -942,7 +1018,7 @@ extern "C" int am_est_state(am_estimator* e, int* h_state, void* stream) {
     h_state[0] = e->h_scal[0]; h_state[1] = e->h_scal[1]; h_state[2] = e->h_scal[2]; h_state[3] = e->h_scal[3];
     h_state[4] = (int)(e->h_scal64[0] & 0xffffffffull); h_state[5] = (int)(e->h_scal64[0] >> 32);
     if (e->h_scal[3]) {
-        fprintf(stderr, "[accessmath_b200] estimator capacity exceeded (uniques/active/arena)\n");
+        fprintf(stderr, "[accessmath_b200] estimator capacity exceeded (flags 0x%x: 8=uniques/active/arena 16=candidate pairs)\n", e->h_scal[3]);
         return AM_ERR_CAPACITY;
     }
     return AM_OK;

@@ -31,8 +31,11 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
-#define CONV_THREADS 320
-#define EPI_WARPS 8
+#ifndef EPI_WARPS
+#define EPI_WARPS 8                       // 2 (or 4 with -DEPI_WARPS=16) epilogue warps per TMEM lane quarter
+#endif
+#define EPI_PER_Q (EPI_WARPS / 4)
+#define CONV_THREADS (64 + 32 * EPI_WARPS)
 
 struct alignas(64) ConvParams {
     CUtensorMap tmA[2];
@@ -72,7 +75,23 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    return done;
+}
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
+    for (uint32_t it = 0; !mbar_try(bar, parity); ++it)
+        if (it > (1u << 26)) { printf("[accessmath_b200] mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (!mbar_try(bar, parity)) mbar_wait_slow(bar, parity);
+}
+__device__ __forceinline__ void mbar_wait_old(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
     for (uint32_t it = 0; !done; ++it) {
         asm volatile(
@@ -117,6 +136,18 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
     d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
     return d;
 }
+// One leader lane of a fully active warp (same lane on every call).  Producer and MMA loops run WARP-UNIFORM (all 32
+// lanes execute the control flow, so addresses/descriptors live in uniform registers) and only the asynchronous
+// instruction itself is predicated on the elected lane -- a `lane == 0` region would make ptxas wrap every
+// UTMALDG/UTCHMMA in an R2UR + ELECT waterfall loop (seen in profiles/ r01: ~220 issue cycles per MMA).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, 0xffffffff;\n\t@px mov.s32 %0, 1;\n\t}" : "+r"(pred));
+    return pred != 0;
+}
+#define DESC_HI_SW128 (((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61))
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | (1u << 16); }
+
 // 16 consecutive fp32 accumulator columns of this thread's TMEM lane (asynchronous: tmem_wait before use)
 __device__ __forceinline__ void tmem_ld16_async(uint32_t taddr, uint32_t* v) {
     asm volatile(
@@ -133,22 +164,24 @@ __device__ __forceinline__ void tmem_wait16(uint32_t* v) {
                  :: "memory");
 }
 
-// nn.GELU() (exact-erf form): 0.5*x*(1+erf(x/sqrt 2)).  erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far
-// below the bf16 rounding of the stored activation); branch free, two MUFU ops (rcp, ex2).
+// nn.GELU() (exact-erf form): 0.5*x*(1+erf(x/sqrt 2)).  erf by Abramowitz-Stegun 7.1.28,
+//   erf(t) = 1 - (1 + a1 t + ... + a6 t^6)^-16,  |error| <= 3e-7 for t >= 0
+// (far below the bf16 rounding of the stored activation); branch free, ONE MUFU op (rcp) -- MUFU issues at 1/8 of the
+// FMA rate on sm_100, so the two-MUFU 7.1.26 form cost more issue slots than all its FMAs together.
 __device__ __forceinline__ float gelu_erf(float x) {
-    const float ax = fabsf(x) * 0.70710678118654752f;
-    float t;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.0f)));
-    float pl = fmaf(1.061405429f, t, -1.453152027f);
-    pl = fmaf(pl, t, 1.421413741f);
-    pl = fmaf(pl, t, -0.284496736f);
-    pl = fmaf(pl, t, 0.254829592f);
-    pl *= t;
-    float e;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(ax * ax * -1.4426950408889634f));
-    const float erf_abs = fmaf(-pl, e, 1.0f);
+    const float t = fabsf(x) * 0.70710678118654752f;
+    float d = fmaf(0.0000430638f, t, 0.0002765672f);
+    d = fmaf(d, t, 0.0001520143f);
+    d = fmaf(d, t, 0.0092705272f);
+    d = fmaf(d, t, 0.0422820123f);
+    d = fmaf(d, t, 0.0705230784f);
+    d = fmaf(d, t, 1.0f);
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+    r *= r; r *= r; r *= r;                              // d^-8
+    const float erf_abs = fmaf(-r, r, 1.0f);             // 1 - d^-16
     const float hx = 0.5f * x;
-    return fmaf(fabsf(hx), erf_abs, hx);             // 0.5x + 0.5|x| erf(|x|/sqrt2) == 0.5x(1 + erf(x/sqrt2))
+    return fmaf(fabsf(hx), erf_abs, hx);                 // 0.5x + 0.5|x| erf(|x|/sqrt2) == 0.5x(1 + erf(x/sqrt2))
 }
 
 struct TileCoord { int frame, y0, r0; bool valid; };
@@ -162,14 +195,16 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int t) {
     return c;
 }
 
+// kMT = M-tiles per work item, kRES = weights resident in shared memory (compile-time so the single-warp issue loops stay short)
+template <int kMT, bool kRES>
 __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv_gemm(const __grid_constant__ ConvParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve: [A ring][B ring | resident B][bias][barriers][tmem ptr]
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bytesA1 = (uint32_t)(p.YT + p.KH - 1) * p.RT * 128u;    // one M-tile box (multiple of 1024: RT % 8 == 0)
-    const uint32_t bytesA = bytesA1 * p.MT;
+    const uint32_t bytesA = bytesA1 * kMT;
     const uint32_t bytesB = (uint32_t)p.NT * 128u;
-    const uint32_t nB = p.residentB ? (uint32_t)(p.total_chunks * p.KH) : (uint32_t)p.stagesB;
+    const uint32_t nB = kRES ? (uint32_t)(p.total_chunks * p.KH) : (uint32_t)p.stagesB;
     const uint32_t sA0 = smem_base;
     const uint32_t sB0 = sA0 + bytesA * p.stagesA;
     const uint32_t sBias = sB0 + ((bytesB * nB + 1023u) & ~1023u);
@@ -200,37 +235,44 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv_gemm(const __grid_cons
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
-            int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
-            if (p.residentB) {                           // all weight tiles once (single N block): fullB[0] collects them
+        // ===================== TMA producer (warp-uniform, elected lane issues) =====================
+        int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+        if (kRES) {                               // all weight tiles once (single N block): fullB[0] collects them
+            if (elect_one()) {
                 mbar_expect_tx(fullB, bytesB * nB);
                 for (uint32_t i = 0; i < nB; ++i) tma_load_2d(sB0 + bytesB * i, &p.tmB, fullB, 0, (int)i * p.Ntot_pad);
             }
-            for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
-                const int st = w / p.nNB, nb = w - st * p.nNB;
-                const int n0 = nb * p.NT;
-                TileCoord tc[2];
-                tc[0] = decode_tile(p, st * p.MT);
-                tc[1] = decode_tile(p, st * p.MT + (p.MT - 1));
-                int chunk = 0;
-                for (int s = 0; s < p.nseg; ++s) {
-                    const CUtensorMap* tm = &p.tmA[s];
-                    for (int kx = 0; kx < p.seg_nkx[s]; ++kx) {
-                        for (int ck = 0; ck < p.seg_nck[s]; ++ck, ++chunk) {
-                            mbar_wait(emptyA + 8 * sa, pa ^ 1);
-                            mbar_expect_tx(fullA + 8 * sa, bytesA);
-                            for (int mt = 0; mt < p.MT; ++mt)
-                                tma_load_4d(sA0 + bytesA * sa + bytesA1 * mt, tm, fullA + 8 * sa, ck * 64,
-                                            tc[mt].r0 + p.seg_c1off[s] + kx * p.seg_c1step[s], tc[mt].y0 - p.padY, tc[mt].frame);
-                            if (++sa == p.stagesA) { sa = 0; pa ^= 1; }
-                            if (!p.residentB) {
-                                for (int dy = 0; dy < p.KH; ++dy) {
-                                    mbar_wait(emptyB + 8 * sb, pb ^ 1);
+            __syncwarp();
+        }
+        for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
+            const int st = w / p.nNB, nb = w - st * p.nNB;
+            const int n0 = nb * p.NT;
+            const TileCoord tc0 = decode_tile(p, st * kMT);
+            const TileCoord tc1 = decode_tile(p, st * kMT + (kMT - 1));
+            int chunk = 0;
+            for (int s = 0; s < p.nseg; ++s) {
+                const CUtensorMap* tm = &p.tmA[s];
+                for (int kx = 0; kx < p.seg_nkx[s]; ++kx) {
+                    const int c1 = p.seg_c1off[s] + kx * p.seg_c1step[s];
+                    for (int ck = 0; ck < p.seg_nck[s]; ++ck, ++chunk) {
+                        mbar_wait(emptyA + 8 * sa, pa ^ 1);
+                        if (elect_one()) {
+                            const uint32_t dst = sA0 + bytesA * sa, bar = fullA + 8 * sa;
+                            mbar_expect_tx(bar, bytesA);
+                            tma_load_4d(dst, tm, bar, ck * 64, tc0.r0 + c1, tc0.y0 - p.padY, tc0.frame);
+                            if (kMT == 2) tma_load_4d(dst + bytesA1, tm, bar, ck * 64, tc1.r0 + c1, tc1.y0 - p.padY, tc1.frame);
+                        }
+                        __syncwarp();
+                        if (++sa == p.stagesA) { sa = 0; pa ^= 1; }
+                        if (!kRES) {
+                            for (int dy = 0; dy < p.KH; ++dy) {
+                                mbar_wait(emptyB + 8 * sb, pb ^ 1);
+                                if (elect_one()) {
                                     mbar_expect_tx(fullB + 8 * sb, bytesB);
                                     tma_load_2d(sB0 + bytesB * sb, &p.tmB, fullB + 8 * sb, 0, (chunk * p.KH + dy) * p.Ntot_pad + n0);
-                                    if (++sb == p.stagesB) { sb = 0; pb ^= 1; }
                                 }
+                                __syncwarp();
+                                if (++sb == p.stagesB) { sb = 0; pb ^= 1; }
                             }
                         }
                     }
@@ -238,50 +280,64 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv_gemm(const __grid_cons
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NT >> 3) << 17) | ((128u >> 4) << 24);
-            int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
-            int as = 0; uint32_t pacc = 0;
-            if (p.residentB) { mbar_wait(fullB, 0); tc_fence_after(); }
-            for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
-                mbar_wait(accEmpty + 8 * as, pacc ^ 1);                  // epilogue drained this accumulator stage
-                tc_fence_after();
-                const uint32_t tacc = tmem_base + (uint32_t)(as * p.MT * p.NTc);
-                uint32_t acc = 0;
-                int chunk = 0;
-                for (int s = 0; s < p.nseg; ++s) {
-                    for (int kx = 0; kx < p.seg_nkx[s]; ++kx) {
-                        for (int ck = 0; ck < p.seg_nck[s]; ++ck, ++chunk) {
-                            const int ksteps = ((ck == p.seg_nck[s] - 1) ? p.seg_klast[s] : 64) >> 4;
-                            mbar_wait(fullA + 8 * sa, pa);
-                            tc_fence_after();
-                            for (int dy = 0; dy < p.KH; ++dy) {
-                                uint32_t b_addr;
-                                if (p.residentB) b_addr = sB0 + bytesB * (uint32_t)(chunk * p.KH + dy);
-                                else { mbar_wait(fullB + 8 * sb, pb); tc_fence_after(); b_addr = sB0 + bytesB * sb; }
-                                for (int mt = 0; mt < p.MT; ++mt) {
-                                    const uint32_t a_addr = sA0 + bytesA * sa + bytesA1 * mt + (uint32_t)dy * p.RT * 128u;
-                                    for (int k = 0; k < ksteps; ++k)
-                                        tc_mma_bf16(tacc + (uint32_t)(mt * p.NTc), make_desc_sw128(a_addr + k * 32), make_desc_sw128(b_addr + k * 32),
-                                                    idesc, acc | (uint32_t)k);
-                                }
-                                acc = 1;
-                                if (!p.residentB) { tc_commit(emptyB + 8 * sb); if (++sb == p.stagesB) { sb = 0; pb ^= 1; } }
+        // ===================== MMA issuer (warp-uniform, elected lane issues) =====================
+        // Everything the loop needs is hoisted into (uniform) registers: the single issuing warp is latency bound, so
+        // each extra instruction per tcgen05.mma shows up directly when N is small (one MMA = N/2 tensor cycles).
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NT >> 3) << 17) | ((128u >> 4) << 24);
+        const int KH = p.KH, stagesA = p.stagesA, stagesB = p.stagesB, acc_stages = p.acc_stages, nseg = p.nseg;
+        const uint32_t NTc = (uint32_t)p.NTc;
+        const uint32_t dy_step = ((uint32_t)p.RT * 128u) >> 4, mt_step = bytesA1 >> 4, b_step = bytesB >> 4, a_step = bytesA >> 4;
+        const uint32_t a_lo0 = desc_lo(sA0), b_lo0 = desc_lo(sB0);
+        int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+        int as = 0; uint32_t pacc = 0;
+        if (kRES) { mbar_wait(fullB, 0); tc_fence_after(); }
+        for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
+            mbar_wait(accEmpty + 8 * as, pacc ^ 1);                      // epilogue drained this accumulator stage
+            tc_fence_after();
+            const uint32_t tacc = tmem_base + (uint32_t)(as * kMT) * NTc;
+            uint32_t acc = 0;
+            uint32_t b_res = b_lo0;                                      // resident mode: walks the weight tiles in order
+            for (int s = 0; s < nseg; ++s) {
+                const int nck = p.seg_nck[s], klast = p.seg_klast[s] >> 4;
+                for (int kc = p.seg_nkx[s] * nck, ck = 0; kc > 0; --kc) {
+                    const int ksteps = (ck == nck - 1) ? klast : 4;
+                    if (++ck == nck) ck = 0;
+                    mbar_wait(fullA + 8 * sa, pa);
+                    tc_fence_after();
+                    uint32_t alo = a_lo0 + a_step * (uint32_t)sa;
+                    for (int dy = 0; dy < KH; ++dy) {
+                        uint32_t blo;
+                        if (kRES) { blo = b_res; b_res += b_step; }
+                        else { mbar_wait(fullB + 8 * sb, pb); tc_fence_after(); blo = b_lo0 + b_step * (uint32_t)sb; }
+                        if (elect_one()) {
+#pragma unroll
+                            for (int mt = 0; mt < kMT; ++mt) {
+                                const uint32_t a = alo + mt_step * mt, td = tacc + NTc * mt;
+                                tc_mma_bf16(td, DESC_HI_SW128 | a, DESC_HI_SW128 | blo, idesc, acc);
+                                if (ksteps > 1) tc_mma_bf16(td, DESC_HI_SW128 | (a + 2), DESC_HI_SW128 | (blo + 2), idesc, 1);
+                                if (ksteps > 2) tc_mma_bf16(td, DESC_HI_SW128 | (a + 4), DESC_HI_SW128 | (blo + 4), idesc, 1);
+                                if (ksteps > 3) tc_mma_bf16(td, DESC_HI_SW128 | (a + 6), DESC_HI_SW128 | (blo + 6), idesc, 1);
                             }
-                            tc_commit(emptyA + 8 * sa);
-                            if (++sa == p.stagesA) { sa = 0; pa ^= 1; }
+                            if (!kRES) tc_commit(emptyB + 8 * sb);
                         }
+                        __syncwarp();
+                        acc = 1;
+                        alo += dy_step;
+                        if (!kRES) { if (++sb == stagesB) { sb = 0; pb ^= 1; } }
                     }
+                    if (elect_one()) tc_commit(emptyA + 8 * sa);
+                    __syncwarp();
+                    if (++sa == stagesA) { sa = 0; pa ^= 1; }
                 }
-                tc_commit(accFull + 8 * as);
-                if (++as == p.acc_stages) { as = 0; pacc ^= 1; }
             }
+            if (elect_one()) tc_commit(accFull + 8 * as);
+            __syncwarp();
+            if (++as == acc_stages) { as = 0; pacc ^= 1; }
         }
     } else {
         // ===================== epilogue (warps 2..9) =====================
         const int q = warp & 3;                          // TMEM lane quarter this warp may access
-        const int h = (warp - 2) >> 2;                   // which half of the 16-column groups
+        const int h = (warp - 2) >> 2;                   // which share of the 16-column groups (0 .. EPI_PER_Q-1)
         const int m = q * 32 + lane;
         const int yy = m >> p.logRT, rr = m & (p.RT - 1);
         // bias of this CTA's N block -> smem (reloaded per work item only when there are several N blocks)
@@ -289,7 +345,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv_gemm(const __grid_cons
         int bias_nb = -1;
         int as = 0; uint32_t pacc = 0;
         const int units_per_tile = p.NT >> 4;
-        const int units = units_per_tile * p.MT;
+        const int units = units_per_tile * kMT;
         const bool vec8 = (p.Cout & 7) == 0 && !p.out_f32;
         for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
             const int st = w / p.nNB, nb = w - st * p.nNB;
@@ -302,28 +358,28 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv_gemm(const __grid_cons
             }
             mbar_wait(accFull + 8 * as, pacc);
             tc_fence_after();
-            const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.MT * p.NTc);
+            const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * kMT * p.NTc);
             uint32_t va[16], vb[16];
             int g = h;
             if (g < units) {
-                const int mt = g / units_per_tile, u = g - mt * units_per_tile;
+                const int mt = g >= units_per_tile ? 1 : 0, u = g - mt * units_per_tile;
                 tmem_ld16_async(tacc + (uint32_t)(mt * p.NTc + u * 16), va);
             }
             int cur_mt = -1;
             bool row_ok = false;
             long long base = 0;
-            for (; g < units; g += 2) {
-                const int mt = g / units_per_tile, u = g - mt * units_per_tile;
+            for (; g < units; g += EPI_PER_Q) {
+                const int mt = g >= units_per_tile ? 1 : 0, u = g - mt * units_per_tile;
                 tmem_wait16(va);
 #pragma unroll
                 for (int i = 0; i < 16; ++i) vb[i] = va[i];
-                if (g + 2 < units) {
-                    const int mt2 = (g + 2) / units_per_tile, u2 = (g + 2) - mt2 * units_per_tile;
+                if (g + EPI_PER_Q < units) {
+                    const int mt2 = (g + EPI_PER_Q) >= units_per_tile ? 1 : 0, u2 = (g + EPI_PER_Q) - mt2 * units_per_tile;
                     tmem_ld16_async(tacc + (uint32_t)(mt2 * p.NTc + u2 * 16), va);
                 }
                 if (mt != cur_mt) {
                     cur_mt = mt;
-                    const TileCoord tc = decode_tile(p, st * p.MT + mt);
+                    const TileCoord tc = decode_tile(p, st * kMT + mt);
                     const int y = tc.y0 + yy, r = tc.r0 + rr;
                     row_ok = tc.valid && (y < p.Hin) && (r < p.nR);
                     base = (long long)tc.frame * p.out_sn + (long long)(p.Sy * y) * p.out_sy + (long long)(p.Sx * r + p.out_padx) * p.out_sx + p.out_coff;
@@ -542,13 +598,16 @@ static int conv_prepare(const am_conv_desc* d, am_conv_plan* plan) {
     return AM_OK;
 }
 
+typedef void (*conv_kernel_t)(const ConvParams);
 static int conv_launch(const am_conv_plan* plan, void* stream) {
+    static const conv_kernel_t kernels[4] = {k_conv_gemm<1, false>, k_conv_gemm<1, true>, k_conv_gemm<2, false>, k_conv_gemm<2, true>};
     static bool attr_set = false;
     if (!attr_set) {
-        AM_CUDA(cudaFuncSetAttribute(k_conv_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+        for (int i = 0; i < 4; ++i) AM_CUDA(cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
         attr_set = true;
     }
-    k_conv_gemm<<<plan->grid, CONV_THREADS, plan->smem, (cudaStream_t)stream>>>(plan->p);
+    const conv_kernel_t k = kernels[(plan->p.MT == 2 ? 2 : 0) + (plan->p.residentB ? 1 : 0)];
+    k<<<plan->grid, CONV_THREADS, plan->smem, (cudaStream_t)stream>>>(plan->p);
     AM_CUDA(cudaGetLastError());
     return AM_OK;
 }

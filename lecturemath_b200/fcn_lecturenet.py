@@ -147,18 +147,23 @@ def pack_weights(w, bias, segs, S, rowrun, NT):
 
 SMEM_BUDGET = 226 * 1024
 L2_BYTES_PER_CLK_SM = 42.0        # ~6300 B/clk chip-wide L2->SM throughput / 148 SMs (B300_MICROARCH.md)
-EPI_CLK_PER_COL = 30.0            # epilogue cycles per accumulator column of a 128-row tile (8 warps, GELU)
+EPI_CLK_PER_COL = 40.0            # epilogue cycles per accumulator column of a 128-row tile (8 warps, bias + GELU + store)
+EPI_CLK_PER_TILE = 600.0          # fixed epilogue cost per tile (barrier round trip, tile decode)
+ISSUE_CLK_PER_MMA = 40.0          # the single issuing warp is latency bound: ~6 dependent scalar instructions per tcgen05.mma
+ISSUE_CLK_PER_DY = (30.0, 150.0)  # per (chunk, dy) step: resident / streamed weights (mbarrier try_wait + commit)
+ISSUE_CLK_PER_CHUNK = 120.0       # per A chunk: full-barrier wait + commit
 
 
 def layer_cost(nr, h, ntot, runs, kh, batch, n_sm=148):
     """Cycle model of one 128-row M-tile of k_conv_gemm (see csrc/fcn_conv.cu) for GEMM width ntot and per-segment run
-    lengths `runs` (elements of K per vertical tap).  Mirrors conv_prepare()'s choices of resident weights / MT."""
+    lengths `runs` (elements of K per vertical tap).  Mirrors conv_prepare()'s choices of resident weights / MT.
+    Calibrated against profiles/ (r01 launch lists): small-N layers are bound by the MMA-issuing warp, not the tensor
+    pipe, which is why the planner prefers N = 128 even though the Toeplitz packing pads K."""
     nt = choose_nt(ntot)
     ntot_pad = ((ntot + nt - 1) // nt) * nt
     nnb = ntot_pad // nt
     rt, yt = choose_tile(nr, h, kh)
     chunks = sum((r + 63) // 64 for r in runs)
-    k16 = sum((r + 15) // 16 for r in runs) * kh
     bytes_a = (yt + kh - 1) * rt * 128
     bytes_b_all = chunks * kh * nt * 128
     fixed = 2560
@@ -168,9 +173,17 @@ def layer_cost(nr, h, ntot, runs, kh, batch, n_sm=148):
     while ntc < nt:
         ntc *= 2
     mt = 2 if (not resident and n_mtiles * nnb >= 4 * n_sm and 2 * ntc <= 512) else 1
-    mma = k16 * max(nt / 2.0, (4096 + 32 * nt) / 128.0)
+    t_mma = max(nt / 2.0, (4096 + 32 * nt) / 128.0)                  # tensor floor vs smem operand read, per K=16 step
+    mma = 0.0
+    for r in runs:
+        nck = (r + 63) // 64
+        for ck in range(nck):
+            ks = 4 if ck < nck - 1 else ((r - ck * 64) + 15) // 16
+            per_dy = max(mt * ks * t_mma, mt * ks * ISSUE_CLK_PER_MMA + ISSUE_CLK_PER_DY[0 if resident else 1])
+            mma += kh * per_dy + ISSUE_CLK_PER_CHUNK
+    mma /= mt
     l2 = (chunks * bytes_a + (0 if resident else chunks * kh * nt * 128 / mt)) / L2_BYTES_PER_CLK_SM
-    epi = EPI_CLK_PER_COL * nt
+    epi = EPI_CLK_PER_COL * nt + EPI_CLK_PER_TILE
     return {"clk": max(mma, l2, epi) * nnb, "mma": mma, "l2": l2, "epi": epi, "resident": resident, "mt": mt, "nt": nt}
 
 
@@ -278,7 +291,7 @@ class FCNPlan:
         w, b = cbn("conv_pixels_2")
         self._conv(w, b, [(self.px1, [3 + c for c in range(pm1)]), (self.diff, dmap)], self.px2, act=1)
         w, b = cbn("conv_out")
-        self._conv(w, b, [(self.px2, [3 + c for c in range(pm2)]), (self.diff, dmap)], None, act=0, cap=16, f32_out=self.logits)
+        self._conv(w, b, [(self.px2, [3 + c for c in range(pm2)]), (self.diff, dmap)], None, act=0, cap=32, f32_out=self.logits)
         self.ops.append(("threshold", None))
 
     @staticmethod
@@ -307,7 +320,7 @@ class FCNPlan:
             return 1
         best = None
         s = 1
-        while s <= 16 and (cap is None or s <= cap):
+        while s <= 32 and (cap is None or s <= cap):
             if s == 1 or (width % s == 0 and s * cout <= 256):
                 c = layer_cost(width // s, height, s * cout, [(KW + s - 1) * c_ for c_ in seg_cs], KH, self.B)
                 cost = c["clk"] / (128.0 * s)

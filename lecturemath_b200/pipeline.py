@@ -40,7 +40,7 @@ class ContentExtractor:
         if not match:
             return None
         self.est.add_frames(eng, 0, self.batch)
-        self.launches += 2 * self.batch
+        self.launches += 4 * self.batch
         return None
 
     def read_rows(self):

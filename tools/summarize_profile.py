@@ -1,0 +1,97 @@
+"""Turns the raw artefacts a tools/gpu_profile.sh run leaves in gpurun_out/ into the small, tracked summaries under
+profiles/:   python tools/summarize_profile.py <tag> <out_prefix>     e.g.  d  profiles/r01_d
+  <out_prefix>_launches.csv   the ncu launch list of one step (kernel, count, total us, share) + every launch
+  <out_prefix>_conv.csv       per conv launch: duration, tensor-pipe %, DRAM bytes, DRAM/L2/L1 throughput %
+  <out_prefix>_summary.md     both as markdown + the bench line
+"""
+import collections
+import csv
+import json
+import os
+import re
+import sys
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = os.path.join(REPO, "gpurun_out")
+CONV_METRICS = [
+    ("gpu__time_duration.sum", "ms"),
+    ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor_pct"),
+    ("dram__bytes_read.sum", "dram_read_GB"),
+    ("dram__bytes_write.sum", "dram_write_GB"),
+    ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram_pct"),
+    ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "l2_pct"),
+    ("l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "l1_pct"),
+    ("sm__cycles_elapsed.avg.per_second", "sm_ghz"),
+    ("launch__grid_size", "grid"),
+]
+
+
+def launches(tag):
+    rows = list(csv.reader(open(os.path.join(G, "launches_%s.csv" % tag))))
+    hdr = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
+    H = rows[hdr]
+    ki, vi = H.index("Kernel Name"), H.index("Metric Value")
+    L = [(re.sub(r"\(.*", "", r[ki]), float(r[vi].replace(",", "")) / 1000.0) for r in rows[hdr + 1:] if len(r) > vi]
+    starts = [i for i, (k, _) in enumerate(L) if k.startswith("k_prep_input")]
+    step = L[starts[-1]:] if starts else L
+    return step
+
+
+def conv_table(tag, layers):
+    rows = list(csv.reader(open(os.path.join(G, "conv_raw_%s.csv" % tag))))
+    H, data = rows[0], rows[2:]
+    idx = {h: i for i, h in enumerate(H)}
+    out = []
+    for r, lay in zip(data, layers):
+        d = collections.OrderedDict(op=lay["op"], N=lay["N"], KH=lay["KH"], S=lay["S"], bench_ms=lay["ms"], bench_tflops=lay["tflops"])
+        for m, name in CONV_METRICS:
+            d[name] = r[idx[m]] if m in idx else ""
+        out.append(d)
+    return out
+
+
+def main():
+    tag, prefix = sys.argv[1], sys.argv[2]
+    os.makedirs(os.path.dirname(prefix), exist_ok=True)
+    step = launches(tag)
+    agg = collections.OrderedDict()
+    for k, us in step:
+        a = agg.setdefault(k, [0, 0.0])
+        a[0] += 1
+        a[1] += us
+    total = sum(us for _, us in step)
+    with open(prefix + "_launches.csv", "w", newline="") as f:
+        w = csv.writer(f)
+        w.writerow(["kernel", "launches", "total_us", "share_pct"])
+        for k, (n, us) in agg.items():
+            w.writerow([k, n, "%.1f" % us, "%.2f" % (100 * us / total)])
+        w.writerow([])
+        w.writerow(["launch_index", "kernel", "us"])
+        for i, (k, us) in enumerate(step):
+            w.writerow([i, k, "%.2f" % us])
+    layers = json.load(open(os.path.join(G, "layers_%s.json" % tag)))
+    conv = conv_table(tag, layers)
+    with open(prefix + "_conv.csv", "w", newline="") as f:
+        w = csv.DictWriter(f, fieldnames=list(conv[0].keys()))
+        w.writeheader()
+        w.writerows(conv)
+    bench = open(os.path.join(G, "bench_%s.json" % tag)).read().strip()
+    with open(prefix + "_summary.md", "w") as f:
+        f.write("# profile %s\n\n" % tag)
+        f.write("Command: `python tools/profile_step.py` (8 x 1080p frames resident in HBM, 2 steps; second step listed). ncu launch list "
+                "(`--metrics gpu__time_duration.sum --clock-control none`): cold-cache, serialised -- compare SHARES.\n\n")
+        f.write("| kernel | launches | total us | share |\n|---|---|---|---|\n")
+        for k, (n, us) in agg.items():
+            f.write("| %s | %d | %.1f | %.1f %% |\n" % (k, n, us, 100 * us / total))
+        f.write("| **step** | %d | %.1f | |\n\n" % (len(step), total))
+        f.write("Per conv launch (`ncu --set full`, same command; bench_* columns are CUDA-event timings from `bench.py --layer-table`):\n\n")
+        keys = list(conv[0].keys())
+        f.write("| " + " | ".join(keys) + " |\n|" + "---|" * len(keys) + "\n")
+        for d in conv:
+            f.write("| " + " | ".join(str(d[k])[:9] for k in keys) + " |\n")
+        f.write("\nbench.py line of the same build:\n\n```\n%s\n```\n" % bench)
+    print("wrote", prefix + "_{launches.csv,conv.csv,summary.md}")
+
+
+if __name__ == "__main__":
+    main()
