@@ -20,8 +20,11 @@
 //
 // Execution model (v2): PERSISTENT CTAs (grid = min(work items, SM count)), 10 warps:
 //   warp 0      TMA producer (A boxes per K chunk; B tiles per (chunk, dy) unless the weights are resident)
-//   warp 1      TMEM owner + single-thread tcgen05.mma issuer
-//   warps 2..9  epilogue: two warps per TMEM lane quarter, alternating 16-column groups
+//   warp 1      TMEM owner + tcgen05.mma issuer of M-tile 0
+//   warp 2      tcgen05.mma issuer of M-tile 1 (kMT = 2): a single issuing warp is latency bound (~100 clk per MMA
+//               measured with N = 64), two issuers on two independent accumulators double the issue rate
+//   warp 3      idle
+//   warps 4..19 epilogue: four warps per TMEM lane quarter, interleaved 16-column groups
 // A work item = MT (1 or 2) M-tiles of 128 GEMM rows x one N block of NT columns.  MT = 2 shares every B tile
 // between two accumulators (halves the L2->smem weight traffic of the streamed mode).  Weights that fit in
 // shared memory are loaded ONCE per CTA ("resident B") and the B ring disappears.  Accumulators are double
@@ -32,10 +35,10 @@
 #include <cuda_bf16.h>
 
 #ifndef EPI_WARPS
-#define EPI_WARPS 8                       // 2 (or 4 with -DEPI_WARPS=16) epilogue warps per TMEM lane quarter
-#endif
+#define EPI_WARPS 16                      // 4 epilogue warps per TMEM lane quarter (8 measured ~3 % slower per step: the
+#endif                                    // epilogue is latency bound -- TMEM load, MUFU -- so more warps hide more of it)
 #define EPI_PER_Q (EPI_WARPS / 4)
-#define CONV_THREADS (64 + 32 * EPI_WARPS)
+#define CONV_THREADS (128 + 32 * EPI_WARPS)
 
 struct alignas(64) ConvParams {
     CUtensorMap tmA[2];
@@ -90,6 +93,11 @@ __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (!mbar_try(bar, parity)) mbar_wait_slow(bar, parity);
+}
+// for the warp-uniform producer / issuer loops: the vote makes the branch provably uniform, so ptxas keeps the loop
+// state in uniform registers instead of moving it R->UR before every UTMALDG / UTCHMMA
+__device__ __forceinline__ void mbar_wait_uniform(uint32_t bar, uint32_t parity) {
+    if (!__all_sync(0xffffffffu, mbar_try(bar, parity))) mbar_wait_slow(bar, parity);
 }
 __device__ __forceinline__ void mbar_wait_old(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
@@ -213,12 +221,14 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv_gemm(const __grid_cons
     const uint32_t fullA = bar0, emptyA = fullA + 8 * p.stagesA, fullB = emptyA + 8 * p.stagesA, emptyB = fullB + 8 * p.stagesB;
     const uint32_t accFull = emptyB + 8 * p.stagesB, accEmpty = accFull + 16;
     const uint32_t tmem_slot = accEmpty + 16;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform for ptxas
+    const int lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < p.stagesA; ++i) { mbar_init(fullA + 8 * i, 1); mbar_init(emptyA + 8 * i, 1); }
-        for (int i = 0; i < p.stagesB; ++i) { mbar_init(fullB + 8 * i, 1); mbar_init(emptyB + 8 * i, 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(accFull + 8 * i, 1); mbar_init(accEmpty + 8 * i, EPI_WARPS); }
+        // every MMA issuer (one per M-tile) commits to the empty / accumulator-full barriers
+        for (int i = 0; i < p.stagesA; ++i) { mbar_init(fullA + 8 * i, 1); mbar_init(emptyA + 8 * i, kMT); }
+        for (int i = 0; i < p.stagesB; ++i) { mbar_init(fullB + 8 * i, 1); mbar_init(emptyB + 8 * i, kMT); }
+        for (int i = 0; i < 2; ++i) { mbar_init(accFull + 8 * i, kMT); mbar_init(accEmpty + 8 * i, EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         tma_prefetch_desc(&p.tmA[0]);
         if (p.nseg > 1) tma_prefetch_desc(&p.tmA[1]);
@@ -255,7 +265,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv_gemm(const __grid_cons
                 for (int kx = 0; kx < p.seg_nkx[s]; ++kx) {
                     const int c1 = p.seg_c1off[s] + kx * p.seg_c1step[s];
                     for (int ck = 0; ck < p.seg_nck[s]; ++ck, ++chunk) {
-                        mbar_wait(emptyA + 8 * sa, pa ^ 1);
+                        mbar_wait_uniform(emptyA + 8 * sa, pa ^ 1);
                         if (elect_one()) {
                             const uint32_t dst = sA0 + bytesA * sa, bar = fullA + 8 * sa;
                             mbar_expect_tx(bar, bytesA);
@@ -266,7 +276,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv_gemm(const __grid_cons
                         if (++sa == p.stagesA) { sa = 0; pa ^= 1; }
                         if (!kRES) {
                             for (int dy = 0; dy < p.KH; ++dy) {
-                                mbar_wait(emptyB + 8 * sb, pb ^ 1);
+                                mbar_wait_uniform(emptyB + 8 * sb, pb ^ 1);
                                 if (elect_one()) {
                                     mbar_expect_tx(fullB + 8 * sb, bytesB);
                                     tma_load_2d(sB0 + bytesB * sb, &p.tmB, fullB + 8 * sb, 0, (chunk * p.KH + dy) * p.Ntot_pad + n0);
@@ -279,22 +289,23 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv_gemm(const __grid_cons
                 }
             }
         }
-    } else if (warp == 1) {
-        // ===================== MMA issuer (warp-uniform, elected lane issues) =====================
-        // Everything the loop needs is hoisted into (uniform) registers: the single issuing warp is latency bound, so
-        // each extra instruction per tcgen05.mma shows up directly when N is small (one MMA = N/2 tensor cycles).
+    } else if (warp == 1 || (warp == 2 && kMT == 2)) {
+        // ===================== MMA issuer of M-tile `mt` (warp-uniform, elected lane issues) =====================
+        // Everything the loop needs is hoisted into (uniform) registers: an issuing warp is latency bound, so each
+        // extra instruction per tcgen05.mma shows up directly when N is small (one MMA = N/2 tensor cycles).
+        const int mt = warp - 1;
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NT >> 3) << 17) | ((128u >> 4) << 24);
         const int KH = p.KH, stagesA = p.stagesA, stagesB = p.stagesB, acc_stages = p.acc_stages, nseg = p.nseg;
         const uint32_t NTc = (uint32_t)p.NTc;
-        const uint32_t dy_step = ((uint32_t)p.RT * 128u) >> 4, mt_step = bytesA1 >> 4, b_step = bytesB >> 4, a_step = bytesA >> 4;
-        const uint32_t a_lo0 = desc_lo(sA0), b_lo0 = desc_lo(sB0);
+        const uint32_t dy_step = ((uint32_t)p.RT * 128u) >> 4, b_step = bytesB >> 4, a_step = bytesA >> 4;
+        const uint32_t a_lo0 = desc_lo(sA0 + bytesA1 * (uint32_t)mt), b_lo0 = desc_lo(sB0);
         int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
         int as = 0; uint32_t pacc = 0;
-        if (kRES) { mbar_wait(fullB, 0); tc_fence_after(); }
+        if (kRES) { mbar_wait_uniform(fullB, 0); tc_fence_after(); }
         for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
-            mbar_wait(accEmpty + 8 * as, pacc ^ 1);                      // epilogue drained this accumulator stage
+            mbar_wait_uniform(accEmpty + 8 * as, pacc ^ 1);              // epilogue drained this accumulator stage
             tc_fence_after();
-            const uint32_t tacc = tmem_base + (uint32_t)(as * kMT) * NTc;
+            const uint32_t td = tmem_base + (uint32_t)(as * kMT + mt) * NTc;
             uint32_t acc = 0;
             uint32_t b_res = b_lo0;                                      // resident mode: walks the weight tiles in order
             for (int s = 0; s < nseg; ++s) {
@@ -302,22 +313,18 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv_gemm(const __grid_cons
                 for (int kc = p.seg_nkx[s] * nck, ck = 0; kc > 0; --kc) {
                     const int ksteps = (ck == nck - 1) ? klast : 4;
                     if (++ck == nck) ck = 0;
-                    mbar_wait(fullA + 8 * sa, pa);
+                    mbar_wait_uniform(fullA + 8 * sa, pa);
                     tc_fence_after();
                     uint32_t alo = a_lo0 + a_step * (uint32_t)sa;
                     for (int dy = 0; dy < KH; ++dy) {
                         uint32_t blo;
                         if (kRES) { blo = b_res; b_res += b_step; }
-                        else { mbar_wait(fullB + 8 * sb, pb); tc_fence_after(); blo = b_lo0 + b_step * (uint32_t)sb; }
+                        else { mbar_wait_uniform(fullB + 8 * sb, pb); tc_fence_after(); blo = b_lo0 + b_step * (uint32_t)sb; }
                         if (elect_one()) {
-#pragma unroll
-                            for (int mt = 0; mt < kMT; ++mt) {
-                                const uint32_t a = alo + mt_step * mt, td = tacc + NTc * mt;
-                                tc_mma_bf16(td, DESC_HI_SW128 | a, DESC_HI_SW128 | blo, idesc, acc);
-                                if (ksteps > 1) tc_mma_bf16(td, DESC_HI_SW128 | (a + 2), DESC_HI_SW128 | (blo + 2), idesc, 1);
-                                if (ksteps > 2) tc_mma_bf16(td, DESC_HI_SW128 | (a + 4), DESC_HI_SW128 | (blo + 4), idesc, 1);
-                                if (ksteps > 3) tc_mma_bf16(td, DESC_HI_SW128 | (a + 6), DESC_HI_SW128 | (blo + 6), idesc, 1);
-                            }
+                            tc_mma_bf16(td, DESC_HI_SW128 | alo, DESC_HI_SW128 | blo, idesc, acc);
+                            if (ksteps > 1) tc_mma_bf16(td, DESC_HI_SW128 | (alo + 2), DESC_HI_SW128 | (blo + 2), idesc, 1);
+                            if (ksteps > 2) tc_mma_bf16(td, DESC_HI_SW128 | (alo + 4), DESC_HI_SW128 | (blo + 4), idesc, 1);
+                            if (ksteps > 3) tc_mma_bf16(td, DESC_HI_SW128 | (alo + 6), DESC_HI_SW128 | (blo + 6), idesc, 1);
                             if (!kRES) tc_commit(emptyB + 8 * sb);
                         }
                         __syncwarp();
@@ -334,10 +341,12 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv_gemm(const __grid_cons
             __syncwarp();
             if (++as == acc_stages) { as = 0; pacc ^= 1; }
         }
+    } else if (warp < 4) {
+        // idle warps (2 when kMT == 1, 3 always)
     } else {
-        // ===================== epilogue (warps 2..9) =====================
+        // ===================== epilogue (warps 4..) =====================
         const int q = warp & 3;                          // TMEM lane quarter this warp may access
-        const int h = (warp - 2) >> 2;                   // which share of the 16-column groups (0 .. EPI_PER_Q-1)
+        const int h = (warp - 4) >> 2;                   // which share of the 16-column groups (0 .. EPI_PER_Q-1)
         const int m = q * 32 + lane;
         const int yy = m >> p.logRT, rr = m & (p.RT - 1);
         // bias of this CTA's N block -> smem (reloaded per work item only when there are several N blocks)
@@ -352,7 +361,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv_gemm(const __grid_cons
             const int n0 = nb * p.NT;
             if (nb != bias_nb) {
                 asm volatile("bar.sync 1, %0;" ::"r"(EPI_WARPS * 32));     // everyone finished reading the previous bias
-                for (int i = threadIdx.x - 64; i < p.NT; i += EPI_WARPS * 32) sbias[i] = __ldg(p.bias + n0 + i);
+                for (int i = threadIdx.x - 128; i < p.NT; i += EPI_WARPS * 32) sbias[i] = __ldg(p.bias + n0 + i);
                 asm volatile("bar.sync 1, %0;" ::"r"(EPI_WARPS * 32));
                 bias_nb = nb;
             }
@@ -566,14 +575,23 @@ static int conv_prepare(const am_conv_desc* d, am_conv_plan* plan) {
     const size_t fixed = 1024 /*align*/ + 1024 /*bias (<= 256 floats)*/ + 512 /*barriers*/;
     const size_t budget = 226 * 1024;
     const size_t allB = bytesB * (size_t)total_chunks * d->KH;
-    // resident weights: single N block and the whole packed filter + >= 3 A stages fit
-    int resident = (d->flags & AM_CONV_NO_RESIDENT) ? 0 : (p.nNB == 1 && fixed + allB + 3 * bytesA1 <= budget);
-    int MT = 1;
-    if (!resident && !(d->flags & AM_CONV_NO_MT2) && p.n_mtiles * p.nNB >= 2 * sm_count() * 2 && 2 * p.NTc <= 512) MT = 2;
+    // Mode choice (mirrored by fcn_lecturenet.layer_cost):
+    //   MT = 2 (two M-tiles per work item, one MMA issuer warp each) whenever there is enough work to keep every SM busy;
+    //   resident weights when a single N block's whole packed filter fits next to >= 2 (MT = 2) / 3 (MT = 1) A stages.
+    //   Narrow layers (N < 128) are issue bound, so for them two issuers beat resident weights if both do not fit.
+    const bool many = !(d->flags & AM_CONV_NO_MT2) && p.n_mtiles * p.nNB >= 4 * sm_count() && 2 * p.NTc <= 512;
+    const bool can_res = !(d->flags & AM_CONV_NO_RESIDENT) && p.nNB == 1;
+    const bool res2 = can_res && many && fixed + allB + 2 * 2 * bytesA1 <= budget;
+    const bool res1 = can_res && fixed + allB + 3 * bytesA1 <= budget;
+    int resident, MT;
+    if (res2) { resident = 1; MT = 2; }
+    else if (res1 && (d->NT >= 128 || !many)) { resident = 1; MT = 1; }
+    else if (many) { resident = 0; MT = 2; }
+    else { resident = res1 ? 1 : 0; MT = 1; }
     int sa, sb;
     if (resident) {
-        sb = 1; sa = 3;
-        while (sa < 8 && fixed + allB + (size_t)(sa + 1) * bytesA1 <= budget) ++sa;
+        sb = 1; sa = MT == 2 ? 2 : 3;
+        while (sa < 8 && fixed + allB + (size_t)(sa + 1) * MT * bytesA1 <= budget) ++sa;
     } else {
         sa = 2; sb = 2;
         while (true) {      // grow the rings alternately while they fit; B stages are consumed KH times faster

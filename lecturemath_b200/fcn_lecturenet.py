@@ -149,7 +149,7 @@ SMEM_BUDGET = 226 * 1024
 L2_BYTES_PER_CLK_SM = 42.0        # ~6300 B/clk chip-wide L2->SM throughput / 148 SMs (B300_MICROARCH.md)
 EPI_CLK_PER_COL = 40.0            # epilogue cycles per accumulator column of a 128-row tile (8 warps, bias + GELU + store)
 EPI_CLK_PER_TILE = 600.0          # fixed epilogue cost per tile (barrier round trip, tile decode)
-ISSUE_CLK_PER_MMA = 40.0          # the single issuing warp is latency bound: ~6 dependent scalar instructions per tcgen05.mma
+ISSUE_CLK_PER_MMA = 70.0          # an issuing warp is latency bound: measured ~100 clk per tcgen05.mma before the uniform-wait fix
 ISSUE_CLK_PER_DY = (30.0, 150.0)  # per (chunk, dy) step: resident / streamed weights (mbarrier try_wait + commit)
 ISSUE_CLK_PER_CHUNK = 120.0       # per A chunk: full-barrier wait + commit
 
@@ -167,19 +167,28 @@ def layer_cost(nr, h, ntot, runs, kh, batch, n_sm=148):
     bytes_a = (yt + kh - 1) * rt * 128
     bytes_b_all = chunks * kh * nt * 128
     fixed = 2560
-    resident = nnb == 1 and fixed + bytes_b_all + 3 * bytes_a <= SMEM_BUDGET
     n_mtiles = math.ceil(nr / rt) * math.ceil(h / yt) * batch
     ntc = 32
     while ntc < nt:
         ntc *= 2
-    mt = 2 if (not resident and n_mtiles * nnb >= 4 * n_sm and 2 * ntc <= 512) else 1
+    many = n_mtiles * nnb >= 4 * n_sm and 2 * ntc <= 512
+    res2 = nnb == 1 and many and fixed + bytes_b_all + 4 * bytes_a <= SMEM_BUDGET
+    res1 = nnb == 1 and fixed + bytes_b_all + 3 * bytes_a <= SMEM_BUDGET
+    if res2:
+        resident, mt = True, 2
+    elif res1 and (nt >= 128 or not many):
+        resident, mt = True, 1
+    elif many:
+        resident, mt = False, 2
+    else:
+        resident, mt = res1, 1
     t_mma = max(nt / 2.0, (4096 + 32 * nt) / 128.0)                  # tensor floor vs smem operand read, per K=16 step
     mma = 0.0
     for r in runs:
         nck = (r + 63) // 64
         for ck in range(nck):
             ks = 4 if ck < nck - 1 else ((r - ck * 64) + 15) // 16
-            per_dy = max(mt * ks * t_mma, mt * ks * ISSUE_CLK_PER_MMA + ISSUE_CLK_PER_DY[0 if resident else 1])
+            per_dy = max(mt * ks * t_mma, ks * ISSUE_CLK_PER_MMA + ISSUE_CLK_PER_DY[0 if resident else 1])   # one issuer per M-tile
             mma += kh * per_dy + ISSUE_CLK_PER_CHUNK
     mma /= mt
     l2 = (chunks * bytes_a + (0 if resident else chunks * kh * nt * 128 / mt)) / L2_BYTES_PER_CLK_SM
