@@ -6,7 +6,7 @@
 
 A "step" = one pass of the hot path over one batch of synthetic 1080p whiteboard frames (BASELINE.json
 configs[1]).  `value` = whole-job frames/s with the frames already resident in HBM; `e2e` = the same metric
-through ContentExtractor.process_batch with HOST buffers (H2D of the frames and D2H of the result rows inside the
+through StreamingExtractor.submit/collect with HOST buffers (H2D of the frames and D2H of the result rows inside the
 timed region).  Multi-GPU: contiguous frame ranges per rank (weak scaling), temporal matching chained rank to
 rank with the active unique-CC set sent over NCCL (lecturemath_b200/pipeline.py).
 """
@@ -125,7 +125,7 @@ def run_reference(args):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from lecturemath_b200.pipeline import ContentExtractor
+    from lecturemath_b200.pipeline import StreamingExtractor
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -134,103 +134,88 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"             # keeps NCCL's version banner off stdout (rank 0 prints ONE JSON line)
         dist.init_process_group("nccl", device_id=dev)
-    B, K, Wm = args.batch, args.steps, args.warmup
+    B, K, Wm = args.batch, args.steps, max(args.warmup, 3)
     net = make_net()
-    ex = ContentExtractor(net, W, H, 0.85, 0.85, 85, batch=B, device=dev)
+    sx = StreamingExtractor(net, W, H, 0.85, 0.85, 85, batch=B, rank=rank, world=world, device=dev)
     pool_n = max(2 * B, 16)
     pool_h = torch.from_numpy(frame_pool(pool_n, 1234 + rank)).pin_memory()
     pool_d = pool_h.to(dev)
     l2_flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+    main = torch.cuda.current_stream(dev)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def batch_dev(i):
+    def batch_of(pool, i):                                # contiguous slice of the (pinned host | device) frame pool
         s = (i % (pool_n // B)) * B
-        return pool_d[s:s + B]
+        return pool[s:s + B]
 
-    def batch_host(i):                                    # contiguous slice of the pinned host pool (no staging copy)
-        s = (i % (pool_n // B)) * B
-        return pool_h[s:s + B]
-
-    # ---------------- device-resident throughput: K steps, then the shard chain -------------------------
-    def timed_device(n_steps, timing=None, bits_store=None):
+    def run_video(n_steps, host_io, timing=None):
+        """n_steps batches through the hot path (and the rank ring); returns (d2h bytes, CC rows seen)."""
+        d2h = n_cc = 0
         for i in range(n_steps):
-            l2_flush.fill_(i & 0xff)                      # L2 flush between timed iterations (also: activations >> L2)
-            fr = batch_dev(i)
-            if rank == 0:
-                ex.step_device(fr, match=True, timing=timing)
-            else:                                         # phase 1 only; masks are kept for the chained phase 2
-                ex.step_device(fr, match=False, timing=timing)
-                bits_store.append(ex.plan.bits.clone())
+            l2_flush.fill_(i & 0xff)                      # L2 flush between timed iterations (activations >> L2 anyway)
+            sx.submit(batch_of(pool_h if host_io else pool_d, i), last=(i == n_steps - 1), timing=timing)
+            if host_io and i >= 1:
+                rows = sx.collect(i - 1)
+                d2h += sum(r.nbytes for r in rows) + (B + 1) * 4
+                n_cc += sum(len(r) for r in rows)
+        if host_io:
+            rows = sx.collect(n_steps - 1)
+            d2h += sum(r.nbytes for r in rows) + (B + 1) * 4
+            n_cc += sum(len(r) for r in rows)
+        return d2h, n_cc
 
-    def chain(bits_store):
-        if world == 1:
-            return
-        if rank > 0:
-            ex.recv_state(rank - 1)
-            for bits in bits_store:
-                ex.engine.label(bits, want_labels=False, sync=False)
-                ex.est.add_frames(ex.engine, 0, B)
-                ex.launches += 12 + 4 * B
-        if rank + 1 < world:
-            ex.send_state(rank + 1)
-
-    # warm-up
-    store = []
-    timed_device(max(Wm, 3), None, store)
-    chain(store)
+    # warm-up (also initialises the NCCL ring)
+    run_video(Wm, False)
+    sx.reset()                                            # every phase is a new video: fresh temporal state, outside the timed region
     barrier()
-    # fresh temporal state for the timed region
-    from lecturemath_b200.cc_engine import Estimator
-    ex.est = Estimator(W, H, 0.85, 0.85, 85, device=dev)
-    ex.launches = 0
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    timing, store = [], []
+    # ---------------- device-resident throughput: K batches already in HBM ------------------------------------
+    timing = []
+    sx.launches = 0
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    timed_device(K, timing, store)
-    chain(store)
+    run_video(K, False, timing)
     e1.record()
     barrier()
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
-    launches = ex.launches
-    state = ex.est.state()
+    launches = sx.launches
+    state = sx.finish()
     conv_ms = sum(a.elapsed_time(b) for _, a, b in timing)
     per_op = {}
     for i, a, b in timing:
         per_op.setdefault(i, []).append(a.elapsed_time(b))
 
-    # ---------------- end-to-end through the public API with host buffers ----------------------------------
-    ex.est = Estimator(W, H, 0.85, 0.85, 85, device=dev)
-    for i in range(2):
-        ex.process_batch(batch_host(i))
-    ex.est = Estimator(W, H, 0.85, 0.85, 85, device=dev)
+    # ---------------- end to end through the public API with HOST buffers -------------------------------------
+    sx.reset()
+    run_video(2, True)
+    sx.reset()
     barrier()
-    t0 = time.perf_counter()
     e0.record()
-    d2h = 0
-    n_cc = 0
-    for i in range(K):
-        rows = ex.process_batch(batch_host(i))
-        d2h += sum(r.nbytes for r in rows) + B * 16
-        n_cc += sum(len(r) for r in rows)
+    d2h, n_cc = run_video(K, True)
     e1.record()
     barrier()
     e2e_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_ms = float(e2e_ms.item())
-    masks = ex.masks_host()
+    state_e2e = sx.finish()
+    fin = torch.tensor([state_e2e["n_unique"], state_e2e["tempo_count"]], dtype=torch.int64, device=dev)
+    if world > 1:                                         # the final temporal state lives on the last rank of the ring
+        dist.broadcast(fin, src=world - 1)
+    masks = sx.masks_host()
     ink_pct = 100.0 * float((masks != 0).mean())
     if rank == 0:
         sampler.stop_flag = True
@@ -240,7 +225,7 @@ def run_ours(args):
         peaks, peak_kind = measured_peaks()
         frames_total = world * K * B
         fps = frames_total / (ms_total / 1000.0)
-        flops_step = ex.plan.flops * B
+        flops_step = sx.plan.flops * B
         conv_ms_step = conv_ms / max(K, 1)
         achieved = flops_step / (conv_ms_step / 1000.0) / 1e12
         n_conv = len(per_op)
@@ -249,7 +234,7 @@ def run_ours(args):
                                              "heads share one launch)" % n_conv,
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "peak_kind": peak_kind + " bf16_tflops_sustained (kernel timed inside a long step)",
-                "traffic": None, "flop_per_step": flops_step, "conv_ms_per_step": conv_ms_step,
+                "traffic": args.traffic, "flop_per_step": flops_step, "conv_ms_per_step": conv_ms_step,
                 "conv_share_of_step": conv_ms_step / (ms_total / K)}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -262,28 +247,32 @@ def run_ours(args):
             dt = cpu_reference_pass(fr[1:4], sd, est)
             cpu = {"value": 3 / dt, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
                    "sample": "3 timed 1080p frames of this workload after 1 warm-up frame (torch-CPU fp32 FCN, oracle CC stage)"}
-        line = {"metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": max(Wm, 3),
+        line = {"metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
                 "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": "1080p synthetic whiteboard video, binarize + CC label/stats + temporal match on B200 "
                                        "(BASELINE configs[1])", "frames_per_step_per_gpu": B, "frame": [H, W],
                            "weights": "random-init seed 0 (FCN_LectureNet.conf widths)", "l2": "256 MB flush write between steps",
-                           "parallelism": "frame-range shards x%d, chained temporal matching" % world,
+                           "parallelism": "frame chunks of %d round-robin over %d GPU(s); temporal matching is one ordered scan, its "
+                                          "active-set state handed rank to rank over NCCL (ring), overlapped with the next chunk's FCN"
+                                          % (B, world),
                            "ink_pct": round(ink_pct, 2), "ccs_per_frame": round(n_cc / max(K * B, 1), 1),
-                           "unique_ccs": state["n_unique"], "tempo_count": state["tempo_count"]},
+                           "unique_ccs": int(fin[0].item()), "tempo_count": int(fin[1].item())},
                 "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu,
                 "e2e": {"value": world * K * B / (e2e_ms / 1000.0), "unit": "frames/s", "h2d_bytes_per_step": B * H * W * 3,
                         "d2h_bytes_per_step": int(d2h / max(K, 1))},
                 "gpu_launches": launches}
         print(json.dumps(line))
+        sys.stdout.flush()
         if args.layer_table:
-            names = {}
             rows = []
             for i in sorted(per_op):
-                d = ex.plan.ops[i][1]
+                d = sx.plan.ops[i][1]
                 t = float(np.mean(per_op[i]))
-                fl = ex.plan.op_flops.get(i, 0) * B
+                fl = sx.plan.op_flops.get(i, 0) * B
+                info = sx.plan.conv_plan_info(i)
                 rows.append({"op": i, "N": d.NT, "Ntot": d.Ntot, "KH": d.KH, "S": d.Sx if d.Sy == 1 else 1, "RT": d.RT, "YT": d.YT,
+                             "MT": info[0], "resident": info[1], "acc_stages": info[2], "stagesA": info[3], "stagesB": info[4],
                              "ms": round(t, 4), "tflops": round(fl / (t / 1000.0) / 1e12, 1)})
             with open(args.layer_table, "w") as f:
                 json.dump(rows, f, indent=1)
@@ -300,6 +289,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--layer-table", default=None, help="write per-layer conv timings (json) here")
+    ap.add_argument("--traffic", type=float, default=None,
+                    help="dram__bytes_read+write per conv launch (bytes, from profiles/ ncu --set full) to report in roofline.traffic")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

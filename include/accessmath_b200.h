@@ -86,6 +86,11 @@ int am_est_export_sizes(am_estimator* est, long long* h_sizes, void* stream);
 int am_est_export(am_estimator* est, int* d_meta, uint32_t* d_crops, void* stream);
 int am_est_import(am_estimator* est, int n_active, int n_unique, int img_idx, unsigned long long tempo_count,
                   const int* d_meta, const uint32_t* d_crops, long long crop_words, void* stream);
+/* the same hand-off without any host synchronisation (sizes stay on the device): ONE fixed-capacity int32 buffer
+ *   d_buf[0..16) = n_active, crop_words, n_unique, img_idx, tempo_count lo, hi, flags (non-zero = did not fit), 0...
+ *   d_buf[16..)  = meta[n_active][10] as above, then the crops.  A failed hand-off surfaces in am_est_state(). */
+int am_est_export_dev(am_estimator* est, int* d_buf, long long capacity_words, void* stream);
+int am_est_import_dev(am_estimator* est, const int* d_buf, void* stream);
 
 /* ===== 6. FCN-LectureNet binarizer (tcgen05 implicit GEMM) ===================================
  * Replaces the PyTorch arithmetic of FCN_LectureNet.forward / binarize
@@ -124,6 +129,7 @@ typedef struct am_conv_desc {
 } am_conv_desc;
 #define AM_CONV_NO_RESIDENT 1      /* always stream the weights through the B ring */
 #define AM_CONV_NO_MT2 2           /* one M-tile per work item even when two would share the weight tiles */
+#define AM_CONV_FORCE_MT2 4        /* two M-tiles per work item (two MMA issuer warps) whenever TMEM and smem allow */
 
 /* one launch: encodes the tensor maps, picks the tiling and runs the persistent tcgen05 kernel */
 int am_conv_gemm(const am_conv_desc* desc, void* stream);

@@ -34,6 +34,8 @@ SIGNATURES = {
     "am_est_export_sizes": (c_int, [c_void_p, c_void_p, c_void_p]),
     "am_est_export": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "am_est_import": (c_int, [c_void_p, c_int, c_int, c_int, c_ull, c_void_p, c_void_p, c_ll, c_void_p]),
+    "am_est_export_dev": (c_int, [c_void_p, c_void_p, c_ll, c_void_p]),
+    "am_est_import_dev": (c_int, [c_void_p, c_void_p, c_void_p]),
     "am_conv_gemm": (c_int, [c_void_p, c_void_p]),
     "am_conv_plan_create": (c_void_p, [c_void_p]),
     "am_conv_plan_destroy": (None, [c_void_p]),

@@ -110,6 +110,13 @@ class CCEngine:
         return rows[:total_cap], offs
 
 
+    def pack_rows_into(self, rows, offs, batch=None):
+        """Asynchronous variant: kept rows of the batch into the preallocated `rows` (cap, 8) / `offs` (batch+1,) CUDA
+        tensors; rows beyond the capacity are dropped (offs[batch] still holds the true total)."""
+        b = batch or self.batch
+        _lib.check(self.lib.am_cc_pack_rows(self.ctx, b, _p(rows), rows.shape[0], _p(offs), _stream()), "am_cc_pack_rows")
+
+
 class Estimator:
     """Handle on the device-side temporal matcher (am_est_*)."""
 
@@ -165,6 +172,14 @@ class Estimator:
         st = self.state()
         header = torch.tensor([n_act, words, st["n_unique"], st["img_idx"], st["tempo_count"], 0], dtype=torch.int64)
         return header, meta, crops
+
+    def export_dev(self, buf):
+        """Asynchronous: pack the active set into the fixed-capacity int32 CUDA tensor `buf` (no host sync)."""
+        _lib.check(self.lib.am_est_export_dev(self.h, _p(buf), buf.numel(), _stream()), "am_est_export_dev")
+
+    def import_dev(self, buf):
+        """Asynchronous: replace this estimator's state by the active set packed in `buf`."""
+        _lib.check(self.lib.am_est_import_dev(self.h, _p(buf), _stream()), "am_est_import_dev")
 
     def import_state(self, header, meta, crops):
         n_act, words, n_unique, img_idx, tempo = [int(v) for v in header[:5]]

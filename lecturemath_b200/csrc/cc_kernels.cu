@@ -755,6 +755,101 @@ __global__ void k_import(int n, const int* __restrict__ meta, const uint32_t* __
     for (int i = threadIdx.x; i < (int)min(carry, (unsigned long long)0x7fffffff); i += blockDim.x) arena[i] = crops[i];
 }
 
+// ------------------------------------------------------------------------------------------------
+// Fully asynchronous hand-off (no host read-back of sizes): the active set travels in ONE fixed-capacity buffer
+//   buf[0..16)  header: n_active, crop_words, n_unique, img_idx, tempo_count lo/hi, flags (1 = did not fit), 0...
+//   buf[16 ..)  meta [n_active][10] (same rows as k_export), then the crops, concatenated in meta order
+#define XHDR 16
+__global__ void k_export_dev_meta(const int* __restrict__ act, const int* __restrict__ scal, const unsigned long long* __restrict__ scal64,
+                                  const int* u_min_x, const int* u_max_x, const int* u_min_y, const int* u_max_y, const int* u_size,
+                                  const int* u_last, const int* u_ff, const int* u_fl, int* __restrict__ buf, long long cap,
+                                  unsigned long long* __restrict__ tmp_off) {
+    __shared__ int sm[33];
+    const int n = scal[1];
+    const bool meta_fits = (long long)XHDR + (long long)n * 10 <= cap;
+    unsigned long long carry = 0;
+    for (int i0 = 0; i0 < n; i0 += blockDim.x) {
+        int i = i0 + threadIdx.x;
+        int words = 0, u = 0;
+        if (i < n) { u = act[i]; words = crop_words_of(u_min_x[u], u_max_x[u], u_min_y[u], u_max_y[u]); }
+        int tot;
+        int ex = block_excl_scan(words, sm, &tot);
+        __syncthreads();
+        if (i < n) {
+            if (meta_fits) {
+                int* m = buf + XHDR + (size_t)i * 10;
+                m[0] = u; m[1] = u_min_x[u]; m[2] = u_max_x[u]; m[3] = u_min_y[u]; m[4] = u_max_y[u]; m[5] = u_size[u];
+                m[6] = u_last[u]; m[7] = u_ff[u]; m[8] = u_fl[u]; m[9] = words;
+            }
+            tmp_off[i] = carry + (unsigned long long)ex;
+        }
+        carry += (unsigned long long)tot;
+    }
+    if (threadIdx.x == 0) {
+        const bool fits = (long long)XHDR + (long long)n * 10 + (long long)carry <= cap;
+        buf[0] = n; buf[1] = (int)carry; buf[2] = scal[0]; buf[3] = scal[2];
+        buf[4] = (int)(scal64[0] & 0xffffffffull); buf[5] = (int)(scal64[0] >> 32);
+        buf[6] = (fits ? 0 : 1) | (scal[3] ? 2 : 0);                   // 1: hand-off buffer too small, 2: sender already overflowed
+        for (int k = 7; k < XHDR; ++k) buf[k] = 0;
+    }
+}
+__global__ void k_export_dev_crops(const int* __restrict__ act, const int* __restrict__ scal, const int* u_min_x, const int* u_max_x,
+                                   const int* u_min_y, const int* u_max_y, const unsigned long long* __restrict__ u_crop_off,
+                                   const uint32_t* __restrict__ arena, int* __restrict__ buf, long long cap,
+                                   const unsigned long long* __restrict__ tmp_off) {
+    const int n = scal[1];
+    const long long base = (long long)XHDR + (long long)n * 10;
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        const int u = act[i];
+        const int words = crop_words_of(u_min_x[u], u_max_x[u], u_min_y[u], u_max_y[u]);
+        const long long dst0 = base + (long long)tmp_off[i];
+        if (dst0 + words > cap) continue;                               // flagged in the header
+        const uint32_t* src = arena + u_crop_off[u];
+        uint32_t* dst = (uint32_t*)buf + dst0;
+        for (int k = threadIdx.x; k < words; k += blockDim.x) dst[k] = src[k];
+    }
+}
+__global__ void k_import_dev_meta(const int* __restrict__ buf, int* act, int* scal, unsigned long long* scal64, int* u_min_x, int* u_max_x,
+                                  int* u_min_y, int* u_max_y, int* u_size, int* u_last, int* u_ff, int* u_fl,
+                                  unsigned long long* u_crop_off, int MU, int MA, unsigned long long AW) {
+    __shared__ int sm[33];
+    const int n = buf[0];
+    const bool ok = buf[6] == 0 && n <= MA && buf[2] <= MU && (unsigned long long)(unsigned)buf[1] <= AW;
+    const int* meta = buf + XHDR;
+    unsigned long long carry = 0;
+    for (int i0 = 0; ok && i0 < n; i0 += blockDim.x) {
+        int i = i0 + threadIdx.x;
+        int words = (i < n) ? meta[(size_t)i * 10 + 9] : 0;
+        int tot;
+        int ex = block_excl_scan(words, sm, &tot);
+        __syncthreads();
+        if (i < n) {
+            const int* m = meta + (size_t)i * 10;
+            int u = m[0];
+            if (u >= 0 && u < MU) {
+                u_min_x[u] = m[1]; u_max_x[u] = m[2]; u_min_y[u] = m[3]; u_max_y[u] = m[4]; u_size[u] = m[5];
+                u_last[u] = m[6]; u_ff[u] = m[7]; u_fl[u] = m[8];
+                u_crop_off[u] = carry + (unsigned long long)ex;
+            }
+            act[i] = u;
+        }
+        carry += (unsigned long long)tot;
+    }
+    if (threadIdx.x == 0) {
+        scal[0] = buf[2]; scal[1] = ok ? n : 0; scal[2] = buf[3]; scal[3] = ok ? 0 : 32;   // 32: hand-off failed
+        scal[4] = 0; scal[5] = 0;
+        scal64[0] = ((unsigned long long)(unsigned)buf[5] << 32) | (unsigned long long)(unsigned)buf[4];
+        scal64[1] = ok ? (unsigned long long)(unsigned)buf[1] : 0ull;
+    }
+}
+__global__ void k_import_dev_crops(const int* __restrict__ buf, uint32_t* __restrict__ arena, unsigned long long AW) {
+    if (buf[6] != 0) return;
+    const long long base = (long long)XHDR + (long long)buf[0] * 10;
+    const long long n = min((long long)(unsigned)buf[1], (long long)AW);
+    const uint32_t* src = (const uint32_t*)buf + base;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) arena[i] = src[i];
+}
+
 // ================================================================================================
 // Host side: C ABI
 // ================================================================================================
@@ -1018,7 +1113,7 @@ extern "C" int am_est_state(am_estimator* e, int* h_state, void* stream) {
     h_state[0] = e->h_scal[0]; h_state[1] = e->h_scal[1]; h_state[2] = e->h_scal[2]; h_state[3] = e->h_scal[3];
     h_state[4] = (int)(e->h_scal64[0] & 0xffffffffull); h_state[5] = (int)(e->h_scal64[0] >> 32);
     if (e->h_scal[3]) {
-        fprintf(stderr, "[accessmath_b200] estimator capacity exceeded (flags 0x%x: 8=uniques/active/arena 16=candidate pairs)\n", e->h_scal[3]);
+        fprintf(stderr, "[accessmath_b200] estimator capacity exceeded (flags 0x%x: 8=uniques/active/arena 16=candidate pairs 32=shard hand-off)\n", e->h_scal[3]);
         return AM_ERR_CAPACITY;
     }
     return AM_OK;
@@ -1080,5 +1175,24 @@ extern "C" int am_est_import(am_estimator* e, int n_active, int n_unique, int im
     AM_CUDA(cudaMemcpyAsync(e->d_scal, sc, 16, cudaMemcpyHostToDevice, S(stream)));
     AM_CUDA(cudaMemcpyAsync(e->d_scal64, sc64, 16, cudaMemcpyHostToDevice, S(stream)));
     AM_CUDA(cudaStreamSynchronize(S(stream)));
+    return AM_OK;
+}
+
+// Asynchronous hand-off: everything (sizes included) stays on the device, nothing synchronises the host.
+extern "C" int am_est_export_dev(am_estimator* e, int* d_buf, long long capacity_words, void* stream) {
+    if (!e || !d_buf || capacity_words < XHDR) return AM_ERR_ARG;
+    k_export_dev_meta<<<1, 1024, 0, S(stream)>>>(e->act[e->cur], e->d_scal, e->d_scal64, e->u_min_x, e->u_max_x, e->u_min_y, e->u_max_y,
+                                                 e->u_size, e->u_last, e->u_first_frame, e->u_first_label, d_buf, capacity_words, est_tmp(e));
+    k_export_dev_crops<<<148, 256, 0, S(stream)>>>(e->act[e->cur], e->d_scal, e->u_min_x, e->u_max_x, e->u_min_y, e->u_max_y, e->u_crop_off,
+                                                   e->arena, d_buf, capacity_words, est_tmp(e));
+    AM_CUDA(cudaGetLastError());
+    return AM_OK;
+}
+extern "C" int am_est_import_dev(am_estimator* e, const int* d_buf, void* stream) {
+    if (!e || !d_buf) return AM_ERR_ARG;
+    k_import_dev_meta<<<1, 1024, 0, S(stream)>>>(d_buf, e->act[e->cur], e->d_scal, e->d_scal64, e->u_min_x, e->u_max_x, e->u_min_y, e->u_max_y,
+                                                 e->u_size, e->u_last, e->u_first_frame, e->u_first_label, e->u_crop_off, e->MU, e->MA, e->AW);
+    k_import_dev_crops<<<148, 256, 0, S(stream)>>>(d_buf, e->arena, e->AW);
+    AM_CUDA(cudaGetLastError());
     return AM_OK;
 }

@@ -39,6 +39,7 @@
 #endif                                    // epilogue is latency bound -- TMEM load, MUFU -- so more warps hide more of it)
 #define EPI_PER_Q (EPI_WARPS / 4)
 #define CONV_THREADS (128 + 32 * EPI_WARPS)
+#define SCHED_DEPTH 4                     // work-item ring between the producer (fetches with atomicAdd) and its consumers
 
 struct alignas(64) ConvParams {
     CUtensorMap tmA[2];
@@ -65,6 +66,7 @@ struct alignas(64) ConvParams {
     int Cout, Sy, Sx, Ntot, act;
     unsigned cout_magic;  // floor(2^32 / Cout) + 1 (Cout >= 2)
     const float* bias;
+    int* work_counter;    // [0] next work item (dynamic tile scheduler), [1] CTAs finished (the last one resets both)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -203,6 +205,86 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int t) {
     return c;
 }
 
+// Epilogue of one 16-column unit of one accumulator row: bias + activation + NHWC store.
+__device__ __forceinline__ void epi_unit(const ConvParams& p, const uint32_t (&v)[16], const float* __restrict__ sbias, int n0, int j0,
+                                         long long base, bool vec8, bool f32fast) {
+    if (vec8) {
+        // two 8-channel groups; a group never straddles a pixel because Cout % 8 == 0
+        uint4 pk[2]; long long offs[2]; bool ok[2];
+#pragma unroll
+        for (int gg = 0; gg < 2; ++gg) {
+            const int n = n0 + j0 + gg * 8;
+            ok[gg] = n < p.Ntot;
+            const int grp = (int)__umulhi((unsigned)n, p.cout_magic), co = n - grp * p.Cout;
+            const int sy = (p.Sy == 2 && grp >= p.Sx) ? 1 : 0, sx = grp - sy * p.Sx;
+            offs[gg] = base + (long long)sy * p.out_sy + (long long)sx * p.out_sx + co;
+            const float4 b0 = *(const float4*)(sbias + j0 + gg * 8), b1 = *(const float4*)(sbias + j0 + gg * 8 + 4);
+            float f[8] = {__uint_as_float(v[gg * 8 + 0]) + b0.x, __uint_as_float(v[gg * 8 + 1]) + b0.y, __uint_as_float(v[gg * 8 + 2]) + b0.z,
+                          __uint_as_float(v[gg * 8 + 3]) + b0.w, __uint_as_float(v[gg * 8 + 4]) + b1.x, __uint_as_float(v[gg * 8 + 5]) + b1.y,
+                          __uint_as_float(v[gg * 8 + 6]) + b1.z, __uint_as_float(v[gg * 8 + 7]) + b1.w};
+            if (p.act == 1) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] = gelu_erf(f[i]);
+            }
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]), h1 = __floats2bfloat162_rn(f[2], f[3]);
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(f[4], f[5]), h3 = __floats2bfloat162_rn(f[6], f[7]);
+            pk[gg].x = *(uint32_t*)&h0; pk[gg].y = *(uint32_t*)&h1; pk[gg].z = *(uint32_t*)&h2; pk[gg].w = *(uint32_t*)&h3;
+        }
+        __nv_bfloat16* o = (__nv_bfloat16*)p.out;
+        if (ok[0] && ok[1] && offs[1] == offs[0] + 8 && ((offs[0] & 15) == 0)) {
+            // 32 contiguous, 32-byte aligned bytes: one full sector per thread (STG.256)
+            asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(o + offs[0]), "r"(pk[0].x), "r"(pk[0].y), "r"(pk[0].z),
+                         "r"(pk[0].w), "r"(pk[1].x), "r"(pk[1].y), "r"(pk[1].z), "r"(pk[1].w) : "memory");
+        } else {
+            if (ok[0]) *(uint4*)(o + offs[0]) = pk[0];
+            if (ok[1]) *(uint4*)(o + offs[1]) = pk[1];
+        }
+    } else if (f32fast) {
+        // fp32 heads / logits: the row's N columns are contiguous in memory (n = sx*Cout + co)
+        float* o = (float*)p.out + base + n0 + j0;
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+            if (n0 + j0 + i >= p.Ntot) break;
+            float4 f;
+            f.x = __uint_as_float(v[i]) + sbias[j0 + i]; f.y = __uint_as_float(v[i + 1]) + sbias[j0 + i + 1];
+            f.z = __uint_as_float(v[i + 2]) + sbias[j0 + i + 2]; f.w = __uint_as_float(v[i + 3]) + sbias[j0 + i + 3];
+            if (p.act == 1) { f.x = gelu_erf(f.x); f.y = gelu_erf(f.y); f.z = gelu_erf(f.z); f.w = gelu_erf(f.w); }
+            *(float4*)(o + i) = f;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int n = n0 + j0 + i;
+            if (n >= p.Ntot) break;
+            const int grp = n / p.Cout, co = n - grp * p.Cout;
+            const int sy = grp / p.Sx, sx = grp - sy * p.Sx;
+            const long long off = base + (long long)sy * p.out_sy + (long long)sx * p.out_sx + co;
+            float x = __uint_as_float(v[i]) + sbias[j0 + i];
+            x = p.act == 1 ? gelu_erf(x) : x;
+            if (p.out_f32) ((float*)p.out)[off] = x;
+            else ((__nv_bfloat16*)p.out)[off] = __float2bfloat16_rn(x);
+        }
+    }
+}
+
+// Dynamic tile scheduler: the producer warp draws work items from a global counter and publishes them through a small
+// shared-memory ring; MMA issuers and epilogue warps consume the ring (-1 = no more work).  Unlike a static
+// blockIdx-strided loop this tolerates SMs that are busy with other streams' kernels (NCCL hand-off, temporal matching).
+__device__ __forceinline__ int sched_fetch(int* counter, int lane) {
+    int v = 0;
+    if (lane == 0) v = atomicAdd(counter, 1);
+    return __shfl_sync(0xffffffffu, v, 0);
+}
+__device__ __forceinline__ int sched_next(uint32_t schedFull, uint32_t schedEmpty, uint32_t sched_w, int& slot, uint32_t& phase, int lane) {
+    mbar_wait(schedFull + 8 * slot, phase);
+    int w;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(sched_w + 4 * slot) : "memory");
+    __syncwarp();
+    if (lane == 0) mbar_arrive(schedEmpty + 8 * slot);
+    if (++slot == SCHED_DEPTH) { slot = 0; phase ^= 1; }
+    return w;
+}
+
 // kMT = M-tiles per work item, kRES = weights resident in shared memory (compile-time so the single-warp issue loops stay short)
 template <int kMT, bool kRES>
 __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv_gemm(const __grid_constant__ ConvParams p) {
@@ -220,7 +302,9 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv_gemm(const __grid_cons
     // barriers: fullA[sA], emptyA[sA], fullB[sB], emptyB[sB], accFull[2], accEmpty[2]
     const uint32_t fullA = bar0, emptyA = fullA + 8 * p.stagesA, fullB = emptyA + 8 * p.stagesA, emptyB = fullB + 8 * p.stagesB;
     const uint32_t accFull = emptyB + 8 * p.stagesB, accEmpty = accFull + 16;
-    const uint32_t tmem_slot = accEmpty + 16;
+    const uint32_t schedFull = accEmpty + 16, schedEmpty = schedFull + 8 * SCHED_DEPTH;
+    const uint32_t sched_w = schedEmpty + 8 * SCHED_DEPTH;             // SCHED_DEPTH ints
+    const uint32_t tmem_slot = sched_w + 4 * SCHED_DEPTH;
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform for ptxas
     const int lane = threadIdx.x & 31;
 
@@ -229,6 +313,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv_gemm(const __grid_cons
         for (int i = 0; i < p.stagesA; ++i) { mbar_init(fullA + 8 * i, 1); mbar_init(emptyA + 8 * i, kMT); }
         for (int i = 0; i < p.stagesB; ++i) { mbar_init(fullB + 8 * i, 1); mbar_init(emptyB + 8 * i, kMT); }
         for (int i = 0; i < 2; ++i) { mbar_init(accFull + 8 * i, kMT); mbar_init(accEmpty + 8 * i, EPI_WARPS); }
+        for (int i = 0; i < SCHED_DEPTH; ++i) { mbar_init(schedFull + 8 * i, 1); mbar_init(schedEmpty + 8 * i, kMT + EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         tma_prefetch_desc(&p.tmA[0]);
         if (p.nseg > 1) tma_prefetch_desc(&p.tmA[1]);
@@ -254,7 +339,19 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv_gemm(const __grid_cons
             }
             __syncwarp();
         }
-        for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
+        int slot = 0; uint32_t ps = 0;
+        int w_next = sched_fetch(p.work_counter, lane);
+        while (true) {
+            const int w = w_next < p.n_work ? w_next : -1;
+            mbar_wait_uniform(schedEmpty + 8 * slot, ps ^ 1);
+            if (elect_one()) {
+                asm volatile("st.shared.b32 [%0], %1;" ::"r"(sched_w + 4 * slot), "r"(w) : "memory");
+                mbar_arrive(schedFull + 8 * slot);
+            }
+            __syncwarp();
+            if (++slot == SCHED_DEPTH) { slot = 0; ps ^= 1; }
+            if (w < 0) break;
+            w_next = sched_fetch(p.work_counter, lane);                  // latency hidden behind this item's loads
             const int st = w / p.nNB, nb = w - st * p.nNB;
             const int n0 = nb * p.NT;
             const TileCoord tc0 = decode_tile(p, st * kMT);
@@ -302,7 +399,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv_gemm(const __grid_cons
         int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
         int as = 0; uint32_t pacc = 0;
         if (kRES) { mbar_wait_uniform(fullB, 0); tc_fence_after(); }
-        for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
+        int slot = 0; uint32_t ps = 0;
+        while (sched_next(schedFull, schedEmpty, sched_w, slot, ps, lane) >= 0) {
             mbar_wait_uniform(accEmpty + 8 * as, pacc ^ 1);              // epilogue drained this accumulator stage
             tc_fence_after();
             const uint32_t td = tmem_base + (uint32_t)(as * kMT + mt) * NTc;
@@ -356,7 +454,11 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv_gemm(const __grid_cons
         const int units_per_tile = p.NT >> 4;
         const int units = units_per_tile * kMT;
         const bool vec8 = (p.Cout & 7) == 0 && !p.out_f32;
-        for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
+        const bool f32fast = p.out_f32 && p.out_sx == p.Cout && p.Sy == 1 && p.out_coff == 0 && ((p.Ntot | (int)p.out_sy | (int)p.out_sn) & 3) == 0;
+        int slot = 0; uint32_t ps = 0;
+        while (true) {
+            const int w = sched_next(schedFull, schedEmpty, sched_w, slot, ps, lane);
+            if (w < 0) break;
             const int st = w / p.nNB, nb = w - st * p.nNB;
             const int n0 = nb * p.NT;
             if (nb != bias_nb) {
@@ -368,24 +470,18 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv_gemm(const __grid_cons
             mbar_wait(accFull + 8 * as, pacc);
             tc_fence_after();
             const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * kMT * p.NTc);
+            // software pipeline over this warp's 16-column units: the TMEM load of the next unit is in flight while the
+            // current one is processed; two register sets ping-pong (no copies)
             uint32_t va[16], vb[16];
-            int g = h;
-            if (g < units) {
-                const int mt = g >= units_per_tile ? 1 : 0, u = g - mt * units_per_tile;
-                tmem_ld16_async(tacc + (uint32_t)(mt * p.NTc + u * 16), va);
-            }
             int cur_mt = -1;
             bool row_ok = false;
             long long base = 0;
-            for (; g < units; g += EPI_PER_Q) {
-                const int mt = g >= units_per_tile ? 1 : 0, u = g - mt * units_per_tile;
-                tmem_wait16(va);
-#pragma unroll
-                for (int i = 0; i < 16; ++i) vb[i] = va[i];
-                if (g + EPI_PER_Q < units) {
-                    const int mt2 = (g + EPI_PER_Q) >= units_per_tile ? 1 : 0, u2 = (g + EPI_PER_Q) - mt2 * units_per_tile;
-                    tmem_ld16_async(tacc + (uint32_t)(mt2 * p.NTc + u2 * 16), va);
-                }
+            auto unit_addr = [&](int g) -> uint32_t {
+                const int mt = g >= units_per_tile ? 1 : 0;
+                return tacc + (uint32_t)(mt * p.NTc + (g - mt * units_per_tile) * 16);
+            };
+            auto enter = [&](int g) -> int {                 // (re)compute the row's output base when the M-tile changes; returns j0
+                const int mt = g >= units_per_tile ? 1 : 0;
                 if (mt != cur_mt) {
                     cur_mt = mt;
                     const TileCoord tc = decode_tile(p, st * kMT + mt);
@@ -394,62 +490,22 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv_gemm(const __grid_cons
                     base = (long long)tc.frame * p.out_sn + (long long)(p.Sy * y) * p.out_sy + (long long)(p.Sx * r + p.out_padx) * p.out_sx + p.out_coff;
                     if (p.Sy * y + p.Sy > p.out_H || p.Sx * r + p.Sx > p.out_W) row_ok = false;   // never true for the FCN's shapes
                 }
-                if (!row_ok) continue;
-                const int j0 = u * 16;
-                if (vec8) {
-                    // two 8-channel groups; a group never straddles a pixel because Cout % 8 == 0
-                    uint4 pk[2]; long long offs[2]; bool ok[2];
-#pragma unroll
-                    for (int gg = 0; gg < 2; ++gg) {
-                        const int n = n0 + j0 + gg * 8;
-                        ok[gg] = n < p.Ntot;
-                        const int grp = (int)__umulhi((unsigned)n, p.cout_magic), co = n - grp * p.Cout;
-                        const int sy = (p.Sy == 2 && grp >= p.Sx) ? 1 : 0, sx = grp - sy * p.Sx;
-                        offs[gg] = base + (long long)sy * p.out_sy + (long long)sx * p.out_sx + co;
-                        float f[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            float x = __uint_as_float(vb[gg * 8 + i]) + sbias[j0 + gg * 8 + i];
-                            f[i] = p.act == 1 ? gelu_erf(x) : x;
-                        }
-                        __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]), h1 = __floats2bfloat162_rn(f[2], f[3]);
-                        __nv_bfloat162 h2 = __floats2bfloat162_rn(f[4], f[5]), h3 = __floats2bfloat162_rn(f[6], f[7]);
-                        pk[gg].x = *(uint32_t*)&h0; pk[gg].y = *(uint32_t*)&h1; pk[gg].z = *(uint32_t*)&h2; pk[gg].w = *(uint32_t*)&h3;
-                    }
-                    __nv_bfloat16* o = (__nv_bfloat16*)p.out;
-                    if (ok[0] && ok[1] && offs[1] == offs[0] + 8 && ((offs[0] & 15) == 0)) {
-                        // 32 contiguous, 32-byte aligned bytes: one full sector per thread (STG.256)
-                        asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(o + offs[0]), "r"(pk[0].x), "r"(pk[0].y), "r"(pk[0].z),
-                                     "r"(pk[0].w), "r"(pk[1].x), "r"(pk[1].y), "r"(pk[1].z), "r"(pk[1].w) : "memory");
-                    } else {
-                        if (ok[0]) *(uint4*)(o + offs[0]) = pk[0];
-                        if (ok[1]) *(uint4*)(o + offs[1]) = pk[1];
-                    }
-                } else if (p.out_f32 && p.out_sx == p.Cout && p.Sy == 1 && p.out_coff == 0 && ((p.Ntot | (int)p.out_sy | (int)p.out_sn) & 3) == 0) {
-                    // fp32 heads / logits: the row's N columns are contiguous in memory (n = sx*Cout + co)
-                    float* o = (float*)p.out + base + n0 + j0;
-#pragma unroll
-                    for (int i = 0; i < 16; i += 4) {
-                        if (n0 + j0 + i >= p.Ntot) break;
-                        float4 f;
-                        f.x = __uint_as_float(vb[i]) + sbias[j0 + i]; f.y = __uint_as_float(vb[i + 1]) + sbias[j0 + i + 1];
-                        f.z = __uint_as_float(vb[i + 2]) + sbias[j0 + i + 2]; f.w = __uint_as_float(vb[i + 3]) + sbias[j0 + i + 3];
-                        if (p.act == 1) { f.x = gelu_erf(f.x); f.y = gelu_erf(f.y); f.z = gelu_erf(f.z); f.w = gelu_erf(f.w); }
-                        *(float4*)(o + i) = f;
-                    }
-                } else {
-                    for (int i = 0; i < 16; ++i) {
-                        const int n = n0 + j0 + i;
-                        if (n >= p.Ntot) break;
-                        const int grp = n / p.Cout, co = n - grp * p.Cout;
-                        const int sy = grp / p.Sx, sx = grp - sy * p.Sx;
-                        const long long off = base + (long long)sy * p.out_sy + (long long)sx * p.out_sx + co;
-                        float x = __uint_as_float(vb[i]) + sbias[j0 + i];
-                        x = p.act == 1 ? gelu_erf(x) : x;
-                        if (p.out_f32) ((float*)p.out)[off] = x;
-                        else ((__nv_bfloat16*)p.out)[off] = __float2bfloat16_rn(x);
-                    }
-                }
+                return (g - mt * units_per_tile) * 16;
+            };
+            int g = h;
+            if (g < units) tmem_ld16_async(unit_addr(g), va);
+            while (g < units) {
+                tmem_wait16(va);
+                int g2 = g + EPI_PER_Q;
+                if (g2 < units) tmem_ld16_async(unit_addr(g2), vb);
+                { const int j0 = enter(g); if (row_ok) epi_unit(p, va, sbias, n0, j0, base, vec8, f32fast); }
+                g = g2;
+                if (g >= units) break;
+                tmem_wait16(vb);
+                g2 = g + EPI_PER_Q;
+                if (g2 < units) tmem_ld16_async(unit_addr(g2), va);
+                { const int j0 = enter(g); if (row_ok) epi_unit(p, vb, sbias, n0, j0, base, vec8, f32fast); }
+                g = g2;
             }
             // all tcgen05.ld of this stage have completed (tmem_wait16 in the last iteration): hand the stage back
             tc_fence_before();
@@ -460,6 +516,10 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv_gemm(const __grid_cons
         tc_fence_before();
     }
     __syncthreads();
+    if (threadIdx.x == 0) {                              // last CTA out re-arms the scheduler for the next launch of this plan
+        __threadfence();
+        if (atomicAdd(p.work_counter + 1, 1) == (int)gridDim.x - 1) { p.work_counter[0] = 0; p.work_counter[1] = 0; __threadfence(); }
+    }
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
@@ -504,6 +564,7 @@ struct am_conv_plan {
     ConvParams p;
     size_t smem;
     int grid;
+    int* d_counter;      // 2 ints, zero between launches
 };
 
 static int sm_count() {
@@ -579,12 +640,15 @@ static int conv_prepare(const am_conv_desc* d, am_conv_plan* plan) {
     //   MT = 2 (two M-tiles per work item, one MMA issuer warp each) whenever there is enough work to keep every SM busy;
     //   resident weights when a single N block's whole packed filter fits next to >= 2 (MT = 2) / 3 (MT = 1) A stages.
     //   Narrow layers (N < 128) are issue bound, so for them two issuers beat resident weights if both do not fit.
-    const bool many = !(d->flags & AM_CONV_NO_MT2) && p.n_mtiles * p.nNB >= 4 * sm_count() && 2 * p.NTc <= 512;
+    const bool tmem2 = 2 * p.NTc <= 512;
+    const bool many = !(d->flags & AM_CONV_NO_MT2) && p.n_mtiles * p.nNB >= 4 * sm_count() && tmem2;
     const bool can_res = !(d->flags & AM_CONV_NO_RESIDENT) && p.nNB == 1;
-    const bool res2 = can_res && many && fixed + allB + 2 * 2 * bytesA1 <= budget;
+    const bool res2 = can_res && fixed + allB + 2 * 2 * bytesA1 <= budget;
     const bool res1 = can_res && fixed + allB + 3 * bytesA1 <= budget;
     int resident, MT;
-    if (res2) { resident = 1; MT = 2; }
+    if ((d->flags & AM_CONV_FORCE_MT2) && tmem2) { MT = 2; resident = res2 ? 1 : 0; }         // the planner decided
+    else if (d->flags & AM_CONV_NO_MT2) { MT = 1; resident = res1 ? 1 : 0; }
+    else if (res2 && many) { resident = 1; MT = 2; }
     else if (res1 && (d->NT >= 128 || !many)) { resident = 1; MT = 1; }
     else if (many) { resident = 0; MT = 2; }
     else { resident = res1 ? 1 : 0; MT = 1; }
@@ -635,16 +699,25 @@ extern "C" int am_conv_gemm(const am_conv_desc* d, void* stream) {
     am_conv_plan plan;
     int rc = conv_prepare(d, &plan);
     if (rc) return rc;
-    return conv_launch(&plan, stream);
+    AM_CUDA(cudaMallocAsync(&plan.d_counter, 8, (cudaStream_t)stream));
+    AM_CUDA(cudaMemsetAsync(plan.d_counter, 0, 8, (cudaStream_t)stream));
+    plan.p.work_counter = plan.d_counter;
+    rc = conv_launch(&plan, stream);
+    AM_CUDA(cudaFreeAsync(plan.d_counter, (cudaStream_t)stream));
+    return rc;
 }
 
 // Prepared form: tensor maps and tiling are computed once per layer, launches reuse them.
 extern "C" am_conv_plan* am_conv_plan_create(const am_conv_desc* d) {
     am_conv_plan* plan = new am_conv_plan();
     if (conv_prepare(d, plan) != AM_OK) { delete plan; return nullptr; }
+    if (cudaMalloc(&plan->d_counter, 8) != cudaSuccess || cudaMemset(plan->d_counter, 0, 8) != cudaSuccess) { delete plan; return nullptr; }
+    plan->p.work_counter = plan->d_counter;
     return plan;
 }
-extern "C" void am_conv_plan_destroy(am_conv_plan* plan) { delete plan; }
+extern "C" void am_conv_plan_destroy(am_conv_plan* plan) {
+    if (plan) { cudaFree(plan->d_counter); delete plan; }
+}
 extern "C" int am_conv_plan_launch(const am_conv_plan* plan, void* stream) {
     if (!plan) return AM_ERR_ARG;
     return conv_launch(plan, stream);

@@ -146,42 +146,56 @@ def pack_weights(w, bias, segs, S, rowrun, NT):
 
 
 SMEM_BUDGET = 226 * 1024
+AM_CONV_NO_MT2, AM_CONV_FORCE_MT2 = 2, 4
 L2_BYTES_PER_CLK_SM = 42.0        # ~6300 B/clk chip-wide L2->SM throughput / 148 SMs (B300_MICROARCH.md)
-EPI_CLK_PER_COL = 40.0            # epilogue cycles per accumulator column of a 128-row tile (8 warps, bias + GELU + store)
+EPI_CLK_PER_COL = 43.0            # epilogue cycles per accumulator column of a 128-row tile (16 warps; ~26 SASS instr/element)
 EPI_CLK_PER_TILE = 600.0          # fixed epilogue cost per tile (barrier round trip, tile decode)
-ISSUE_CLK_PER_MMA = 70.0          # an issuing warp is latency bound: measured ~100 clk per tcgen05.mma before the uniform-wait fix
+ISSUE_CLK_PER_MMA = 110.0         # an issuing warp is latency bound: ~100-120 clk per tcgen05.mma measured on the narrow layers (r01 profiles)
 ISSUE_CLK_PER_DY = (30.0, 150.0)  # per (chunk, dy) step: resident / streamed weights (mbarrier try_wait + commit)
 ISSUE_CLK_PER_CHUNK = 120.0       # per A chunk: full-barrier wait + commit
 
 
-def layer_cost(nr, h, ntot, runs, kh, batch, n_sm=148):
-    """Cycle model of one 128-row M-tile of k_conv_gemm (see csrc/fcn_conv.cu) for GEMM width ntot and per-segment run
-    lengths `runs` (elements of K per vertical tap).  Mirrors conv_prepare()'s choices of resident weights / MT.
-    Calibrated against profiles/ (r01 launch lists): small-N layers are bound by the MMA-issuing warp, not the tensor
-    pipe, which is why the planner prefers N = 128 even though the Toeplitz packing pads K."""
-    nt = choose_nt(ntot)
+def nt_candidates(ntot):
+    """UMMA N per CTA: one block when it fits, else / also equal splits (more N blocks = smaller accumulators, which is
+    what lets two M-tiles AND two accumulator stages share the 512 TMEM columns)."""
+    r16 = ((ntot + 15) // 16) * 16
+    out = []
+    for nt in (256, 192, 128, 96, 64, 48, 32, 16):
+        if nt > r16:
+            continue
+        pad = ((ntot + nt - 1) // nt) * nt
+        if nt == r16 or (pad - ntot) * 10 <= ntot and nt >= 64:
+            out.append(nt)
+    if r16 <= 256 and r16 not in out:
+        out.append(r16)
+    return out
+
+
+def layer_cost(nr, h, ntot, runs, kh, batch, nt=None, mt=None, n_sm=148):
+    """Cycle model of k_conv_gemm (csrc/fcn_conv.cu) for one layer: GEMM width ntot, per-segment run lengths `runs`
+    (elements of K per vertical tap), UMMA N `nt` and `mt` M-tiles per work item.  Mirrors conv_prepare()'s feasibility
+    rules (resident weights, accumulator stages).  Calibrated against profiles/ (r01): narrow layers are bound by the
+    MMA-issuing warps, single-stage accumulators serialise main loop and epilogue.  Returns None when infeasible."""
+    nt = nt or choose_nt(ntot)
     ntot_pad = ((ntot + nt - 1) // nt) * nt
     nnb = ntot_pad // nt
     rt, yt = choose_tile(nr, h, kh)
     chunks = sum((r + 63) // 64 for r in runs)
-    bytes_a = (yt + kh - 1) * rt * 128
-    bytes_b_all = chunks * kh * nt * 128
+    bytes_a, bytes_b = (yt + kh - 1) * rt * 128, nt * 128
+    bytes_b_all = chunks * kh * bytes_b
     fixed = 2560
     n_mtiles = math.ceil(nr / rt) * math.ceil(h / yt) * batch
     ntc = 32
     while ntc < nt:
         ntc *= 2
-    many = n_mtiles * nnb >= 4 * n_sm and 2 * ntc <= 512
-    res2 = nnb == 1 and many and fixed + bytes_b_all + 4 * bytes_a <= SMEM_BUDGET
-    res1 = nnb == 1 and fixed + bytes_b_all + 3 * bytes_a <= SMEM_BUDGET
-    if res2:
-        resident, mt = True, 2
-    elif res1 and (nt >= 128 or not many):
-        resident, mt = True, 1
-    elif many:
-        resident, mt = False, 2
-    else:
-        resident, mt = res1, 1
+    if mt is None:
+        mt = 2 if (n_mtiles * nnb >= 4 * n_sm and 2 * ntc <= 512) else 1
+    if mt == 2 and 2 * ntc > 512:
+        return None
+    resident = nnb == 1 and fixed + bytes_b_all + (4 if mt == 2 else 3) * bytes_a <= SMEM_BUDGET
+    if not resident and fixed + 2 * mt * bytes_a + 2 * bytes_b > SMEM_BUDGET:
+        return None
+    acc_stages = 2 if 2 * mt * ntc <= 512 else 1
     t_mma = max(nt / 2.0, (4096 + 32 * nt) / 128.0)                  # tensor floor vs smem operand read, per K=16 step
     mma = 0.0
     for r in runs:
@@ -190,10 +204,13 @@ def layer_cost(nr, h, ntot, runs, kh, batch, n_sm=148):
             ks = 4 if ck < nck - 1 else ((r - ck * 64) + 15) // 16
             per_dy = max(mt * ks * t_mma, ks * ISSUE_CLK_PER_MMA + ISSUE_CLK_PER_DY[0 if resident else 1])   # one issuer per M-tile
             mma += kh * per_dy + ISSUE_CLK_PER_CHUNK
-    mma /= mt
-    l2 = (chunks * bytes_a + (0 if resident else chunks * kh * nt * 128 / mt)) / L2_BYTES_PER_CLK_SM
-    epi = EPI_CLK_PER_COL * nt + EPI_CLK_PER_TILE
-    return {"clk": max(mma, l2, epi) * nnb, "mma": mma, "l2": l2, "epi": epi, "resident": resident, "mt": mt, "nt": nt}
+    l2 = (mt * chunks * bytes_a + (0 if resident else bytes_b_all)) / L2_BYTES_PER_CLK_SM
+    epi = mt * (EPI_CLK_PER_COL * nt + EPI_CLK_PER_TILE)
+    item = max(mma, l2, epi) if acc_stages == 2 else max(mma + epi, l2)
+    n_items = math.ceil(n_mtiles / mt) * nnb
+    total = math.ceil(n_items / n_sm) * item
+    return {"clk": total, "item": item, "mma": mma, "l2": l2, "epi": epi, "resident": resident, "mt": mt, "nt": nt,
+            "acc_stages": acc_stages, "items": n_items}
 
 
 class _Buf:
@@ -321,29 +338,29 @@ class FCNPlan:
         return 2 * macs
 
     # -------------------------------------------------------------------------------------------------
-    def _pick_s(self, width, height, cout, seg_cs, KW, KH, cap=None):
-        """x-packing factor S (output pixels per GEMM row) from a per-tile cycle model of csrc/fcn_conv.cu:
-        the slowest of MMA issue (tcgen05 floor N/2 clk per K=16 step, or the smem operand read (4 KB + 32 N B) at
-        128 B/clk), L2->smem traffic (A boxes + streamed weight tiles at ~42 B/clk/SM) and the epilogue."""
+    def _pick_config(self, width, height, cout, seg_cs, KW, KH, cap=None):
+        """(S, NT, MT) minimising the cycle model: S = x-packing factor (output pixels per GEMM row), NT = UMMA N per CTA,
+        MT = M-tiles per work item."""
         if not self.rowrun:
-            return 1
+            return 1, choose_nt(cout), None
         best = None
         s = 1
         while s <= 32 and (cap is None or s <= cap):
             if s == 1 or (width % s == 0 and s * cout <= 256):
-                c = layer_cost(width // s, height, s * cout, [(KW + s - 1) * c_ for c_ in seg_cs], KH, self.B)
-                cost = c["clk"] / (128.0 * s)
-                if best is None or cost < best[0] * 0.97:      # prefer the smaller S on near ties (less padding work)
-                    best = (cost, s)
+                runs = [(KW + s - 1) * c_ for c_ in seg_cs]
+                for nt in nt_candidates(s * cout):
+                    for mt in (1, 2):
+                        c = layer_cost(width // s, height, s * cout, runs, KH, self.B, nt=nt, mt=mt)
+                        if c is not None and (best is None or c["clk"] < best[0] * 0.97):   # near ties: keep the earlier (less padding)
+                            best = (c["clk"], s, nt, mt)
             s *= 2
-        return best[1]
+        return best[1], best[2], best[3]
 
     def _conv(self, w, b, srcs, dst, act, cap=None, f32_out=None):
         nrows, cin_total, KH, KW = w.shape
         first = srcs[0][0]
         Hin, Win = first.H, first.W
-        S = self._pick_s(Win, Hin, nrows, [buf.C for buf, _ in srcs], KW, KH, cap)
-        NT = choose_nt(S * nrows)
+        S, NT, MT = self._pick_config(Win, Hin, nrows, [buf.C for buf, _ in srcs], KW, KH, cap)
         packed, bias, ntot, ntot_pad = pack_weights(w, b, [(buf.C, cmap) for buf, cmap in srcs], S, self.rowrun, NT)
         packed, bias = packed.to(self.device), bias.to(self.device)
         self.keep += [packed, bias]
@@ -373,6 +390,7 @@ class FCNPlan:
             d.out_sx, d.out_sy, d.out_sn = dst.C, dst.Wp * dst.C, dst.H * dst.Wp * dst.C
             d.out_padx, d.out_coff = dst.pad, 0
         d.Cout, d.Sy, d.Sx, d.act = nrows, 1, S, act
+        d.flags = 0 if MT is None else (AM_CONV_FORCE_MT2 if MT == 2 else AM_CONV_NO_MT2)
         self.ops.append(("conv", d))
         self.op_flops[len(self.ops) - 1] = 2 * Hin * Win * nrows * cin_total * KH * KW
         self.flops += 2 * Hin * Win * nrows * cin_total * KH * KW
@@ -382,7 +400,13 @@ class FCNPlan:
         bias-only row/column (output_padding, FCN_lecturenet.py:280) from a border fill."""
         cin, cout = wt.shape[0], wt.shape[1]
         w = wt.permute(2, 3, 1, 0).reshape(4 * cout, cin, 1, 1).contiguous()      # n = (sy*2+sx)*Cout + co
-        NT = choose_nt(4 * cout)
+        best = None
+        for nt in nt_candidates(4 * cout):
+            for mt in (1, 2):
+                c = layer_cost(src.W, src.H, 4 * cout, [src.C], 1, self.B, nt=nt, mt=mt)
+                if c is not None and (best is None or c["clk"] < best[0] * 0.97):
+                    best = (c["clk"], nt, mt)
+        NT, MT = best[1], best[2]
         packed, bias, ntot, ntot_pad = pack_weights(w, bt.repeat(4), [(src.C, list(range(src.C)))], 1, self.rowrun, NT)
         packed, bias = packed.to(self.device), bias.to(self.device)
         d = ConvDesc()
@@ -400,6 +424,7 @@ class FCNPlan:
         d.out_sx, d.out_sy, d.out_sn = dst.C, dst.Wp * dst.C, dst.H * dst.Wp * dst.C
         d.out_padx, d.out_coff = dst.pad, 0
         d.Cout, d.Sy, d.Sx, d.act = cout, 2, 2, 1
+        d.flags = AM_CONV_FORCE_MT2 if MT == 2 else AM_CONV_NO_MT2
         self.ops.append(("conv", d))
         gelu_b = (0.5 * bt.double() * (1.0 + torch.erf(bt.double() / math.sqrt(2.0)))).float().to(torch.bfloat16).to(self.device)
         self.keep += [packed, bias, gelu_b]

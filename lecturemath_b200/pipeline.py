@@ -104,6 +104,98 @@ def recv_active_set(src, device=None):
     return h, meta, crops
 
 
+class StreamingExtractor:
+    """The hot path over a stream of frame batches, optionally as one rank of a multi-GPU ring.
+
+    Per batch s, all on ONE stream:  H2D copy -> FCN binarizer -> CC label/stats/crops -> [recv + import active set] ->
+    temporal matching -> pack rows -> [export + send active set].  Host read-back of batch s (collect) happens after
+    batch s+1 has been enqueued, so the GPU never idles on the host.
+
+    Multi-GPU sharding: global chunk c = s * world + rank (chunks of `batch` consecutive frames, round-robin over the
+    ranks); the active unique-CC set travels rank -> rank+1 around the ring once per chunk, which keeps the matching of
+    the whole video ONE ordered scan (bit-exact) while every rank's FCN work is independent.  The hand-off
+    is one fixed-capacity buffer (am_est_export_dev / am_est_import_dev): nothing synchronises the host.  The blocking
+    recv self-staggers the ranks by (match + hand-off) per ring position after the first round, after which no rank
+    waits: a rank's predecessor finished matching chunk c-1 while this rank was still in its own FCN.
+    (A second stream for the matching was measured and rejected: the persistent conv kernels fill every SM's registers
+    and shared memory, so side-stream kernels only start at conv-kernel boundaries and ~40 small launches per batch
+    then lag more than a whole step behind.)"""
+
+    def __init__(self, net, width, height, min_recall=0.85, min_precision=0.85, max_gap=85, batch=8, rank=0, world=1,
+                 device=None, handoff_words=8 << 20, row_capacity=1 << 16, depth=2):
+        self.net, self.width, self.height, self.batch = net, width, height, batch
+        self.rank, self.world, self.depth = rank, world, depth
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        net.cuda(self.device.index)
+        self.plan = net.plan(batch, height, width)
+        self.engines = [CCEngine(width, height, batch, device=self.device) for _ in range(depth)]
+        self.est_params = (min_recall, min_precision, max_gap)
+        self.est = Estimator(width, height, min_recall, min_precision, max_gap, device=self.device)
+        self.ev_matched = [torch.cuda.Event() for _ in range(depth)]
+        self.rows = [torch.zeros((row_capacity, 8), dtype=torch.int32, device=self.device) for _ in range(depth)]
+        self.offs = [torch.zeros((batch + 1,), dtype=torch.int32, device=self.device) for _ in range(depth)]
+        if world > 1:
+            self.buf_send = torch.zeros(handoff_words, dtype=torch.int32, device=self.device)
+            self.buf_recv = torch.zeros(handoff_words, dtype=torch.int32, device=self.device)
+        self.step = 0
+        self.launches = 0
+
+    def submit(self, frames, last=False, timing=None):
+        """Enqueue one batch (uint8 (batch,H,W,3) BGR; pinned host or device tensor).  `last`: no further batch follows on
+        ANY rank after this round (the final rank then keeps the state instead of sending it on)."""
+        import torch.distributed as dist
+        s, k = self.step, self.step % self.depth
+        plan, eng = self.plan, self.engines[k]
+        main = torch.cuda.current_stream(self.device)
+        plan.frames.copy_(frames, non_blocking=True)
+        plan.run(main.cuda_stream, False, 128, timing)
+        eng.label(plan.bits, want_labels=False, sync=False)
+        self.launches += plan.launches_per_run + 12
+        if self.world > 1 and not (self.rank == 0 and s == 0):
+            dist.recv(self.buf_recv, src=(self.rank - 1) % self.world)
+            self.est.import_dev(self.buf_recv)
+            self.launches += 2
+        self.est.add_frames(eng, 0, self.batch)
+        eng.pack_rows_into(self.rows[k], self.offs[k], self.batch)
+        self.launches += 4 * self.batch + 2
+        if self.world > 1 and not (last and self.rank == self.world - 1):
+            self.est.export_dev(self.buf_send)
+            dist.send(self.buf_send, dst=(self.rank + 1) % self.world)
+            self.launches += 2
+        self.ev_matched[k].record(main)
+        self.step += 1
+        return s
+
+    def reset(self):
+        """Start a new video: fresh temporal state, step counter back to 0 (all ranks must call it between videos)."""
+        torch.cuda.current_stream(self.device).synchronize()
+        self.est = Estimator(self.width, self.height, self.est_params[0], self.est_params[1], self.est_params[2], device=self.device)
+        self.step = 0
+
+    def collect(self, s):
+        """Result rows of batch s on the host: list (per frame) of int32 [n_cc][7] = (unique_idx, raw_label, min_x, max_x,
+        min_y, max_y, size).  Must be called before batch s + depth is submitted."""
+        k = s % self.depth
+        self.ev_matched[k].synchronize()
+        offs = self.offs[k].cpu().numpy()
+        total = int(offs[-1])
+        if total > self.rows[k].shape[0]:
+            raise RuntimeError("result rows exceed row_capacity (%d > %d)" % (total, self.rows[k].shape[0]))
+        rows = self.rows[k][:total].cpu().numpy()
+        return [rows[offs[f]:offs[f + 1], :7] for f in range(self.batch)]
+
+    def finish(self):
+        """Drain both streams and surface any capacity / hand-off failure recorded on the device."""
+        torch.cuda.current_stream(self.device).synchronize()
+        for eng in self.engines:
+            eng.batch = self.batch
+            eng.read_counts()
+        return self.est.state()
+
+    def masks_host(self):
+        return self.engines[0].unpack(self.plan.bits).cpu().numpy()
+
+
 def shard_ranges(n_frames, world):
     """Contiguous frame ranges [r*F/G, (r+1)*F/G) per rank."""
     return [(r * n_frames // world, (r + 1) * n_frames // world) for r in range(world)]
