@@ -121,6 +121,57 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def conv_traffic(args):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the conv launches of one step, from the committed ncu capture
+    (profiles/conv_traffic.json, written by tools/summarize_profile.py); None when no capture of this build exists."""
+    if args.traffic is not None:
+        return args.traffic
+    p = os.path.join(REPO, "profiles", "conv_traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f).get("dram_bytes_per_step")
+    return None
+
+
+def cc_stage_roofline(dev, peaks, batch=32, iters=5):
+    """Secondary roofline: the CC stage alone (label + stats + crops, then temporal matching) on dense-handwriting masks
+    (BASELINE configs[3]: >5k CCs per 1080p frame), `batch` frames per launch sequence, masks resident in HBM.
+    achieved = canonical operator-boundary bytes (12.125*P + 24*n per frame) / label-stage time."""
+    import torch
+    from lecturemath_b200 import synth
+    from lecturemath_b200.cc_engine import CCEngine, Estimator
+    masks = np.stack(list(synth.glyph_masks(batch, H, W, seed=0)))
+    eng = CCEngine(W, H, batch, device=dev)
+    bits = eng.pack(torch.from_numpy(masks).to(dev))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    t_label = t_match = 0.0
+    for it in range(iters + 2):
+        est = Estimator(W, H, 0.85, 0.85, 85, device=dev)
+        flush.fill_(it)
+        ev[0].record()
+        eng.label(bits, want_labels=False, sync=False)
+        ev[1].record()
+        est.add_frames(eng, 0, batch)
+        ev[2].record()
+        torch.cuda.synchronize()
+        if it >= 2:
+            t_label += ev[0].elapsed_time(ev[1])
+            t_match += ev[1].elapsed_time(ev[2])
+    counts = eng.read_counts()
+    st = est.state()
+    n_labels = float(counts[:, 1].mean())
+    bytes_frame = 12.125 * H * W + 24 * n_labels
+    fps_label = batch * iters / (t_label / 1000.0)
+    achieved = fps_label * bytes_frame / 1e9
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    return {"bound": "hbm", "kernel": "CC label+stats+crops (12 launches per %d-frame batch), dense glyph masks" % batch,
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "bytes_per_frame_canonical": bytes_frame, "bytes_per_frame_strict_floor": 4.125 * H * W + 24 * n_labels,
+            "label_frames_per_s": fps_label, "match_frames_per_s": batch * iters / (t_match / 1000.0),
+            "ccs_per_frame": float(counts[:, 2].mean()), "labels_per_frame": n_labels, "tempo_count": st["tempo_count"]}
+
+
 # ------------------------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch
@@ -234,7 +285,7 @@ def run_ours(args):
                                              "heads share one launch)" % n_conv,
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "peak_kind": peak_kind + " bf16_tflops_sustained (kernel timed inside a long step)",
-                "traffic": args.traffic, "flop_per_step": flops_step, "conv_ms_per_step": conv_ms_step,
+                "traffic": conv_traffic(args), "flop_per_step": flops_step, "conv_ms_per_step": conv_ms_step,
                 "conv_share_of_step": conv_ms_step / (ms_total / K)}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -247,6 +298,7 @@ def run_ours(args):
             dt = cpu_reference_pass(fr[1:4], sd, est)
             cpu = {"value": 3 / dt, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
                    "sample": "3 timed 1080p frames of this workload after 1 warm-up frame (torch-CPU fp32 FCN, oracle CC stage)"}
+        cc_roof = cc_stage_roofline(dev, peaks) if (world == 1 and not args.no_cc_stage) else None
         line = {"metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
                 "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16", "data": "synthetic",
@@ -254,11 +306,11 @@ def run_ours(args):
                                        "(BASELINE configs[1])", "frames_per_step_per_gpu": B, "frame": [H, W],
                            "weights": "random-init seed 0 (FCN_LectureNet.conf widths)", "l2": "256 MB flush write between steps",
                            "parallelism": "frame chunks of %d round-robin over %d GPU(s); temporal matching is one ordered scan, its "
-                                          "active-set state handed rank to rank over NCCL (ring), overlapped with the next chunk's FCN"
+                                          "active-set state handed rank to rank over NCCL p2p (ring, self-staggering)"
                                           % (B, world),
                            "ink_pct": round(ink_pct, 2), "ccs_per_frame": round(n_cc / max(K * B, 1), 1),
                            "unique_ccs": int(fin[0].item()), "tempo_count": int(fin[1].item())},
-                "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu,
+                "clocks": sampler.summary(), "roofline": roof, "roofline_cc_stage": cc_roof, "cpu_baseline": cpu,
                 "e2e": {"value": world * K * B / (e2e_ms / 1000.0), "unit": "frames/s", "h2d_bytes_per_step": B * H * W * 3,
                         "d2h_bytes_per_step": int(d2h / max(K, 1))},
                 "gpu_launches": launches}
@@ -288,6 +340,7 @@ def main():
     ap.add_argument("--batch", type=int, default=8, help="frames per step per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cc-stage", action="store_true", help="skip the secondary CC-stage roofline measurement")
     ap.add_argument("--layer-table", default=None, help="write per-layer conv timings (json) here")
     ap.add_argument("--traffic", type=float, default=None,
                     help="dram__bytes_read+write per conv launch (bytes, from profiles/ ncu --set full) to report in roofline.traffic")

@@ -39,13 +39,18 @@ def launches(tag):
 
 def conv_table(tag, layers):
     rows = list(csv.reader(open(os.path.join(G, "conv_raw_%s.csv" % tag))))
-    H, data = rows[0], rows[2:]
+    H, U, data = rows[0], rows[1], rows[2:]
     idx = {h: i for i, h in enumerate(H)}
+    scale = {"byte": 1e-9, "Kbyte": 1e-6, "Mbyte": 1e-3, "Gbyte": 1.0, "Tbyte": 1e3, "us": 1e-3, "ms": 1.0, "s": 1e3, "ns": 1e-6}
     out = []
     for r, lay in zip(data, layers):
-        d = collections.OrderedDict(op=lay["op"], N=lay["N"], KH=lay["KH"], S=lay["S"], bench_ms=lay["ms"], bench_tflops=lay["tflops"])
+        d = collections.OrderedDict(op=lay["op"], N=lay["N"], KH=lay["KH"], S=lay["S"], MT=lay.get("MT", ""), resident=lay.get("resident", ""),
+                                    bench_ms=lay["ms"], bench_tflops=lay["tflops"])
         for m, name in CONV_METRICS:
-            d[name] = r[idx[m]] if m in idx else ""
+            v = r[idx[m]] if m in idx else ""
+            if v and (name.endswith("_GB") or name == "ms"):
+                v = "%.6f" % (float(v.replace(",", "")) * scale.get(U[idx[m]], 1.0))      # normalise to GB / ms
+            d[name] = v
         out.append(d)
     return out
 
@@ -75,6 +80,13 @@ def main():
         w = csv.DictWriter(f, fieldnames=list(conv[0].keys()))
         w.writeheader()
         w.writerows(conv)
+    try:
+        tot = sum(float(d["dram_read_GB"]) + float(d["dram_write_GB"]) for d in conv) * 1e9
+        with open(os.path.join(REPO, "profiles", "conv_traffic.json"), "w") as f:
+            json.dump({"dram_bytes_per_step": tot, "launches": len(conv), "source": os.path.basename(prefix) + "_conv.csv",
+                       "note": "sum over the conv launches of one 8-frame step of dram__bytes_read.sum + dram__bytes_write.sum (ncu --set full)"}, f)
+    except Exception as e:            # units other than Gbyte: leave the file alone
+        print("conv_traffic.json not written:", e)
     bench = open(os.path.join(G, "bench_%s.json" % tag)).read().strip()
     with open(prefix + "_summary.md", "w") as f:
         f.write("# profile %s\n\n" % tag)
