@@ -323,7 +323,8 @@ def run_ours(args):
                 t = float(np.mean(per_op[i]))
                 fl = sx.plan.op_flops.get(i, 0) * B
                 info = sx.plan.conv_plan_info(i)
-                rows.append({"op": i, "N": d.NT, "Ntot": d.Ntot, "KH": d.KH, "S": d.Sx if d.Sy == 1 else 1, "RT": d.RT, "YT": d.YT,
+                rows.append({"op": i, "N": d.NT, "Ntot": d.Ntot, "KH": d.KH, "S": 1 if (d.Sy == 2 and d.in_ystep != 2) else d.Sx,
+                             "Sy": d.in_ystep if d.in_ystep else 1, "RT": d.RT, "YT": d.YT,
                              "MT": info[0], "resident": info[1], "acc_stages": info[2], "stagesA": info[3], "stagesB": info[4],
                              "ms": round(t, 4), "tflops": round(fl / (t / 1000.0) / 1e12, 1)})
             with open(args.layer_table, "w") as f:

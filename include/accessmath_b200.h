@@ -117,7 +117,7 @@ typedef struct am_conv_desc {
     const float* bias;             /* fp32 [Ntot_pad], BatchNorm folded */
     int KH, padY;
     int RT, YT;                    /* tile: RT groups x YT rows = 128 GEMM rows, RT % 8 == 0 */
-    int nR, Hin, batch;            /* GEMM rows per image row, image rows, frames */
+    int nR, Hin, batch;            /* GEMM rows per image row, GEMM row units per frame column (image rows / in_ystep), frames */
     int NT, Ntot, Ntot_pad;        /* UMMA N per CTA, valid N, padded N (multiple of NT) */
     void* out; int out_f32;        /* destination (bf16 or fp32), NHWC */
     int out_H, out_W;
@@ -126,6 +126,8 @@ typedef struct am_conv_desc {
     int Cout, Sy, Sx;              /* GEMM column n = ((sy*Sx)+sx)*Cout + co  ->  pixel (Sy*y+sy, Sx*r+sx), channel co */
     int act;                       /* 0 = none, 1 = exact-erf GELU */
     int flags;                     /* AM_CONV_* tuning overrides (0 = let the library choose) */
+    int in_ystep;                  /* input rows per GEMM row step: 1, or 2 = "2-D packing": a GEMM row produces Sy = 2 output rows,
+                                      KH is then the Toeplitz-extended tap count KH_conv + 1 and RT must be 8 (0 means 1) */
 } am_conv_desc;
 #define AM_CONV_NO_RESIDENT 1      /* always stream the weights through the B ring */
 #define AM_CONV_NO_MT2 2           /* one M-tile per work item even when two would share the weight tiles */

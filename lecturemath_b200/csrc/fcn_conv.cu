@@ -51,6 +51,7 @@ struct alignas(64) ConvParams {
     int seg_c1step[2];   // coordinate-1 step per kx (0 in row-run mode)
     int seg_c1off[2];    // coordinate-1 offset
     int KH, RT, YT, padY, logRT;
+    int ystep;           // input rows per GEMM row step (2 = 2-D packing: UMMA M-atoms skip every other image row)
     int nRT, nYT, batch; // tiles per row / per frame column, frames
     int nR, Hin;         // valid groups per row, valid rows
     int NT, NTc;         // UMMA N of this launch, TMEM columns per accumulator (power of two >= NT)
@@ -155,7 +156,9 @@ __device__ __forceinline__ bool elect_one() {
     asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, 0xffffffff;\n\t@px mov.s32 %0, 1;\n\t}" : "+r"(pred));
     return pred != 0;
 }
-#define DESC_HI_SW128 (((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61))
+// descriptor bits 32..63: stride byte offset between 8-row M/N atoms (1024 B; 2048 B for A when every other image row is
+// skipped), version, SWIZZLE_128B
+__device__ __forceinline__ uint64_t desc_hi_sw128(uint32_t sbo_bytes) { return ((uint64_t)(sbo_bytes >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61); }
 __device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | (1u << 16); }
 
 // 16 consecutive fp32 accumulator columns of this thread's TMEM lane (asynchronous: tmem_wait before use)
@@ -207,16 +210,16 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int t) {
 
 // Epilogue of one 16-column unit of one accumulator row: bias + activation + NHWC store.
 __device__ __forceinline__ void epi_unit(const ConvParams& p, const uint32_t (&v)[16], const float* __restrict__ sbias, int n0, int j0,
-                                         long long base, bool vec8, bool f32fast) {
+                                         long long base, bool vec8, bool f32fast, bool sy1_ok) {
     if (vec8) {
         // two 8-channel groups; a group never straddles a pixel because Cout % 8 == 0
         uint4 pk[2]; long long offs[2]; bool ok[2];
 #pragma unroll
         for (int gg = 0; gg < 2; ++gg) {
             const int n = n0 + j0 + gg * 8;
-            ok[gg] = n < p.Ntot;
             const int grp = (int)__umulhi((unsigned)n, p.cout_magic), co = n - grp * p.Cout;
             const int sy = (p.Sy == 2 && grp >= p.Sx) ? 1 : 0, sx = grp - sy * p.Sx;
+            ok[gg] = n < p.Ntot && (sy == 0 || sy1_ok);
             offs[gg] = base + (long long)sy * p.out_sy + (long long)sx * p.out_sx + co;
             const float4 b0 = *(const float4*)(sbias + j0 + gg * 8), b1 = *(const float4*)(sbias + j0 + gg * 8 + 4);
             float f[8] = {__uint_as_float(v[gg * 8 + 0]) + b0.x, __uint_as_float(v[gg * 8 + 1]) + b0.y, __uint_as_float(v[gg * 8 + 2]) + b0.z,
@@ -258,6 +261,7 @@ __device__ __forceinline__ void epi_unit(const ConvParams& p, const uint32_t (&v
             if (n >= p.Ntot) break;
             const int grp = n / p.Cout, co = n - grp * p.Cout;
             const int sy = grp / p.Sx, sx = grp - sy * p.Sx;
+            if (sy > 0 && !sy1_ok) continue;
             const long long off = base + (long long)sy * p.out_sy + (long long)sx * p.out_sx + co;
             float x = __uint_as_float(v[i]) + sbias[j0 + i];
             x = p.act == 1 ? gelu_erf(x) : x;
@@ -291,7 +295,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv_gemm(const __grid_cons
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve: [A ring][B ring | resident B][bias][barriers][tmem ptr]
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t bytesA1 = (uint32_t)(p.YT + p.KH - 1) * p.RT * 128u;    // one M-tile box (multiple of 1024: RT % 8 == 0)
+    const uint32_t bytesA1 = (uint32_t)(p.ystep * (p.YT - 1) + p.KH) * p.RT * 128u;    // one M-tile box (multiple of 1024: RT % 8 == 0)
     const uint32_t bytesA = bytesA1 * kMT;
     const uint32_t bytesB = (uint32_t)p.NT * 128u;
     const uint32_t nB = kRES ? (uint32_t)(p.total_chunks * p.KH) : (uint32_t)p.stagesB;
@@ -366,8 +370,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv_gemm(const __grid_cons
                         if (elect_one()) {
                             const uint32_t dst = sA0 + bytesA * sa, bar = fullA + 8 * sa;
                             mbar_expect_tx(bar, bytesA);
-                            tma_load_4d(dst, tm, bar, ck * 64, tc0.r0 + c1, tc0.y0 - p.padY, tc0.frame);
-                            if (kMT == 2) tma_load_4d(dst + bytesA1, tm, bar, ck * 64, tc1.r0 + c1, tc1.y0 - p.padY, tc1.frame);
+                            tma_load_4d(dst, tm, bar, ck * 64, tc0.r0 + c1, tc0.y0 * p.ystep - p.padY, tc0.frame);
+                            if (kMT == 2) tma_load_4d(dst + bytesA1, tm, bar, ck * 64, tc1.r0 + c1, tc1.y0 * p.ystep - p.padY, tc1.frame);
                         }
                         __syncwarp();
                         if (++sa == p.stagesA) { sa = 0; pa ^= 1; }
@@ -396,6 +400,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv_gemm(const __grid_cons
         const uint32_t NTc = (uint32_t)p.NTc;
         const uint32_t dy_step = ((uint32_t)p.RT * 128u) >> 4, b_step = bytesB >> 4, a_step = bytesA >> 4;
         const uint32_t a_lo0 = desc_lo(sA0 + bytesA1 * (uint32_t)mt), b_lo0 = desc_lo(sB0);
+        const uint64_t hiA = desc_hi_sw128(1024u * (uint32_t)p.ystep), hiB = desc_hi_sw128(1024u);
         int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
         int as = 0; uint32_t pacc = 0;
         if (kRES) { mbar_wait_uniform(fullB, 0); tc_fence_after(); }
@@ -419,10 +424,10 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv_gemm(const __grid_cons
                         if (kRES) { blo = b_res; b_res += b_step; }
                         else { mbar_wait_uniform(fullB + 8 * sb, pb); tc_fence_after(); blo = b_lo0 + b_step * (uint32_t)sb; }
                         if (elect_one()) {
-                            tc_mma_bf16(td, DESC_HI_SW128 | alo, DESC_HI_SW128 | blo, idesc, acc);
-                            if (ksteps > 1) tc_mma_bf16(td, DESC_HI_SW128 | (alo + 2), DESC_HI_SW128 | (blo + 2), idesc, 1);
-                            if (ksteps > 2) tc_mma_bf16(td, DESC_HI_SW128 | (alo + 4), DESC_HI_SW128 | (blo + 4), idesc, 1);
-                            if (ksteps > 3) tc_mma_bf16(td, DESC_HI_SW128 | (alo + 6), DESC_HI_SW128 | (blo + 6), idesc, 1);
+                            tc_mma_bf16(td, hiA | alo, hiB | blo, idesc, acc);
+                            if (ksteps > 1) tc_mma_bf16(td, hiA | (alo + 2), hiB | (blo + 2), idesc, 1);
+                            if (ksteps > 2) tc_mma_bf16(td, hiA | (alo + 4), hiB | (blo + 4), idesc, 1);
+                            if (ksteps > 3) tc_mma_bf16(td, hiA | (alo + 6), hiB | (blo + 6), idesc, 1);
                             if (!kRES) tc_commit(emptyB + 8 * sb);
                         }
                         __syncwarp();
@@ -474,7 +479,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv_gemm(const __grid_cons
             // current one is processed; two register sets ping-pong (no copies)
             uint32_t va[16], vb[16];
             int cur_mt = -1;
-            bool row_ok = false;
+            bool row_ok = false, sy1_ok = true;
             long long base = 0;
             auto unit_addr = [&](int g) -> uint32_t {
                 const int mt = g >= units_per_tile ? 1 : 0;
@@ -488,7 +493,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv_gemm(const __grid_cons
                     const int y = tc.y0 + yy, r = tc.r0 + rr;
                     row_ok = tc.valid && (y < p.Hin) && (r < p.nR);
                     base = (long long)tc.frame * p.out_sn + (long long)(p.Sy * y) * p.out_sy + (long long)(p.Sx * r + p.out_padx) * p.out_sx + p.out_coff;
-                    if (p.Sy * y + p.Sy > p.out_H || p.Sx * r + p.Sx > p.out_W) row_ok = false;   // never true for the FCN's shapes
+                    if (p.Sy * y >= p.out_H || p.Sx * r + p.Sx > p.out_W) row_ok = false;
+                    sy1_ok = p.Sy * y + 1 < p.out_H;                               // odd image height: the last row pair has no second row
                 }
                 return (g - mt * units_per_tile) * 16;
             };
@@ -498,13 +504,13 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv_gemm(const __grid_cons
                 tmem_wait16(va);
                 int g2 = g + EPI_PER_Q;
                 if (g2 < units) tmem_ld16_async(unit_addr(g2), vb);
-                { const int j0 = enter(g); if (row_ok) epi_unit(p, va, sbias, n0, j0, base, vec8, f32fast); }
+                { const int j0 = enter(g); if (row_ok) epi_unit(p, va, sbias, n0, j0, base, vec8, f32fast, sy1_ok); }
                 g = g2;
                 if (g >= units) break;
                 tmem_wait16(vb);
                 g2 = g + EPI_PER_Q;
                 if (g2 < units) tmem_ld16_async(unit_addr(g2), va);
-                { const int j0 = enter(g); if (row_ok) epi_unit(p, vb, sbias, n0, j0, base, vec8, f32fast); }
+                { const int j0 = enter(g); if (row_ok) epi_unit(p, vb, sbias, n0, j0, base, vec8, f32fast, sy1_ok); }
                 g = g2;
             }
             // all tcgen05.ld of this stage have completed (tmem_wait16 in the last iteration): hand the stage back
@@ -584,19 +590,21 @@ static int conv_prepare(const am_conv_desc* d, am_conv_plan* plan) {
     ConvParams& p = plan->p;
     memset(&p, 0, sizeof(p));
     p.nseg = d->nseg;
-    const int box_rows = d->YT + d->KH - 1;
+    const int ystep = d->in_ystep == 2 ? 2 : 1;
+    if (ystep == 2 && d->RT != 8) return AM_ERR_ARG;      // M-atoms must be whole image rows for the descriptor stride trick
+    const int box_rows = ystep * (d->YT - 1) + d->KH;
     int total_chunks = 0;
     for (int s = 0; s < d->nseg; ++s) {
         const am_conv_seg* g = &d->seg[s];
         unsigned long long dims[4], strides[3]; unsigned box[4];
         if (g->rowrun) {        // dim0 = run elements, dim1 = output group r (row stride S*C elements: rows overlap)
-            dims[0] = (unsigned long long)g->run_len; dims[1] = (unsigned long long)d->nR; dims[2] = (unsigned long long)d->Hin; dims[3] = (unsigned long long)d->batch;
+            dims[0] = (unsigned long long)g->run_len; dims[1] = (unsigned long long)d->nR; dims[2] = (unsigned long long)g->Hbuf; dims[3] = (unsigned long long)d->batch;
             strides[0] = (unsigned long long)g->S * g->C * 2ull;
             p.seg_nkx[s] = 1; p.seg_c1step[s] = 0; p.seg_c1off[s] = 0;
             p.seg_nck[s] = (g->run_len + 63) / 64;
             p.seg_klast[s] = ((g->run_len - (p.seg_nck[s] - 1) * 64) + 15) & ~15;
         } else {                // dim0 = channels, dim1 = padded x; one load per horizontal tap
-            dims[0] = (unsigned long long)g->C; dims[1] = (unsigned long long)g->Wp; dims[2] = (unsigned long long)d->Hin; dims[3] = (unsigned long long)d->batch;
+            dims[0] = (unsigned long long)g->C; dims[1] = (unsigned long long)g->Wp; dims[2] = (unsigned long long)g->Hbuf; dims[3] = (unsigned long long)d->batch;
             strides[0] = (unsigned long long)g->C * 2ull;
             p.seg_nkx[s] = g->KW; p.seg_c1step[s] = 1; p.seg_c1off[s] = 0;
             p.seg_nck[s] = (g->C + 63) / 64;
@@ -618,7 +626,7 @@ static int conv_prepare(const am_conv_desc* d, am_conv_plan* plan) {
         int rc = encode_map(&p.tmB, (void*)d->weights, 2, dims, strides, box);
         if (rc) return rc;
     }
-    p.KH = d->KH; p.RT = d->RT; p.YT = d->YT; p.padY = d->padY;
+    p.KH = d->KH; p.RT = d->RT; p.YT = d->YT; p.padY = d->padY; p.ystep = ystep;
     p.logRT = 0; while ((1 << p.logRT) < d->RT) ++p.logRT;
     p.nRT = (d->nR + d->RT - 1) / d->RT; p.nYT = (d->Hin + d->YT - 1) / d->YT; p.batch = d->batch;
     p.nR = d->nR; p.Hin = d->Hin; p.NT = d->NT; p.Ntot_pad = d->Ntot_pad; p.nNB = d->Ntot_pad / d->NT;

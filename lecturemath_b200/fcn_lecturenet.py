@@ -74,7 +74,7 @@ class ConvDesc(ctypes.Structure):
                 ("out", ctypes.c_void_p), ("out_f32", ctypes.c_int), ("out_H", ctypes.c_int), ("out_W", ctypes.c_int),
                 ("out_sn", ctypes.c_longlong), ("out_sy", ctypes.c_longlong),
                 ("out_sx", ctypes.c_int), ("out_padx", ctypes.c_int), ("out_coff", ctypes.c_int),
-                ("Cout", ctypes.c_int), ("Sy", ctypes.c_int), ("Sx", ctypes.c_int), ("act", ctypes.c_int), ("flags", ctypes.c_int)]
+                ("Cout", ctypes.c_int), ("Sy", ctypes.c_int), ("Sx", ctypes.c_int), ("act", ctypes.c_int), ("flags", ctypes.c_int), ("in_ystep", ctypes.c_int)]
 
 
 def fold_bn(w, b, bn_w, bn_b, mean, var, out_dim=0):
@@ -106,15 +106,18 @@ def choose_tile(nr, h, kh):
     return best[1], best[2]
 
 
-def pack_weights(w, bias, segs, S, rowrun, NT):
+def pack_weights(w, bias, segs, S, rowrun, NT, Sy=1):
     """Re-pack a folded filter for the row-run implicit GEMM (csrc/fcn_conv.cu header comment).
 
     w    : fp32 [Nrows][Cin][KH][KW]  (Nrows = Cout, or 4*Cout for the transposed conv's (sy,sx,co))
     segs : list of (C_buf, index tensor mapping buffer channel -> w input channel, -1 = zero padding)
-    ->   bf16 [chunks*KH*Ntot_pad][64], fp32 bias [Ntot_pad], Ntot, Ntot_pad
+    S, Sy: output pixels packed per GEMM row in x and (2-D packing) in y; GEMM column n = ((sy*S)+sx)*Nrows + co and the
+           filter becomes a zero-padded Toeplitz block over KW+S-1 horizontal and KH+Sy-1 vertical taps
+    ->   bf16 [chunks*KHe*Ntot_pad][64], fp32 bias [Ntot_pad], Ntot, Ntot_pad        (KHe = KH + Sy - 1)
     """
     nrows, _, KH, KW = w.shape
-    ntot = S * nrows
+    KHe = KH + Sy - 1
+    ntot = Sy * S * nrows
     ntot_pad = ((ntot + NT - 1) // NT) * NT
     blocks = []
     for C, cmap in segs:
@@ -124,24 +127,25 @@ def pack_weights(w, bias, segs, S, rowrun, NT):
         wseg[:, valid] = w[:, cmap[valid]]
         if rowrun:
             J = KW + S - 1
-            run = torch.zeros((S, nrows, KH, J, C), dtype=torch.float32)
-            for sx in range(S):
-                run[sx, :, :, sx:sx + KW, :] = wseg.permute(0, 2, 3, 1)          # [co][dy][tap][c]
+            run = torch.zeros((Sy, S, nrows, KHe, J, C), dtype=torch.float32)
+            for sy in range(Sy):
+                for sx in range(S):
+                    run[sy, sx, :, sy:sy + KH, sx:sx + KW, :] = wseg.permute(0, 2, 3, 1)    # [co][dy][tap][c]
             K = J * C
-            mat = run.permute(2, 0, 1, 3, 4).reshape(KH, ntot, K)                # [dy][n=(sx,co)][k=(j,c)]
+            mat = run.permute(3, 0, 1, 2, 4, 5).reshape(KHe, ntot, K)            # [dy'][n=(sy,sx,co)][k=(j,c)]
             nck = (K + 63) // 64
-            full = torch.zeros((KH, ntot_pad, nck * 64), dtype=torch.float32)
+            full = torch.zeros((KHe, ntot_pad, nck * 64), dtype=torch.float32)
             full[:, :ntot, :K] = mat
-            blocks.append(full.view(KH, ntot_pad, nck, 64).permute(2, 0, 1, 3))  # [ck][dy][n][64]
+            blocks.append(full.view(KHe, ntot_pad, nck, 64).permute(2, 0, 1, 3))  # [ck][dy'][n][64]
         else:
-            assert S == 1
+            assert S == 1 and Sy == 1
             nck = (C + 63) // 64
             full = torch.zeros((KW, KH, ntot_pad, nck * 64), dtype=torch.float32)
             full[:, :, :ntot, :C] = wseg.permute(3, 2, 0, 1)                     # [kx][dy][co][c]
             blocks.append(full.view(KW, KH, ntot_pad, nck, 64).permute(0, 3, 1, 2, 4).reshape(KW * nck, KH, ntot_pad, 64))
     packed = torch.cat(blocks, 0).reshape(-1, 64).to(torch.bfloat16).contiguous()
     b = torch.zeros(ntot_pad, dtype=torch.float32)
-    b[:ntot] = bias.repeat(S)
+    b[:ntot] = bias.repeat(Sy * S)
     return packed, b, ntot, ntot_pad
 
 
@@ -171,7 +175,7 @@ def nt_candidates(ntot):
     return out
 
 
-def layer_cost(nr, h, ntot, runs, kh, batch, nt=None, mt=None, n_sm=148):
+def layer_cost(nr, h, ntot, runs, kh, batch, nt=None, mt=None, sy=1, n_sm=148):
     """Cycle model of k_conv_gemm (csrc/fcn_conv.cu) for one layer: GEMM width ntot, per-segment run lengths `runs`
     (elements of K per vertical tap), UMMA N `nt` and `mt` M-tiles per work item.  Mirrors conv_prepare()'s feasibility
     rules (resident weights, accumulator stages).  Calibrated against profiles/ (r01): narrow layers are bound by the
@@ -179,9 +183,12 @@ def layer_cost(nr, h, ntot, runs, kh, batch, nt=None, mt=None, n_sm=148):
     nt = nt or choose_nt(ntot)
     ntot_pad = ((ntot + nt - 1) // nt) * nt
     nnb = ntot_pad // nt
-    rt, yt = choose_tile(nr, h, kh)
+    if sy == 2:                                   # 2-D packing: `h` image rows -> ceil(h/2) GEMM row units, kh + 1 Toeplitz taps, RT = 8
+        h, kh, (rt, yt) = (h + 1) // 2, kh + 1, (8, 16)
+    else:
+        rt, yt = choose_tile(nr, h, kh)
     chunks = sum((r + 63) // 64 for r in runs)
-    bytes_a, bytes_b = (yt + kh - 1) * rt * 128, nt * 128
+    bytes_a, bytes_b = (sy * (yt - 1) + kh) * rt * 128, nt * 128
     bytes_b_all = chunks * kh * bytes_b
     fixed = 2560
     n_mtiles = math.ceil(nr / rt) * math.ceil(h / yt) * batch
@@ -230,7 +237,8 @@ class _Buf:
 class FCNPlan:
     """All device buffers, packed weights and kernel descriptors for one (batch, H, W)."""
 
-    def __init__(self, net, B, H, W, device, rowrun=True):
+    def __init__(self, net, B, H, W, device, rowrun=True, overrides=None):
+        self.ov = dict(overrides or {})      # planner overrides for tests / tuning, e.g. {"sy": 2} forces 2-D packing where legal
         self.lib = _lib.load()          # building a plan needs no device; run() does (and fails loudly without one)
         self.B, self.H, self.W, self.device, self.rowrun = B, H, W, device, rowrun
         sd = {k: v.detach().float().cpu() for k, v in net.state_dict().items()}
@@ -338,30 +346,36 @@ class FCNPlan:
         return 2 * macs
 
     # -------------------------------------------------------------------------------------------------
-    def _pick_config(self, width, height, cout, seg_cs, KW, KH, cap=None):
-        """(S, NT, MT) minimising the cycle model: S = x-packing factor (output pixels per GEMM row), NT = UMMA N per CTA,
+    def _pick_config(self, width, height, cout, seg_cs, KW, KH, cap=None, allow_sy=True):
+        """(S, Sy, NT, MT) minimising the cycle model: S / Sy = output pixels per GEMM row in x / y, NT = UMMA N per CTA,
         MT = M-tiles per work item."""
         if not self.rowrun:
-            return 1, choose_nt(cout), None
+            return 1, 1, choose_nt(cout), None
         best = None
-        s = 1
-        while s <= 32 and (cap is None or s <= cap):
-            if s == 1 or (width % s == 0 and s * cout <= 256):
-                runs = [(KW + s - 1) * c_ for c_ in seg_cs]
-                for nt in nt_candidates(s * cout):
-                    for mt in (1, 2):
-                        c = layer_cost(width // s, height, s * cout, runs, KH, self.B, nt=nt, mt=mt)
-                        if c is not None and (best is None or c["clk"] < best[0] * 0.97):   # near ties: keep the earlier (less padding)
-                            best = (c["clk"], s, nt, mt)
-            s *= 2
-        return best[1], best[2], best[3]
+        sy_options = (1, 2) if allow_sy and KH > 1 and height >= 2 else (1,)
+        if "sy" in self.ov and self.ov["sy"] in sy_options:
+            sy_options = (self.ov["sy"],)
+        for sy in sy_options:
+            s = 1
+            while s <= 32 and (cap is None or s * sy <= cap):
+                if s == 1 or (width % s == 0 and s * sy * cout <= 256):
+                    runs = [(KW + s - 1) * c_ for c_ in seg_cs]
+                    for nt in nt_candidates(s * sy * cout):
+                        for mt in (1, 2):
+                            c = layer_cost(width // s, height, s * sy * cout, runs, KH, self.B, nt=nt, mt=mt, sy=sy)
+                            if c is not None and (best is None or c["clk"] < best[0] * 0.97):   # near ties: keep the earlier (less padding)
+                                best = (c["clk"], s, sy, nt, mt)
+                s *= 2
+        return best[1], best[2], best[3], best[4]
 
     def _conv(self, w, b, srcs, dst, act, cap=None, f32_out=None):
         nrows, cin_total, KH, KW = w.shape
         first = srcs[0][0]
         Hin, Win = first.H, first.W
-        S, NT, MT = self._pick_config(Win, Hin, nrows, [buf.C for buf, _ in srcs], KW, KH, cap)
-        packed, bias, ntot, ntot_pad = pack_weights(w, b, [(buf.C, cmap) for buf, cmap in srcs], S, self.rowrun, NT)
+        S, Sy, NT, MT = self._pick_config(Win, Hin, nrows, [buf.C for buf, _ in srcs], KW, KH, cap, allow_sy=f32_out is None)
+        packed, bias, ntot, ntot_pad = pack_weights(w, b, [(buf.C, cmap) for buf, cmap in srcs], S, self.rowrun, NT, Sy)
+        Himg, KHc = Hin, KH
+        Hin, KH = (Himg + Sy - 1) // Sy, KHc + Sy - 1          # GEMM row units per frame column, Toeplitz-extended vertical taps
         packed, bias = packed.to(self.device), bias.to(self.device)
         self.keep += [packed, bias]
         d = ConvDesc()
@@ -373,27 +387,27 @@ class FCNPlan:
             assert g.x_off >= 0
             g.rowrun, g.S, g.run_len, g.KW = int(self.rowrun), S, (KW + S - 1) * buf.C, KW
         d.weights, d.bias = packed.data_ptr(), bias.data_ptr()
-        d.KH, d.padY = KH, (KH - 1) // 2
+        d.KH, d.padY, d.in_ystep = KH, (KHc - 1) // 2, Sy
         d.nR, d.Hin, d.batch = Win // S, Hin, self.B
-        d.RT, d.YT = choose_tile(d.nR, Hin, KH)
+        d.RT, d.YT = (8, 16) if Sy == 2 else choose_tile(d.nR, Hin, KH)
         d.NT, d.Ntot, d.Ntot_pad = NT, ntot, ntot_pad
         if f32_out is not None:
             d.out, d.out_f32 = f32_out.data_ptr(), 1
-            d.out_H, d.out_W = Hin, Win
+            d.out_H, d.out_W = Himg, Win
             d.out_sx = nrows
             d.out_sy = Win * nrows
-            d.out_sn = Hin * Win * nrows
+            d.out_sn = Himg * Win * nrows
             d.out_padx, d.out_coff = 0, 0
         else:
             d.out, d.out_f32 = dst.ptr, 0
             d.out_H, d.out_W = dst.H, dst.W
             d.out_sx, d.out_sy, d.out_sn = dst.C, dst.Wp * dst.C, dst.H * dst.Wp * dst.C
             d.out_padx, d.out_coff = dst.pad, 0
-        d.Cout, d.Sy, d.Sx, d.act = nrows, 1, S, act
+        d.Cout, d.Sy, d.Sx, d.act = nrows, Sy, S, act
         d.flags = 0 if MT is None else (AM_CONV_FORCE_MT2 if MT == 2 else AM_CONV_NO_MT2)
         self.ops.append(("conv", d))
-        self.op_flops[len(self.ops) - 1] = 2 * Hin * Win * nrows * cin_total * KH * KW
-        self.flops += 2 * Hin * Win * nrows * cin_total * KH * KW
+        self.op_flops[len(self.ops) - 1] = 2 * Himg * Win * nrows * cin_total * KHc * KW
+        self.flops += 2 * Himg * Win * nrows * cin_total * KHc * KW
 
     def _tconv(self, wt, bt, src, dst):
         """ConvTranspose2d(k=2,s=2) + BN + GELU as a 1x1 GEMM with N = (sy,sx,co); odd output sizes get the
@@ -415,7 +429,7 @@ class FCNPlan:
         g.ptr, g.C, g.Wp, g.Hbuf, g.x_off = src.ptr, src.C, src.Wp, src.H, src.pad
         g.rowrun, g.S, g.run_len, g.KW = int(self.rowrun), 1, src.C, 1
         d.weights, d.bias = packed.data_ptr(), bias.data_ptr()
-        d.KH, d.padY = 1, 0
+        d.KH, d.padY, d.in_ystep = 1, 0, 1
         d.nR, d.Hin, d.batch = src.W, src.H, self.B
         d.RT, d.YT = choose_tile(src.W, src.H, 1)
         d.NT, d.Ntot, d.Ntot_pad = NT, ntot, ntot_pad
@@ -511,6 +525,7 @@ class FCN_LectureNet:
         self._plans = {}
         self._device = None
         self.rowrun = True
+        self.plan_overrides = None
 
     # ---- reference-compatible plumbing ---------------------------------------------------------------
     @staticmethod
@@ -559,10 +574,10 @@ class FCN_LectureNet:
         if self._device is None:
             _lib.lib()      # raises loudly without a GPU: there is no CPU path
             self.cuda()
-        key = (B, H, W, self.rowrun)
+        key = (B, H, W, self.rowrun, repr(self.plan_overrides))
         if key not in self._plans:
             with torch.cuda.device(self._device):
-                self._plans[key] = FCNPlan(self.params, B, H, W, self._device, self.rowrun)
+                self._plans[key] = FCNPlan(self.params, B, H, W, self._device, self.rowrun, self.plan_overrides)
         return self._plans[key]
 
     def binarize_frames(self, frames_bgr, want_others=False, threshold=128):

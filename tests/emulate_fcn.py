@@ -39,16 +39,17 @@ def emulate_conv(d, mem):
         for kx in range(nkx):
             for ck in range(nck):
                 kvalid = klast if ck == nck - 1 else 64
+                ystep = 2 if d.in_ystep == 2 else 1
                 for dy in range(KH):
-                    yy = y_i + dy - d.padY
+                    yy = y_i * ystep + dy - d.padY
                     k = ck * 64 + kk
                     if g.rowrun:
                         idx = base + ((n_i * g.Hbuf + yy) * g.Wp) * g.C + r_i * g.S * g.C + k
-                        ok = (yy >= 0) & (yy < Hin) & (k < dim0)
+                        ok = (yy >= 0) & (yy < g.Hbuf) & (k < dim0)
                     else:
                         x = r_i + kx
                         idx = base + ((n_i * g.Hbuf + yy) * g.Wp + x) * g.C + k
-                        ok = (yy >= 0) & (yy < Hin) & (k < dim0) & (x < g.Wp)
+                        ok = (yy >= 0) & (yy < g.Hbuf) & (k < dim0) & (x < g.Wp)
                     ok = ok & (kk < kvalid)
                     idx = torch.where(ok, idx, torch.zeros_like(idx))
                     a = torch.where(ok, flat[idx.reshape(-1)].view(idx.shape), torch.zeros(()))

@@ -20,11 +20,13 @@ def _sig(a):
 
 
 @pytest.mark.parametrize("tag", ["tiny", "full"])
-@pytest.mark.parametrize("rowrun", [True, False])
-def test_forward_vs_reference_golden(golden, tag, rowrun):
+@pytest.mark.parametrize("mode", ["rowrun", "kx", "sy2"])
+def test_forward_vs_reference_golden(golden, tag, mode):
+    """mode: rowrun = planner's choice, kx = one TMA load per horizontal tap, sy2 = 2-D (row-pair) packing forced."""
     z = golden("fcn_forward.npz")
     net = golden_net(tag, z).cuda()
-    net.rowrun = rowrun
+    net.rowrun = mode != "kx"
+    net.plan_overrides = {"sy": 2} if mode == "sy2" else None
     frame = z["frame_bgr"]
     plan = net.binarize_frames(frame[None], want_others=True)
     torch.cuda.synchronize()

@@ -45,12 +45,16 @@ def test_seeded_init_reproduces_reference_weights(golden):
         np.testing.assert_array_equal(v.numpy(), z["tiny_sd/" + k])
 
 
-@pytest.mark.parametrize("rowrun", [True, False])
-def test_emulated_kernel_plan_matches_reference_logits(golden, rowrun):
+@pytest.mark.parametrize("mode", ["rowrun", "kx", "sy2"])
+def test_emulated_kernel_plan_matches_reference_logits(golden, mode):
+    """mode: rowrun = planner's choice, kx = one TMA load per horizontal tap, sy2 = 2-D (row-pair) packing forced."""
     z = golden("fcn_forward.npz")
     net = golden_net("tiny", z)
     frame = z["frame_bgr"]
-    plan = FCNPlan(net.params, 1, frame.shape[0], frame.shape[1], torch.device("cpu"), rowrun=rowrun)
+    plan = FCNPlan(net.params, 1, frame.shape[0], frame.shape[1], torch.device("cpu"), rowrun=(mode != "kx"),
+                   overrides={"sy": 2} if mode == "sy2" else None)
+    if mode == "sy2":
+        assert sum(1 for k, d in plan.ops if k == "conv" and d.in_ystep == 2) >= 10
     logits, text, rec, ink = emulate_plan(plan, frame[None])
     # bf16 activations/weights with fp32 accumulation: stated tolerance 1e-2 on probabilities (BASELINE north_star)
     p, p_ref = torch.sigmoid(logits[0]).numpy(), 1 / (1 + np.exp(-z["tiny_logit"]))
