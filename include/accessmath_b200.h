@@ -25,6 +25,33 @@ int CC_AgeBoundaries(int* labels, float* ages, int width, int height, int count_
                      int* out_mins_y, int* out_maxs_y, int* out_mins_x, int* out_maxs_x,
                      int* out_counts, float* output_age);
 
+/* ===== 1b. The other four exports of the reference's accessmath_lib (legacy 2013-15 binarizer / speaker detection).
+ * Same names and signatures as R/accessmath_lib.c so that ctypes.CDLL callers resolve them unchanged;
+ * host pointers, H2D/D2H staged internally, results bit-identical to the gcc x86-64 build of the reference (fp64
+ * evaluated in the reference's order without FMA contraction).  am_*_dev = the same operators on device pointers. */
+/* R/accessmath_lib.c:175-329; caller R/AccessMath/preprocessing/tools/adaptive_equalizer.py:273-291 */
+int adapthisteq(unsigned char* grayscale, int width, int height, double slope, int grid_x, int grid_y,
+                unsigned char* output);
+/* R/accessmath_lib.c:113-173 (internal helper of adapthisteq, exported by the reference) */
+void regionCumulativeDistribution(unsigned char* grayscale, int width, int height, int min_x, int max_x,
+                                  int min_y, int max_y, double slope_max, double* output);
+/* R/accessmath_lib.c:331-354; caller R/AccessMath/preprocessing/content/binarizer.py:381-402 */
+int combine_results(unsigned char* only_board, unsigned char* equalized, int width, int height,
+                    unsigned char threshold, unsigned char* final_content);
+/* R/accessmath_lib.c:7-111 (no Python caller in this release); returns total_changes, -1 on a CUDA failure */
+int speaker_detection_handle_frame(unsigned char* frame, unsigned char* last_frame, int width, int height,
+                                   int channels, int threshold, int jump_cells, double* change_boundaries,
+                                   double* change_avg, double* change_deviation);
+int am_adapthisteq_dev(const uint8_t* d_gray, int width, int height, double slope, int grid_x, int grid_y,
+                       uint8_t* d_out, void* stream);
+int am_region_cdf_dev(const uint8_t* d_gray, int width, int height, int min_x, int max_x, int min_y, int max_y,
+                      double slope_max, double* d_out256, void* stream);
+int am_combine_results_dev(const uint8_t* d_only_board, const uint8_t* d_equalized, int width, int height,
+                           unsigned char threshold, uint8_t* d_out, void* stream);
+/* d_result[9] = change_boundaries[4], change_avg[2], change_deviation[2], total_changes */
+int am_speaker_detection_dev(const uint8_t* d_frame, const uint8_t* d_last_frame, int width, int height, int channels,
+                             int threshold, int jump_cells, double* d_result, void* stream);
+
 /* ===== 2. Library / device ================================================================== */
 int am_version(void);
 int am_device_count(void);                 /* 0 when no CUDA device: callers must fail loudly */

@@ -12,6 +12,14 @@ c_int, c_void_p, c_double, c_ll, c_ull = ctypes.c_int, ctypes.c_void_p, ctypes.c
 # name -> (restype, argtypes): one entry per symbol declared in include/accessmath_b200.h
 SIGNATURES = {
     "CC_AgeBoundaries": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int] + [c_void_p] * 6),
+    "adapthisteq": (c_int, [c_void_p, c_int, c_int, c_double, c_int, c_int, c_void_p]),
+    "regionCumulativeDistribution": (None, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_double, c_void_p]),
+    "combine_results": (c_int, [c_void_p, c_void_p, c_int, c_int, ctypes.c_ubyte, c_void_p]),
+    "speaker_detection_handle_frame": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "am_adapthisteq_dev": (c_int, [c_void_p, c_int, c_int, c_double, c_int, c_int, c_void_p, c_void_p]),
+    "am_region_cdf_dev": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_double, c_void_p, c_void_p]),
+    "am_combine_results_dev": (c_int, [c_void_p, c_void_p, c_int, c_int, ctypes.c_ubyte, c_void_p, c_void_p]),
+    "am_speaker_detection_dev": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "am_version": (c_int, []),
     "am_device_count": (c_int, []),
     "am_words_per_row": (c_int, [c_int]),

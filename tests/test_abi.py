@@ -13,7 +13,8 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def declared_symbols():
     src = open(os.path.join(REPO, "include", "accessmath_b200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b((?:am_|CC_)\w+)\s*\(", src)))
+    legacy = "adapthisteq|regionCumulativeDistribution|combine_results|speaker_detection_handle_frame"
+    return sorted(set(re.findall(r"\b((?:am_|CC_)\w+|%s)\s*\(" % legacy, src)))
 
 
 def test_library_exports_every_declared_symbol():
@@ -21,6 +22,8 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load()
     names = declared_symbols()
     assert "CC_AgeBoundaries" in names and len(names) >= 20
+    for legacy in ("adapthisteq", "regionCumulativeDistribution", "combine_results", "speaker_detection_handle_frame"):
+        assert legacy in names          # the drop-in .so exports all five reference symbols
     for n in names:
         assert hasattr(lib, n), "missing export " + n
         assert n in _lib.SIGNATURES, "no ctypes signature for " + n
