@@ -65,10 +65,13 @@ class CCEngine:
         return out
 
     # ---- labeling + stats + crops ------------------------------------------------------------------
-    def label(self, bits, want_labels=False, sync=True):
+    def label(self, bits, want_labels=False, sync=True, out=None):
         b = bits.shape[0]
         assert b <= self.max_batch and bits.is_contiguous() and bits.shape[1:] == (self.height, self.wpr)
-        labels = torch.empty((b, self.height, self.width), dtype=torch.int32, device=bits.device) if want_labels else None
+        labels = None
+        if want_labels:
+            labels = out if out is not None else torch.empty((b, self.height, self.width), dtype=torch.int32, device=bits.device)
+            assert labels.is_contiguous() and labels.dtype == torch.int32 and labels.shape == (b, self.height, self.width)
         _lib.check(self.lib.am_cc_label_batch(self.ctx, _p(bits), b, _p(labels) if want_labels else None, _stream()),
                    "am_cc_label_batch")
         self.batch = b

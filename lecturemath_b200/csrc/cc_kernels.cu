@@ -27,13 +27,12 @@
 #define NONE_U32 0xFFFFFFFFu
 
 struct CcFrame {                 // device pointers of one frame slot
-    uint32_t* wprefix;           // [H][WPR] runs that start before word w in its row
-    int* rowbase;                // [H+1] exclusive scan of runs per row
-    int* run_parent;             // [MR]
-    int* run_yx;                 // [MR] y<<16 | x_start
-    int* run_xe;                 // [MR] x_end (inclusive)
-    int* run_label;              // [MR]
-    int* blockcnt;               // [MR/1024+1]
+    uint32_t* wfirst;            // [H][WPR] run slot of the first run that STARTS in word w (runs before it in its strip + strip base)
+    uint32_t* run_comp;          // [NS*CAP] run slot -> strip-component slot
+    int *c_min_x, *c_max_x, *c_min_y, *c_max_y, *c_count;   // [NS*CAP] strip-component partial statistics
+    int* c_link;                 // [NS*CAP] union-find over strip components (seam merge), flattened by k_resolve
+    int* c_label;                // [NS*CAP] final raster-order label of each strip component
+    int2* strip_n;               // [NS] (runs, components) of each strip
     int* t_min_y; int* t_max_y; int* t_min_x; int* t_max_x; int* t_count;   // [ML]
     uint32_t* lab_crop_off;      // [ML]
     int* kept_label;             // [MK]
@@ -43,7 +42,9 @@ struct CcFrame {                 // device pointers of one frame slot
 };
 
 struct am_cc_ctx {
-    int W, H, WPR, B, MR, ML, MK, CW, min_pixels;
+    int W, H, WPR, B, ML, MK, CW, min_pixels;
+    int R, NS, CAP;              // strip height (rows), strips per frame, run / component slots per strip (= R * ceil(W/2): worst case)
+    int strip_smem;              // dynamic shared memory of k_strip_label
     CcFrame* h_frames;           // host copy of slot descriptors
     CcFrame* d_frames;           // device copy
     int* d_counts;               // [B][4]: n_runs, n_labels, n_kept, crop_words
@@ -72,85 +73,10 @@ __global__ void k_unpack_u8(const uint32_t* __restrict__ bits, int W, int H, int
     dst[((size_t)f * H + y) * W + x] = ((m >> (x & 31)) & 1u) ? 255 : 0;
 }
 
-// ------------------------------------------------------------------------------------------------
-// K1: one warp per row: runs starting before each word, runs per row.
-__global__ void k_row_scan(const uint32_t* __restrict__ bits, const CcFrame* __restrict__ frames, int H, int WPR) {
-    const int f = blockIdx.y;
-    const int y = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (y >= H) return;
-    const int lane = threadIdx.x & 31;
-    const uint32_t* row = bits + ((size_t)f * H + y) * WPR;
-    uint32_t* wp = frames[f].wprefix + (size_t)y * WPR;
-    int running = 0;
-    uint32_t carry = 0;                               // bit31 of the word before this chunk
-    for (int w0 = 0; w0 < WPR; w0 += 32) {
-        int w = w0 + lane;
-        uint32_t m = (w < WPR) ? row[w] : 0u;
-        uint32_t prev = __shfl_up_sync(0xffffffffu, m, 1);
-        if (lane == 0) prev = carry;
-        uint32_t starts = m & ~((m << 1) | (prev >> 31));
-        int c = __popc(starts);
-        int inc = warp_incl_scan(c);
-        if (w < WPR) wp[w] = (uint32_t)(running + inc - c);
-        running += __shfl_sync(0xffffffffu, inc, 31);
-        carry = __shfl_sync(0xffffffffu, m, 31);
-    }
-    if (lane == 0) frames[f].rowbase[y + 1] = running;   // counts, scanned in place by k_row_base
-}
-
-// K2: one block per frame: exclusive scan of runs per row -> rowbase[0..H], n_runs
-__global__ void k_row_base(const CcFrame* __restrict__ frames, int H, int MR, int* __restrict__ counts, int* __restrict__ status) {
-    __shared__ int sm[33];
-    const int f = blockIdx.x;
-    int* rb = frames[f].rowbase;
-    int carry = 0;
-    for (int y0 = 0; y0 < H; y0 += blockDim.x) {
-        int y = y0 + threadIdx.x;
-        int v = (y < H) ? rb[y + 1] : 0;
-        int total;
-        int ex = block_excl_scan(v, sm, &total);
-        __syncthreads();
-        if (y < H) rb[y + 1] = carry + ex + v;           // inclusive -> rowbase[y+1]
-        carry += total;
-    }
-    if (threadIdx.x == 0) {
-        rb[0] = 0;
-        if (carry > MR) { atomicOr(status, 1); }
-        counts[f * 4 + 0] = carry;
-    }
-}
-
 __device__ __forceinline__ uint32_t mask_le(int b) { return (2u << b) - 1u; }   // bits 0..b
 
-// K3: one thread per word: write run start / end records, parent = self
-__global__ void k_run_init(const uint32_t* __restrict__ bits, const CcFrame* __restrict__ frames, int H, int WPR, int MR) {
-    const int f = blockIdx.z, y = blockIdx.y;
-    const int w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= WPR) return;
-    const uint32_t* row = bits + ((size_t)f * H + y) * WPR;
-    const CcFrame fr = frames[f];
-    uint32_t m = row[w];
-    if (m == 0) return;
-    uint32_t cin = (w > 0) ? (row[w - 1] >> 31) : 0u;
-    uint32_t nb0 = (w + 1 < WPR) ? (row[w + 1] & 1u) : 0u;
-    uint32_t starts = m & ~((m << 1) | cin);
-    uint32_t ends = m & ~((m >> 1) | (nb0 << 31));
-    int base = fr.rowbase[y] + (int)fr.wprefix[(size_t)y * WPR + w];
-    uint32_t s = starts;
-    int k = 0;
-    while (s) {
-        int b = __ffs(s) - 1; s &= s - 1;
-        int id = base + k++;
-        if (id < MR) { fr.run_yx[id] = (y << 16) | (w * 32 + b); fr.run_parent[id] = id; }
-    }
-    uint32_t e = ends;
-    while (e) {
-        int b = __ffs(e) - 1; e &= e - 1;
-        int id = base + __popc(starts & mask_le(b)) - 1;
-        if (id >= 0 && id < MR) fr.run_xe[id] = w * 32 + b;
-    }
-}
-
+// union-find with "link the larger root under the smaller" (works on shared or global memory): the root of a set is
+// its minimum id, i.e. the run / strip component that holds the first raster pixel
 __device__ __forceinline__ int uf_find(int* parent, int a) {
     int p;
     while ((p = ((volatile int*)parent)[a]) != a) a = p;
@@ -167,208 +93,387 @@ __device__ __forceinline__ void uf_union(int* parent, int a, int b) {
     }
 }
 
-// K4: one thread per word (rows >= 1): union the runs of vertically adjacent ink
-__global__ void k_run_merge(const uint32_t* __restrict__ bits, const CcFrame* __restrict__ frames, int H, int WPR, int MR) {
-    const int f = blockIdx.z, y = blockIdx.y + 1;
-    const int w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= WPR || y >= H) return;
-    const uint32_t* row = bits + ((size_t)f * H + y) * WPR;
-    const uint32_t* up = row - WPR;
-    uint32_t m = row[w], u = up[w];
-    uint32_t ov = m & u;
-    if (ov == 0) return;
-    uint32_t mp = (w > 0) ? row[w - 1] : 0u, upv = (w > 0) ? up[w - 1] : 0u;
-    uint32_t ovs = ov & ~(ov << 1);
-    ovs &= ~(((mp & upv) >> 31) & 1u);                  // overlap continuing from the previous word: done there
-    if (ovs == 0) return;
-    const CcFrame fr = frames[f];
-    uint32_t st_m = m & ~((m << 1) | (mp >> 31));
-    uint32_t st_u = u & ~((u << 1) | (upv >> 31));
-    int base_m = fr.rowbase[y] + (int)fr.wprefix[(size_t)y * WPR + w];
-    int base_u = fr.rowbase[y - 1] + (int)fr.wprefix[(size_t)(y - 1) * WPR + w];
-    while (ovs) {
-        int b = __ffs(ovs) - 1; ovs &= ovs - 1;
-        int ia = base_m + __popc(st_m & mask_le(b)) - 1;
-        int ib = base_u + __popc(st_u & mask_le(b)) - 1;
-        if (ia < MR && ib < MR && ia >= 0 && ib >= 0) uf_union(fr.run_parent, ia, ib);
-    }
+// One maximal run of ones of word m starting at the lowest set bit of x (x = the not yet visited bits of m)
+__device__ __forceinline__ uint32_t next_segment(uint32_t m, uint32_t x, int* b0, int* len) {
+    const int b = __ffs(x) - 1;
+    const uint32_t t = ~(m >> b);                        // zero bits where the run continues
+    const int l = t ? (__ffs(t) - 1) : 32;
+    *b0 = b; *len = l;
+    return (l == 32) ? 0xFFFFFFFFu : (((1u << l) - 1u) << b);
 }
 
-// K5: flatten + count roots per block of 1024 runs
-__global__ void k_run_flatten(const CcFrame* __restrict__ frames, const int* __restrict__ counts, int MR) {
-    const int f = blockIdx.y;
-    int n = min(counts[f * 4], MR);
-    if ((int)(blockIdx.x * blockDim.x) >= n) return;
+// ------------------------------------------------------------------------------------------------
+// K1: one CTA per strip of R rows.  Everything a strip can decide alone happens in shared memory:
+//   runs (maximal horizontal ink runs, numbered in raster order inside the strip) -> union-find over vertically
+//   adjacent runs -> strip components (numbered by their first raster pixel) with bbox / pixel count reduced by
+//   shared-memory atomics.  Global output: wfirst (one word per mask word), run_comp (one word per run) and one
+//   row per strip component.  Slots are laid out strip by strip with a worst-case capacity, so global slot order ==
+//   raster order of first pixels without any inter-CTA prefix.
+#ifndef STRIP_THREADS
+#define STRIP_THREADS 512
+#endif
+#ifndef STRIP_CAPS
+#define STRIP_CAPS 2048          // strip components reduced in shared memory; the (rare) rest uses global atomics
+#endif
+#ifndef STRIP_MAX_RUNS
+#define STRIP_MAX_RUNS 16384     // worst-case runs of a strip (R * ceil(W/2)) the shared-memory union-find is sized for
+#endif
+#ifndef STRIP_MIN_BLOCKS
+#define STRIP_MIN_BLOCKS 2
+#endif
+__global__ void __launch_bounds__(STRIP_THREADS, STRIP_MIN_BLOCKS)
+k_strip_label(const uint32_t* __restrict__ bits, const CcFrame* __restrict__ frames, int W, int H, int WPR, int R, int CAP) {
+    extern __shared__ uint32_t smem[];
+    __shared__ int s_scan[33];
+    __shared__ int s_rowbase[33];
+    const int s = blockIdx.x, f = blockIdx.y;
+    const int y0 = s * R, rows = min(R, H - y0), nwords = rows * WPR;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = STRIP_THREADS >> 5;
+    uint32_t* s_bits = smem;
+    int* s_first = (int*)(smem + R * WPR);
+    int* s_parent = s_first + R * WPR;
+    int* s_minx = s_parent + CAP;
+    int* s_maxx = s_minx + STRIP_CAPS;
+    int* s_miny = s_maxx + STRIP_CAPS;
+    int* s_maxy = s_miny + STRIP_CAPS;
+    int* s_cnt = s_maxy + STRIP_CAPS;
     const CcFrame fr = frames[f];
-    int id = blockIdx.x * blockDim.x + threadIdx.x;
-    int isroot = 0;
-    if (id < n) {
-        int r = uf_find(fr.run_parent, id);
-        fr.run_parent[id] = r;
-        isroot = (r == id);
-    }
-    int c = __syncthreads_count(isroot);
-    if (threadIdx.x == 0) fr.blockcnt[blockIdx.x] = c;
-}
+    const int base = s * CAP;                            // first run slot == first component slot of this strip
 
-// K6: one block per frame: scan block counts -> block bases, n_labels
-__global__ void k_block_base(const CcFrame* __restrict__ frames, int* __restrict__ counts, int MR, int ML, int* __restrict__ status) {
-    __shared__ int sm[33];
-    const int f = blockIdx.x;
-    int n = min(counts[f * 4], MR);
-    int nb = (n + 1023) >> 10;
-    int* bc = frames[f].blockcnt;
-    int carry = 0;
-    for (int i0 = 0; i0 < nb; i0 += blockDim.x) {
-        int i = i0 + threadIdx.x;
-        int v = (i < nb) ? bc[i] : 0;
-        int total;
-        int ex = block_excl_scan(v, sm, &total);
-        __syncthreads();
-        if (i < nb) bc[i] = carry + ex;
-        carry += total;
-    }
-    if (threadIdx.x == 0) {
-        if (carry > ML) atomicOr(status, 2);
-        counts[f * 4 + 1] = carry;
-    }
-}
-
-// K7: roots get their raster-order label (rank + 1) and initialise their table row
-__global__ void k_root_label(const CcFrame* __restrict__ frames, const int* __restrict__ counts, int MR, int ML, int W, int H) {
-    __shared__ int sm[33];
-    const int f = blockIdx.y;
-    int n = min(counts[f * 4], MR);
-    if ((int)(blockIdx.x * blockDim.x) >= n) return;
-    const CcFrame fr = frames[f];
-    int id = blockIdx.x * blockDim.x + threadIdx.x;
-    int isroot = (id < n) && (fr.run_parent[id] == id);
-    int total;
-    int ex = block_excl_scan(isroot, sm, &total);
-    if (isroot) {
-        int lab = fr.blockcnt[blockIdx.x] + ex;          // 0-based
-        fr.run_label[id] = lab + 1;
-        if (lab < ML) {                                  // accessmath_lib.c:364-374
-            fr.t_min_y[lab] = H; fr.t_max_y[lab] = 0; fr.t_min_x[lab] = W; fr.t_max_x[lab] = 0; fr.t_count[lab] = 0;
+    // 1. the strip's mask words (rows are contiguous in memory)
+    {
+        const uint32_t* src = bits + ((size_t)f * H + y0) * WPR;
+        if ((WPR & 3) == 0) {
+            const uint4* s4 = (const uint4*)src; uint4* d4 = (uint4*)s_bits;
+            for (int i = tid; i < (nwords >> 2); i += STRIP_THREADS) d4[i] = s4[i];
+        } else {
+            for (int i = tid; i < nwords; i += STRIP_THREADS) s_bits[i] = src[i];
         }
     }
+    __syncthreads();
+    // 2. warp per row: run starts per word, prefix inside the row
+    for (int r = warp; r < rows; r += nwarps) {
+        int running = 0;
+        uint32_t carry = 0;
+        for (int w0 = 0; w0 < WPR; w0 += 32) {
+            const int w = w0 + lane;
+            const uint32_t m = (w < WPR) ? s_bits[r * WPR + w] : 0u;
+            uint32_t prev = __shfl_up_sync(0xffffffffu, m, 1);
+            if (lane == 0) prev = carry;
+            const int c = __popc(m & ~((m << 1) | (prev >> 31)));
+            const int inc = warp_incl_scan(c);
+            if (w < WPR) s_first[r * WPR + w] = running + inc - c;
+            running += __shfl_sync(0xffffffffu, inc, 31);
+            carry = __shfl_sync(0xffffffffu, m, 31);
+        }
+        if (lane == 0) s_rowbase[r + 1] = running;
+    }
+    __syncthreads();
+    // 3. scan over the rows (R <= 32)
+    if (warp == 0) {
+        const int v = (lane < rows) ? s_rowbase[lane + 1] : 0;
+        const int inc = warp_incl_scan(v);
+        if (lane < rows) s_rowbase[lane + 1] = inc;
+        if (lane == 0) s_rowbase[0] = 0;
+    }
+    __syncthreads();
+    const int n_runs = s_rowbase[rows];
+    // 4. strip-local run id of the first run starting in each word; parent = self
+    for (int i = tid; i < nwords; i += STRIP_THREADS) {
+        const int v = s_first[i] + s_rowbase[i / WPR];
+        s_first[i] = v;
+        fr.wfirst[(size_t)y0 * WPR + i] = (uint32_t)(base + v);
+    }
+    for (int i = tid; i < n_runs; i += STRIP_THREADS) s_parent[i] = i;
+    __syncthreads();
+    // 5. union the runs of vertically adjacent ink (one overlap-run start = one union)
+    for (int i = tid + WPR; i < nwords; i += STRIP_THREADS) {
+        const int w = i % WPR;
+        const uint32_t m = s_bits[i], u = s_bits[i - WPR];
+        const uint32_t ov = m & u;
+        if (ov == 0) continue;
+        const uint32_t mp = (w > 0) ? s_bits[i - 1] : 0u, upv = (w > 0) ? s_bits[i - WPR - 1] : 0u;
+        uint32_t ovs = ov & ~(ov << 1);
+        ovs &= ~(((mp & upv) >> 31) & 1u);              // overlap continuing from the previous word: done there
+        if (ovs == 0) continue;
+        const uint32_t st_m = m & ~((m << 1) | (mp >> 31));
+        const uint32_t st_u = u & ~((u << 1) | (upv >> 31));
+        const int fm = s_first[i], fu = s_first[i - WPR];
+        while (ovs) {
+            const int b = __ffs(ovs) - 1; ovs &= ovs - 1;
+            // link the lower run straight to the upper run (no root search: chains are at most one hop per row);
+            // a run that already had a different parent is a join of two upper runs -> a real union of those
+            const int ia = fm + __popc(st_m & mask_le(b)) - 1, ib = fu + __popc(st_u & mask_le(b)) - 1;
+            const int old = atomicMin(&s_parent[ia], ib);
+            if (old != ia && old != ib) uf_union(s_parent, old, ib);
+        }
+    }
+    __syncthreads();
+    // 6. flatten: pointer jumping covers the one-hop-per-row chains (depth < R <= 32), then a plain root search
+    //    for what joins left over
+#pragma unroll 1
+    for (int round = 0; round < 5; ++round) {
+        for (int i = tid; i < n_runs; i += STRIP_THREADS) {
+            const int p = s_parent[i];
+            const int g = s_parent[p];
+            if (g != p) s_parent[i] = g;
+        }
+        __syncthreads();
+    }
+    for (int i = tid; i < n_runs; i += STRIP_THREADS) {
+        const int r = uf_find(s_parent, i);
+        if (r != s_parent[i]) s_parent[i] = r;
+    }
+    __syncthreads();
+    // 7. number the roots in run order (= raster order of first pixels); a root's parent entry becomes ~component
+    int n_comp = 0;
+    for (int i0 = 0; i0 < n_runs; i0 += STRIP_THREADS) {
+        const int i = i0 + tid;
+        const int isroot = (i < n_runs) && (s_parent[i] == i);
+        int tot;
+        const int cid = n_comp + block_excl_scan(isroot, s_scan, &tot);
+        if (isroot) {
+            s_parent[i] = ~cid;
+            if (cid < STRIP_CAPS) { s_minx[cid] = W; s_maxx[cid] = 0; s_miny[cid] = H; s_maxy[cid] = 0; s_cnt[cid] = 0; }
+            else {
+                const int slot = base + cid;
+                fr.c_min_x[slot] = W; fr.c_max_x[slot] = 0; fr.c_min_y[slot] = H; fr.c_max_y[slot] = 0; fr.c_count[slot] = 0;
+                fr.c_link[slot] = slot;
+            }
+        }
+        n_comp += tot;
+    }
+    __syncthreads();
+    // 8. every segment (part of a run inside one word) adds to its component; run starts record run -> component
+    for (int i = tid; i < nwords; i += STRIP_THREADS) {
+        const uint32_t m = s_bits[i];
+        if (m == 0) continue;
+        const int r = i / WPR, w = i - r * WPR, y = y0 + r;
+        const uint32_t cin = (w > 0) ? (s_bits[i - 1] >> 31) : 0u;
+        const uint32_t starts = m & ~((m << 1) | cin);
+        const int first = s_first[i];
+        uint32_t x = m;
+        while (x) {
+            int b0, len;
+            const uint32_t seg = next_segment(m, x, &b0, &len);
+            x &= ~seg;
+            const int id = first + __popc(starts & mask_le(b0)) - 1;
+            const int p = s_parent[id];
+            const int cid = (p < 0) ? ~p : ~s_parent[p];
+            const int xs = w * 32 + b0, xe = xs + len - 1;
+            if (cid < STRIP_CAPS) {
+                atomicMin(&s_minx[cid], xs); atomicMax(&s_maxx[cid], xe); atomicMax(&s_maxy[cid], y); atomicAdd(&s_cnt[cid], len);
+                if (p < 0) s_miny[cid] = y;              // the root run holds the first raster pixel: its row is min_y
+            } else {
+                const int slot = base + cid;
+                atomicMin(&fr.c_min_x[slot], xs); atomicMax(&fr.c_max_x[slot], xe);
+                atomicMin(&fr.c_min_y[slot], y); atomicMax(&fr.c_max_y[slot], y); atomicAdd(&fr.c_count[slot], len);
+            }
+            if (seg & starts) fr.run_comp[base + id] = (uint32_t)(base + cid);
+        }
+    }
+    __syncthreads();
+    // 9. strip-component rows
+    for (int c = tid; c < min(n_comp, STRIP_CAPS); c += STRIP_THREADS) {
+        const int slot = base + c;
+        fr.c_min_x[slot] = s_minx[c]; fr.c_max_x[slot] = s_maxx[c]; fr.c_min_y[slot] = s_miny[c]; fr.c_max_y[slot] = s_maxy[c];
+        fr.c_count[slot] = s_cnt[c]; fr.c_link[slot] = slot;
+    }
+    if (tid == 0) fr.strip_n[s] = make_int2(n_runs, n_comp);
 }
 
-// K8: every run takes its root's label; warp-aggregated bbox / count reduction (accessmath_lib.c:378-409)
-__global__ void k_run_stats(const CcFrame* __restrict__ frames, const int* __restrict__ counts, int MR, int ML) {
-    const int f = blockIdx.y;
-    int n = min(counts[f * 4], MR);
-    if ((int)(blockIdx.x * blockDim.x) >= n) return;
-    const CcFrame fr = frames[f];
-    int id = blockIdx.x * blockDim.x + threadIdx.x;
-    int lab = 0, y = 0, xs = 0, xe = 0;
-    if (id < n) {
-        lab = fr.run_label[fr.run_parent[id]];
-        fr.run_label[id] = lab;
-        int yx = fr.run_yx[id];
-        y = yx >> 16; xs = yx & 0xffff; xe = fr.run_xe[id];
-        if (lab > ML) lab = 0;
-    }
-    unsigned peers = __match_any_sync(0xffffffffu, lab);
-    int mn_x = __reduce_min_sync(peers, xs), mx_x = __reduce_max_sync(peers, xe);
-    int mn_y = __reduce_min_sync(peers, y), mx_y = __reduce_max_sync(peers, y);
-    int cnt = __reduce_add_sync(peers, xe - xs + 1);
-    if (lab > 0 && (int)(threadIdx.x & 31) == __ffs(peers) - 1) {
-        int l = lab - 1;
-        atomicMin(&fr.t_min_x[l], mn_x); atomicMax(&fr.t_max_x[l], mx_x);
-        atomicMin(&fr.t_min_y[l], mn_y); atomicMax(&fr.t_max_y[l], mx_y);
-        atomicAdd(&fr.t_count[l], cnt);
-    }
-}
-
-// K9: one block per frame: compact labels with count >= min_pixels (labeler.py:177), crop offsets
-__global__ void k_kept_scan(const CcFrame* __restrict__ frames, int* __restrict__ counts, int ML, int MK, int CW,
-                            int min_pixels, int* __restrict__ status) {
+// K2: one CTA per frame over its strip components (a few thousand): union the components of vertically adjacent ink
+// across the seams between strips, flatten, number the roots in slot order (= raster order of first pixels = the
+// SciPy label), reduce the partial statistics into the label table (= CC_AgeBoundaries, accessmath_lib.c:357-413),
+// then compact the labels with count >= min_pixels (labeler.py:177), lay out their crops and zero the crop arena.
+#define RESOLVE_THREADS 1024
+__global__ void __launch_bounds__(RESOLVE_THREADS)
+k_resolve(const uint32_t* __restrict__ bits, const CcFrame* __restrict__ frames, int* __restrict__ counts, int H, int WPR, int R,
+          int NS, int CAP, int ML, int MK, int CW, int min_pixels, int* __restrict__ status) {
+    extern __shared__ int s_prefix[];                    // [NS + 1] components before each strip
     __shared__ int sm[33];
-    const int f = blockIdx.x;
+    const int f = blockIdx.x, tid = threadIdx.x;
     const CcFrame fr = frames[f];
-    int n = min(counts[f * 4 + 1], ML);
+    // 0. seams: one (seam, word) per thread
+    for (int i = tid; i < (NS - 1) * WPR; i += RESOLVE_THREADS) {
+        const int sidx = i / WPR, w = i - sidx * WPR, y = (sidx + 1) * R;
+        const uint32_t* row = bits + ((size_t)f * H + y) * WPR;
+        const uint32_t* up = row - WPR;
+        const uint32_t m = row[w], u = up[w];
+        const uint32_t ov = m & u;
+        if (ov == 0) continue;
+        const uint32_t mp = (w > 0) ? row[w - 1] : 0u, upv = (w > 0) ? up[w - 1] : 0u;
+        uint32_t ovs = ov & ~(ov << 1);
+        ovs &= ~(((mp & upv) >> 31) & 1u);              // overlap continuing from the previous word: done there
+        if (ovs == 0) continue;
+        const uint32_t st_m = m & ~((m << 1) | (mp >> 31));
+        const uint32_t st_u = u & ~((u << 1) | (upv >> 31));
+        const int fm = (int)fr.wfirst[(size_t)y * WPR + w], fu = (int)fr.wfirst[(size_t)(y - 1) * WPR + w];
+        while (ovs) {
+            const int b = __ffs(ovs) - 1; ovs &= ovs - 1;
+            const int ca = (int)fr.run_comp[fm + __popc(st_m & mask_le(b)) - 1];
+            const int cb = (int)fr.run_comp[fu + __popc(st_u & mask_le(b)) - 1];
+            uf_union(fr.c_link, ca, cb);
+        }
+    }
+    int total = 0, runs = 0;
+    for (int s0 = 0; s0 < NS; s0 += RESOLVE_THREADS) {
+        const int s = s0 + tid;
+        const int2 n = (s < NS) ? fr.strip_n[s] : make_int2(0, 0);
+        int tot, rtot;
+        const int ex = block_excl_scan(n.y, sm, &tot);
+        block_excl_scan(n.x, sm, &rtot);
+        if (s < NS) s_prefix[s] = total + ex;
+        total += tot; runs += rtot;
+    }
+    if (tid == 0) s_prefix[NS] = total;
+    __syncthreads();
+    auto slot_of = [&](int idx) {                        // compact component index -> slot
+        int lo = 0, hi = NS;                             // last strip with prefix <= idx
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_prefix[mid] <= idx) lo = mid; else hi = mid; }
+        return lo * CAP + (idx - s_prefix[lo]);
+    };
+    // a. flatten
+    for (int idx = tid; idx < total; idx += RESOLVE_THREADS) {
+        const int c = slot_of(idx);
+        fr.c_link[c] = uf_find(fr.c_link, c);
+    }
+    __syncthreads();
+    // b. roots -> labels, own statistics start the table row
+    int n_labels = 0;
+    for (int i0 = 0; i0 < total; i0 += RESOLVE_THREADS) {
+        const int idx = i0 + tid;
+        int c = 0, isroot = 0;
+        if (idx < total) { c = slot_of(idx); isroot = (fr.c_link[c] == c); }
+        int tot;
+        const int lab = n_labels + block_excl_scan(isroot, sm, &tot);       // 0-based
+        if (isroot) {
+            fr.c_label[c] = lab + 1;
+            if (lab < ML) {
+                fr.t_min_y[lab] = fr.c_min_y[c]; fr.t_max_y[lab] = fr.c_max_y[c]; fr.t_min_x[lab] = fr.c_min_x[c];
+                fr.t_max_x[lab] = fr.c_max_x[c]; fr.t_count[lab] = fr.c_count[c];
+            }
+        }
+        n_labels += tot;
+    }
+    __syncthreads();
+    // c. the other strip components of a label (components that cross a seam) fold into the root's row
+    for (int idx = tid; idx < total; idx += RESOLVE_THREADS) {
+        const int c = slot_of(idx);
+        const int r = fr.c_link[c];
+        if (r == c) continue;
+        const int lab = fr.c_label[r];
+        fr.c_label[c] = lab;
+        if (lab <= ML) {
+            const int l = lab - 1;                        // min_y: the root holds the first raster pixel
+            atomicMax(&fr.t_max_y[l], fr.c_max_y[c]); atomicMin(&fr.t_min_x[l], fr.c_min_x[c]);
+            atomicMax(&fr.t_max_x[l], fr.c_max_x[c]); atomicAdd(&fr.t_count[l], fr.c_count[c]);
+        }
+    }
+    __syncthreads();
+    // d. kept labels + crop offsets
+    const int n = min(n_labels, ML);
     int kcarry = 0; unsigned wcarry = 0; bool over = false;
-    for (int i0 = 0; i0 < n; i0 += blockDim.x) {
-        int l = i0 + threadIdx.x;
+    for (int i0 = 0; i0 < n; i0 += RESOLVE_THREADS) {
+        const int l = i0 + tid;
         int keep = 0, words = 0;
         if (l < n && fr.t_count[l] >= min_pixels) {
             keep = 1;
             words = ((fr.t_max_x[l] >> 5) - (fr.t_min_x[l] >> 5) + 1) * (fr.t_max_y[l] - fr.t_min_y[l] + 1);
         }
         int ktot, wtot;
-        int kex = block_excl_scan(keep, sm, &ktot);
-        int wex = block_excl_scan(words, sm, &wtot);
-        __syncthreads();
+        const int kex = block_excl_scan(keep, sm, &ktot);
+        const int wex = block_excl_scan(words, sm, &wtot);
         if (l < n) {
             uint32_t off = NONE_U32;
             if (keep) {
-                int ki = kcarry + kex;
-                unsigned wo = wcarry + (unsigned)wex;
+                const int ki = kcarry + kex;
+                const unsigned wo = wcarry + (unsigned)wex;
                 if (ki < MK && wo + (unsigned)words <= (unsigned)CW) {
-                    fr.kept_label[ki] = l + 1; fr.kept_crop_off[ki] = wo; off = wo;
+                    fr.kept_label[ki] = l + 1; fr.kept_crop_off[ki] = wo; fr.match_unique[ki] = -1; off = wo;
                 } else over = true;
             }
             fr.lab_crop_off[l] = off;
         }
         kcarry += ktot; wcarry += (unsigned)wtot;
     }
-    if (__syncthreads_or(over) && threadIdx.x == 0) atomicOr(status, 4);
-    if (threadIdx.x == 0) {
-        counts[f * 4 + 2] = min(kcarry, MK);
-        counts[f * 4 + 3] = (int)min(wcarry, (unsigned)CW);
+    const int any_over = __syncthreads_or(over);
+    {                                                    // zero the crop arena (16-byte aligned, padded by 4 words)
+        const int n4 = (int)((min(wcarry, (unsigned)CW) + 3u) >> 2);
+        uint4* c4 = (uint4*)fr.crops;
+        for (int i = tid; i < n4; i += RESOLVE_THREADS) c4[i] = make_uint4(0, 0, 0, 0);
+    }
+    if (tid == 0) {
+        if (any_over) atomicOr(status, 4);
+        if (n_labels > ML) atomicOr(status, 2);
+        counts[f * 4 + 0] = runs; counts[f * 4 + 1] = n_labels;
+        counts[f * 4 + 2] = min(kcarry, MK); counts[f * 4 + 3] = (int)min(wcarry, (unsigned)CW);
     }
 }
 
-__global__ void k_crop_clear(const CcFrame* __restrict__ frames, const int* __restrict__ counts) {
-    const int f = blockIdx.y;
-    int n = counts[f * 4 + 3];
-    uint32_t* c = frames[f].crops;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) c[i] = 0u;
-}
+__device__ __forceinline__ int label_of_run(const CcFrame& fr, int run_slot) { return fr.c_label[fr.run_comp[run_slot]]; }
 
-// K10: one thread per run: OR the run's bits into its CC's crop (labeler.py:183, bit-packed)
-__global__ void k_crop_fill(const CcFrame* __restrict__ frames, const int* __restrict__ counts, int MR) {
+// K3: one thread per mask word: OR every segment into its CC's crop (labeler.py:183, bit-packed, absolute x)
+__global__ void k_crop_fill(const uint32_t* __restrict__ bits, const CcFrame* __restrict__ frames, int H, int WPR) {
     const int f = blockIdx.y;
-    int n = min(counts[f * 4], MR);
-    int id = blockIdx.x * blockDim.x + threadIdx.x;
-    if (id >= n) return;
-    const CcFrame fr = frames[f];
-    int lab = fr.run_label[id];
-    if (lab <= 0) return;
-    uint32_t off = fr.lab_crop_off[lab - 1];
-    if (off == NONE_U32) return;
-    int l = lab - 1;
-    int wx0 = fr.t_min_x[l] >> 5, cw = (fr.t_max_x[l] >> 5) - wx0 + 1;
-    int yx = fr.run_yx[id];
-    int y = yx >> 16, xs = yx & 0xffff, xe = fr.run_xe[id];
-    uint32_t* dst = fr.crops + off + (size_t)(y - fr.t_min_y[l]) * cw - wx0;
-    for (int w = xs >> 5; w <= (xe >> 5); ++w) {
-        int lo = max(xs, w * 32) & 31, hi = min(xe, w * 32 + 31) & 31;
-        uint32_t b = mask_le(hi) & ~(mask_le(lo) >> 1);
-        if (lo == 0) b = mask_le(hi);
-        atomicOr(&dst[w], b);
-    }
-}
-
-// K11: label image (int32, 0 = background), one thread per pixel, coalesced stores
-__global__ void k_label_image(const uint32_t* __restrict__ bits, const CcFrame* __restrict__ frames, int W, int H, int WPR, int MR,
-                              int32_t* __restrict__ labels) {
-    const int f = blockIdx.z, y = blockIdx.y;
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    if (x >= W) return;
-    const uint32_t* row = bits + ((size_t)f * H + y) * WPR;
-    int w = x >> 5, b = x & 31;
-    uint32_t m = row[w];
-    int lab = 0;
-    if ((m >> b) & 1u) {
+    const uint32_t* fbits = bits + (size_t)f * H * WPR;
+    const int nwords = H * WPR;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += gridDim.x * blockDim.x) {
+        const uint32_t m = fbits[i];
+        if (m == 0) continue;
+        const int y = i / WPR, w = i - y * WPR;
         const CcFrame fr = frames[f];
-        uint32_t cin = (w > 0) ? (row[w - 1] >> 31) : 0u;
-        uint32_t starts = m & ~((m << 1) | cin);
-        int id = fr.rowbase[y] + (int)fr.wprefix[(size_t)y * WPR + w] + __popc(starts & mask_le(b)) - 1;
-        if (id >= 0 && id < MR) lab = fr.run_label[id];
+        const uint32_t cin = (w > 0) ? (fbits[i - 1] >> 31) : 0u;
+        const uint32_t starts = m & ~((m << 1) | cin);
+        const int first = (int)fr.wfirst[i];
+        uint32_t x = m;
+        while (x) {
+            int b0, len;
+            const uint32_t seg = next_segment(m, x, &b0, &len);
+            x &= ~seg;
+            const int l = label_of_run(fr, first + __popc(starts & mask_le(b0)) - 1) - 1;
+            const uint32_t off = fr.lab_crop_off[l];
+            if (off == NONE_U32) continue;
+            const int wx0 = fr.t_min_x[l] >> 5, cw = (fr.t_max_x[l] >> 5) - wx0 + 1;
+            atomicOr(&fr.crops[off + (size_t)(y - fr.t_min_y[l]) * cw + (w - wx0)], seg);
+        }
     }
-    labels[((size_t)f * H + y) * W + x] = lab;
+}
+
+// K4 (optional): label image (int32, 0 = background = scipy.ndimage.label's output), four pixels per thread
+__global__ void k_label_image(const uint32_t* __restrict__ bits, const CcFrame* __restrict__ frames, int W, int H, int WPR,
+                              int32_t* __restrict__ labels) {
+    const int f = blockIdx.y;
+    const uint32_t* fbits = bits + (size_t)f * H * WPR;
+    int32_t* out = labels + (size_t)f * H * W;
+    const int gpr = (W + 3) >> 2, ngroups = H * gpr;     // groups of 4 pixels per row
+    const bool vec = (W & 3) == 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ngroups; i += gridDim.x * blockDim.x) {
+        const int y = i / gpr, x0 = (i - y * gpr) << 2, w = x0 >> 5, b = x0 & 31;
+        const uint32_t m = fbits[(size_t)y * WPR + w];
+        int lab[4] = {0, 0, 0, 0};
+        if ((m >> b) & 15u) {
+            const CcFrame fr = frames[f];
+            const uint32_t cin = (w > 0) ? (fbits[(size_t)y * WPR + w - 1] >> 31) : 0u;
+            const uint32_t starts = m & ~((m << 1) | cin);
+            const int first = (int)fr.wfirst[(size_t)y * WPR + w];
+            int prev_id = -1, prev_lab = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if ((m >> (b + k)) & 1u) {
+                    const int id = first + __popc(starts & mask_le(b + k)) - 1;
+                    if (id != prev_id) { prev_id = id; prev_lab = label_of_run(fr, id); }
+                    lab[k] = prev_lab;
+                }
+            }
+        }
+        int32_t* dst = out + (size_t)y * W + x0;
+        if (vec) *(int4*)dst = make_int4(lab[0], lab[1], lab[2], lab[3]);
+        else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) if (x0 + k < W) dst[k] = lab[k];
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -667,10 +772,6 @@ __global__ void k_rows_all(const CcFrame* __restrict__ frames, const int* __rest
     int r = offs[f] + c;
     if (r < cap) write_row(frames[f], c, rows + (size_t)r * 8);
 }
-__global__ void k_init_match(const CcFrame* __restrict__ frames, int MK) {
-    int* m = frames[blockIdx.y].match_unique;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < MK; i += gridDim.x * blockDim.x) m[i] = -1;
-}
 
 // ------------------------------------------------------------------------------------------------
 // active-set export / import (frame-shard hand-off)
@@ -882,30 +983,39 @@ extern "C" int am_unpack_mask_u8(const uint32_t* d_bits, int width, int height, 
 
 extern "C" am_cc_ctx* am_cc_create(int width, int height, int max_batch, int max_runs, int max_labels, int max_kept,
                                    int crop_words, int min_pixels) {
+    (void)max_runs;                                      // run / strip-component slots are sized for the worst case
     if (width <= 0 || height <= 0 || width > 65535 || height > 32767 || max_batch <= 0) return nullptr;
     am_cc_ctx* c = new am_cc_ctx();
     c->W = width; c->H = height; c->WPR = am_words_per_row_impl(width); c->B = max_batch;
     long long P = (long long)width * height;
-    c->MR = max_runs > 0 ? max_runs : (int)(P / 2 + 64);
-    c->ML = max_labels > 0 ? max_labels : c->MR;
-    if (c->ML > c->MR) c->ML = c->MR;
+    // strip height: the largest power of two whose worst-case run count (every other pixel) fits the shared-memory
+    // union-find of k_strip_label
+    const int per_row = (width + 1) / 2;
+    int R = 32;
+    while (R > 1 && (long long)R * per_row > STRIP_MAX_RUNS) R >>= 1;
+    c->R = R; c->NS = (height + R - 1) / R; c->CAP = R * per_row;
+    c->strip_smem = (2 * R * c->WPR + c->CAP + 5 * STRIP_CAPS) * 4;
+    if (c->strip_smem > 200 * 1024) { fprintf(stderr, "[accessmath_b200] am_cc_create: width %d too large\n", width); delete c; return nullptr; }
+    c->ML = max_labels > 0 ? max_labels : (int)(P / 2 + 64);
     c->MK = max_kept > 0 ? max_kept : (int)(P / 20 + 64);      // a kept CC has >= min_pixels (20) pixels
     if (c->MK > c->ML) c->MK = c->ML;
     c->CW = crop_words > 0 ? crop_words : (int)(4 * (long long)c->WPR * height + 1024);
     c->min_pixels = min_pixels;
+    const size_t slots = (size_t)c->NS * c->CAP;
     size_t per = 0;
     auto add = [&](size_t bytes) { size_t o = per; per += align_up(bytes); return o; };
-    size_t o_wp = add((size_t)height * c->WPR * 4), o_rb = add((size_t)(height + 1) * 4);
-    size_t o_par = add((size_t)c->MR * 4), o_yx = add((size_t)c->MR * 4), o_xe = add((size_t)c->MR * 4), o_rl = add((size_t)c->MR * 4);
-    size_t o_bc = add((size_t)(c->MR / 1024 + 2) * 4);
+    size_t o_wf = add((size_t)height * c->WPR * 4), o_rc = add(slots * 4);
+    size_t o_c[7]; for (int i = 0; i < 7; ++i) o_c[i] = add(slots * 4);
+    size_t o_sn = add((size_t)c->NS * sizeof(int2));
     size_t o_t[5]; for (int i = 0; i < 5; ++i) o_t[i] = add((size_t)c->ML * 4);
     size_t o_lco = add((size_t)c->ML * 4);
     size_t o_kl = add((size_t)c->MK * 4), o_kco = add((size_t)c->MK * 4), o_mu = add((size_t)c->MK * 4);
-    size_t o_cr = add((size_t)c->CW * 4);
+    size_t o_cr = add((size_t)(c->CW + 4) * 4);
     size_t head = align_up(sizeof(CcFrame) * max_batch) + align_up((size_t)max_batch * 16) + 256;
     size_t total = head + per * max_batch;
     if (cudaMalloc(&c->slab, total) != cudaSuccess) {
         fprintf(stderr, "[accessmath_b200] am_cc_create: cudaMalloc(%zu) failed\n", total);
+        cudaGetLastError();
         delete c; return nullptr;
     }
     char* base = (char*)c->slab;
@@ -916,8 +1026,10 @@ extern "C" am_cc_ctx* am_cc_create(int width, int height, int max_batch, int max
     for (int f = 0; f < max_batch; ++f) {
         char* p = base + head + per * f;
         CcFrame& fr = c->h_frames[f];
-        fr.wprefix = (uint32_t*)(p + o_wp); fr.rowbase = (int*)(p + o_rb); fr.run_parent = (int*)(p + o_par);
-        fr.run_yx = (int*)(p + o_yx); fr.run_xe = (int*)(p + o_xe); fr.run_label = (int*)(p + o_rl); fr.blockcnt = (int*)(p + o_bc);
+        fr.wfirst = (uint32_t*)(p + o_wf); fr.run_comp = (uint32_t*)(p + o_rc);
+        fr.c_min_x = (int*)(p + o_c[0]); fr.c_max_x = (int*)(p + o_c[1]); fr.c_min_y = (int*)(p + o_c[2]); fr.c_max_y = (int*)(p + o_c[3]);
+        fr.c_count = (int*)(p + o_c[4]); fr.c_link = (int*)(p + o_c[5]); fr.c_label = (int*)(p + o_c[6]);
+        fr.strip_n = (int2*)(p + o_sn);
         fr.t_min_y = (int*)(p + o_t[0]); fr.t_max_y = (int*)(p + o_t[1]); fr.t_min_x = (int*)(p + o_t[2]);
         fr.t_max_x = (int*)(p + o_t[3]); fr.t_count = (int*)(p + o_t[4]); fr.lab_crop_off = (uint32_t*)(p + o_lco);
         fr.kept_label = (int*)(p + o_kl); fr.kept_crop_off = (uint32_t*)(p + o_kco); fr.match_unique = (int*)(p + o_mu);
@@ -927,6 +1039,8 @@ extern "C" am_cc_ctx* am_cc_create(int width, int height, int max_batch, int max
     cudaMemset(c->d_counts, 0, (size_t)max_batch * 16);
     cudaMemset(c->d_status, 0, 4);
     cudaMallocHost(&c->h_counts, (size_t)max_batch * 16 + 16);
+    cudaFuncSetAttribute(k_strip_label, cudaFuncAttributeMaxDynamicSharedMemorySize, c->strip_smem);
+    if ((size_t)(c->NS + 1) * 4 > 48 * 1024) cudaFuncSetAttribute(k_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (c->NS + 1) * 4);
     return c;
 }
 extern "C" void am_cc_destroy(am_cc_ctx* c) {
@@ -938,23 +1052,15 @@ extern "C" int am_cc_label_batch(am_cc_ctx* c, const uint32_t* d_bits, int batch
     if (!c || !d_bits || batch <= 0 || batch > c->B) return AM_ERR_ARG;
     cudaStream_t st = S(stream);
     const int H = c->H, W = c->W, WPR = c->WPR;
-    k_row_scan<<<dim3(am_div_up(H, 4), batch), 128, 0, st>>>(d_bits, c->d_frames, H, WPR);
-    k_row_base<<<batch, 1024, 0, st>>>(c->d_frames, H, c->MR, c->d_counts, c->d_status);
-    dim3 gw(am_div_up(WPR, 64), H, batch);
-    k_run_init<<<gw, 64, 0, st>>>(d_bits, c->d_frames, H, WPR, c->MR);
-    if (H > 1) k_run_merge<<<dim3(gw.x, H - 1, batch), 64, 0, st>>>(d_bits, c->d_frames, H, WPR, c->MR);
-    // run-level kernels: grid sized for the capacity; blocks beyond n_runs exit immediately
-    long long P = (long long)W * H;
-    int run_blocks = am_div_up(c->MR < P / 2 + 64 ? c->MR : P / 2 + 64, 1024);
-    k_run_flatten<<<dim3(run_blocks, batch), 1024, 0, st>>>(c->d_frames, c->d_counts, c->MR);
-    k_block_base<<<batch, 1024, 0, st>>>(c->d_frames, c->d_counts, c->MR, c->ML, c->d_status);
-    k_root_label<<<dim3(run_blocks, batch), 1024, 0, st>>>(c->d_frames, c->d_counts, c->MR, c->ML, W, H);
-    k_run_stats<<<dim3(run_blocks, batch), 1024, 0, st>>>(c->d_frames, c->d_counts, c->MR, c->ML);
-    k_kept_scan<<<batch, 1024, 0, st>>>(c->d_frames, c->d_counts, c->ML, c->MK, c->CW, c->min_pixels, c->d_status);
-    k_crop_clear<<<dim3(64, batch), 256, 0, st>>>(c->d_frames, c->d_counts);
-    k_crop_fill<<<dim3(run_blocks * 4, batch), 256, 0, st>>>(c->d_frames, c->d_counts, c->MR);
-    k_init_match<<<dim3(8, batch), 256, 0, st>>>(c->d_frames, c->MK);
-    if (d_labels) k_label_image<<<dim3(am_div_up(W, 256), H, batch), 256, 0, st>>>(d_bits, c->d_frames, W, H, WPR, c->MR, d_labels);
+    k_strip_label<<<dim3(c->NS, batch), STRIP_THREADS, c->strip_smem, st>>>(d_bits, c->d_frames, W, H, WPR, c->R, c->CAP);
+    k_resolve<<<batch, RESOLVE_THREADS, (c->NS + 1) * 4, st>>>(d_bits, c->d_frames, c->d_counts, H, WPR, c->R, c->NS, c->CAP, c->ML, c->MK,
+                                                             c->CW, c->min_pixels, c->d_status);
+    const int nwords = H * WPR;
+    k_crop_fill<<<dim3(nwords >= 128 * 256 ? 128 : am_div_up(nwords, 256), batch), 256, 0, st>>>(d_bits, c->d_frames, H, WPR);
+    if (d_labels) {
+        const int ngroups = H * ((W + 3) / 4);
+        k_label_image<<<dim3(ngroups >= 256 * 256 ? 256 : am_div_up(ngroups, 256), batch), 256, 0, st>>>(d_bits, c->d_frames, W, H, WPR, d_labels);
+    }
     AM_CUDA(cudaGetLastError());
     return AM_OK;
 }
