@@ -531,9 +531,12 @@ struct am_estimator {
     int *u_min_x, *u_max_x, *u_min_y, *u_max_y, *u_size, *u_last, *u_first_frame, *u_first_label;
     unsigned long long* u_crop_off;
     uint32_t* arena;             // first-seen crops, append only
-    int *act[2];                 // active lists (ascending unique idx), double buffered
-    int cur;                     // which act buffer is current
-    // device scalars: [0]=n_uniq [1]=n_act [2]=img_idx [3]=status ; 64-bit: tested, arena_used
+    int *act[2];                 // active lists (unordered), double buffered
+    int* newlist;                // [MA] current-CC indices of the frame's new uniques (k_match_update -> k_match_copy)
+    uint2* box[2];               // packed bbox of act[i]: .x = min_x | min_y << 16, .y = (max_x | max_y << 16) | 0x80008000
+    int cur;                     // which act / box buffer is current
+    // device scalars: [0]=n_uniq [1]=n_act [2]=img_idx [3]=status [4]=n_pairs [5]=n_items [6]=block ticket
+    //                 [7]=n_act being built [8]=new uniques of the frame ; 64-bit: tested, arena_used
     int* d_scal; unsigned long long* d_scal64;
     // per-frame candidate work lists (reset by k_match_update): scal[4] = n_pairs, scal[5] = n_items
     int MP, MI;                  // capacities
@@ -549,58 +552,115 @@ struct am_estimator {
 // Temporal matching is pair-parallel.  The reference tests a CC's candidates in ascending unique index and stops
 // computing at the first one that passes (cc_stability_estimator.py:90-108) while still COUNTING every candidate
 // (tempo_count, :85).  Equivalent and parallel: compute the overlap of every candidate pair, then take the MINIMUM
-// unique index among the passing ones.  Large overlaps (a board-sized CC) are split into MATCH_CHUNK-word items so
-// that one giant pair does not serialise on a single warp.
+// unique index among the passing ones (so the order of the active list is irrelevant).  Large overlaps (a board-sized
+// CC) are split into MATCH_CHUNK-word items so that one giant pair does not serialise on a single warp.
 //
-// M1a: one warp per current CC: scan the active uniques, append every bbox-overlapping pair (+ its work items)
-__global__ void k_match_pairs(const CcFrame* __restrict__ frames, const int* __restrict__ counts, int f,
-                              const int* __restrict__ act, int* __restrict__ scal,
-                              const int* __restrict__ u_min_x, const int* __restrict__ u_max_x, const int* __restrict__ u_min_y,
-                              const int* __restrict__ u_max_y, int2* __restrict__ pair_cu, int* __restrict__ pair_m,
-                              int2* __restrict__ items, int MP, int MI, unsigned long long* __restrict__ tested_total) {
+// M1a: all-pairs inclusive bbox test (= the two IntervalIndex sweeps + set intersection, interval_index.py:42-99,
+// cc_stability_estimator.py:73-84), tiled: a block tests MP_THREADS current CCs (one per thread) against a tile of
+// MP_TILE active boxes staged in shared memory.  Boxes are packed 2 x 16 bit with a bias bit so that one subtraction
+// compares x and y at once: ((C1 | bias) - lo) has bit 15 / 31 set  <=>  c.max_x >= u.min_x / c.max_y >= u.min_y.
+#define MP_TILE 256
+#define MP_THREADS 256
+#define BOX_BIAS 0x80008000u
+#define MP_QUEUE 2048            // candidate pairs a tile queues in shared memory (the rest appends directly)
+__device__ __forceinline__ void append_pair(int c, int u, int cx0, int cx1, int cy0, int cy1, uint2 b, int* scal, int2* pair_cu,
+                                            int* pair_m, int2* items, int MP, int MI) {
+    const int ux0 = (int)(b.x & 0xFFFFu), uy0 = (int)(b.x >> 16), ux1 = (int)(b.y & 0x7FFFu), uy1 = (int)((b.y >> 16) & 0x7FFFu);
+    const int nw = (min(cx1, ux1) >> 5) - (max(cx0, ux0) >> 5) + 1;
+    const int tot = nw * (min(cy1, uy1) - max(cy0, uy0) + 1);
+    const int n_items = (tot + MATCH_CHUNK - 1) / MATCH_CHUNK;
+    const int pi = atomicAdd(&scal[4], 1);
+    int ii = atomicAdd(&scal[5], n_items);
+    if (pi < MP) {
+        pair_cu[pi] = make_int2(c, u); pair_m[pi] = 0;
+        for (int k = 0; k < n_items; ++k, ++ii)
+            if (ii < MI) items[ii] = make_int2(pi, k);
+    }
+}
+__global__ void __launch_bounds__(MP_THREADS, 4)
+k_match_pairs(const CcFrame* __restrict__ frames, const int* __restrict__ counts, int f, const int* __restrict__ act,
+              const uint2* __restrict__ box, int* __restrict__ scal, int2* __restrict__ pair_cu, int* __restrict__ pair_m,
+              int2* __restrict__ items, int MP, int MI, unsigned long long* __restrict__ tested_total) {
+    __shared__ __align__(16) uint2 s_box[MP_TILE];
+    __shared__ int4 s_cc[MP_THREADS];                    // boxes of the tile's current CCs
+    __shared__ unsigned s_queue[MP_QUEUE];               // (thread << 16) | j
+    __shared__ int s_nq, s_base[2], s_scan[33];
     const CcFrame fr = frames[f];
     const int n_kept = counts[f * 4 + 2];
-    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (c >= n_kept) return;
-    const int lane = threadIdx.x & 31;
-    const int img_idx = scal[2], n_act = scal[1];
-    if (lane == 0) fr.match_unique[c] = MATCH_NONE;
-    if (img_idx == 0) return;                            // frame 0: every CC becomes a unique CC (:52-69)
-    const int l = fr.kept_label[c] - 1;
-    const int cx0 = fr.t_min_x[l], cx1 = fr.t_max_x[l], cy0 = fr.t_min_y[l], cy1 = fr.t_max_y[l];
-    unsigned tested = 0;
-    for (int a0 = 0; a0 < n_act; a0 += 32) {
-        const int u = (a0 + lane < n_act) ? act[a0 + lane] : -1;
-        bool ov = false;
-        int n_items = 0;
-        if (u >= 0) {
-            const int ux0 = u_min_x[u], ux1 = u_max_x[u], uy0 = u_min_y[u], uy1 = u_max_y[u];
-            ov = (cy1 >= uy0 && uy1 >= cy0 && cx1 >= ux0 && ux1 >= cx0);      // inclusive bbox overlap (interval_index.py:42-99)
-            if (ov) {
-                const int nw = (min(cx1, ux1) >> 5) - (max(cx0, ux0) >> 5) + 1;
-                const int tot = nw * (min(cy1, uy1) - max(cy0, uy0) + 1);
-                n_items = (tot + MATCH_CHUNK - 1) / MATCH_CHUNK;
+    const int img_idx = scal[2];
+    const int n_act = (img_idx == 0) ? 0 : scal[1];      // frame 0: every CC becomes a unique CC (:52-69)
+    const int tiles_c = (n_kept + MP_THREADS - 1) / MP_THREADS, tiles_a = max(1, (n_act + MP_TILE - 1) / MP_TILE);
+    const int tid = threadIdx.x;
+    unsigned hits = 0;
+    for (int t = blockIdx.x; t < tiles_c * tiles_a; t += gridDim.x) {
+        const int ci = t % tiles_c, ai = t / tiles_c;
+        const int a0 = ai * MP_TILE, jn = min(MP_TILE, n_act - a0);
+        __syncthreads();
+        if (tid == 0) s_nq = 0;
+        for (int j = tid; j < MP_TILE; j += MP_THREADS)      // padding boxes (min = 32767, max = 0) never overlap
+            s_box[j] = (j < jn) ? box[a0 + j] : make_uint2(0x7FFF7FFFu, BOX_BIAS);
+        const int c = ci * MP_THREADS + tid;
+        int cx0 = 0, cx1 = 0, cy0 = 0, cy1 = 0;
+        if (c < n_kept) {
+            if (ai == 0) fr.match_unique[c] = MATCH_NONE;
+            const int l = fr.kept_label[c] - 1;
+            cx0 = fr.t_min_x[l]; cx1 = fr.t_max_x[l]; cy0 = fr.t_min_y[l]; cy1 = fr.t_max_y[l];
+        }
+        s_cc[tid] = make_int4(cx0, cx1, cy0, cy1);
+        __syncthreads();
+        if (c < n_kept && jn > 0) {
+            const uint32_t C0 = (uint32_t)cx0 | ((uint32_t)cy0 << 16), C1 = ((uint32_t)cx1 | ((uint32_t)cy1 << 16)) | BOX_BIAS;
+            const int jn4 = (jn + 3) & ~3;
+#pragma unroll 2
+            for (int j = 0; j < jn4; j += 4) {               // four boxes per step, branch only on a hit
+                const uint4 b01 = *(const uint4*)&s_box[j], b23 = *(const uint4*)&s_box[j + 2];
+                const uint32_t t0 = (C1 - b01.x) & (b01.y - C0), t1 = (C1 - b01.z) & (b01.w - C0);
+                const uint32_t t2 = (C1 - b23.x) & (b23.y - C0), t3 = (C1 - b23.z) & (b23.w - C0);
+                unsigned m = ((t0 & BOX_BIAS) == BOX_BIAS ? 1u : 0u) | ((t1 & BOX_BIAS) == BOX_BIAS ? 2u : 0u) |
+                             ((t2 & BOX_BIAS) == BOX_BIAS ? 4u : 0u) | ((t3 & BOX_BIAS) == BOX_BIAS ? 8u : 0u);
+                while (m) {
+                    const int jj = j + __ffs(m) - 1; m &= m - 1;
+                    ++hits;
+                    const int q = atomicAdd(&s_nq, 1);
+                    if (q < MP_QUEUE) s_queue[q] = ((unsigned)tid << 16) | (unsigned)jj;
+                    else append_pair(c, act[a0 + jj], cx0, cx1, cy0, cy1, s_box[jj], scal, pair_cu, pair_m, items, MP, MI);
+                }
             }
         }
-        const unsigned bal = __ballot_sync(0xffffffffu, ov);
-        if (bal == 0) continue;
-        tested += __popc(bal);
-        const int my_items_incl = warp_incl_scan(n_items);
-        const int tot_items = __shfl_sync(0xffffffffu, my_items_incl, 31);
-        int pbase = 0, ibase = 0;
-        if (lane == 0) { pbase = atomicAdd(&scal[4], __popc(bal)); ibase = atomicAdd(&scal[5], tot_items); }
-        pbase = __shfl_sync(0xffffffffu, pbase, 0); ibase = __shfl_sync(0xffffffffu, ibase, 0);
-        if (ov) {
-            const int pi = pbase + __popc(bal & ((1u << lane) - 1u));
-            if (pi < MP) {
-                pair_cu[pi] = make_int2(c, u); pair_m[pi] = 0;
-                int ii = ibase + my_items_incl - n_items;
-                for (int k = 0; k < n_items; ++k, ++ii)
-                    if (ii < MI) items[ii] = make_int2(pi, k);
+        __syncthreads();
+        // queued candidates: one reservation of pair / item slots per round of MP_THREADS entries (the two list
+        // counters are single addresses: per-candidate atomics would serialise in L2)
+        const int nq = min(s_nq, MP_QUEUE);
+        for (int q0 = 0; q0 < nq; q0 += MP_THREADS) {
+            const int q = q0 + tid;
+            int n_items = 0, cc_i = 0, u = 0;
+            if (q < nq) {
+                const unsigned e = s_queue[q];
+                const int ct = (int)(e >> 16), j = (int)(e & 0xFFFFu);
+                const int4 cc = s_cc[ct];
+                const uint2 b = s_box[j];
+                const int ux0 = (int)(b.x & 0xFFFFu), uy0 = (int)(b.x >> 16), ux1 = (int)(b.y & 0x7FFFu), uy1 = (int)((b.y >> 16) & 0x7FFFu);
+                const int nw = (min(cc.y, ux1) >> 5) - (max(cc.x, ux0) >> 5) + 1;
+                n_items = (nw * (min(cc.w, uy1) - max(cc.z, uy0) + 1) + MATCH_CHUNK - 1) / MATCH_CHUNK;
+                cc_i = ci * MP_THREADS + ct; u = act[a0 + j];
+            }
+            int tot;
+            const int ex = block_excl_scan(n_items, s_scan, &tot);
+            if (tid == 0) { s_base[0] = atomicAdd(&scal[4], min(MP_THREADS, nq - q0)); s_base[1] = atomicAdd(&scal[5], tot); }
+            __syncthreads();
+            if (q < nq) {
+                const int pi = s_base[0] + tid;
+                int ii = s_base[1] + ex;
+                if (pi < MP) {
+                    pair_cu[pi] = make_int2(cc_i, u); pair_m[pi] = 0;
+                    for (int k = 0; k < n_items; ++k, ++ii)
+                        if (ii < MI) items[ii] = make_int2(pi, k);
+                }
             }
         }
     }
-    if (lane == 0 && tested) atomicAdd(tested_total, (unsigned long long)tested);
+    hits = __reduce_add_sync(0xffffffffu, hits);
+    if ((tid & 31) == 0 && hits) atomicAdd(tested_total, (unsigned long long)hits);
 }
 
 // M1b: persistent warps over the work items: popcount(cc.mask & unique.mask) on the bit-packed crops, which sit at
@@ -658,90 +718,130 @@ __global__ void k_match_select(const CcFrame* __restrict__ frames, int f, const 
     }
 }
 
-// M2: one block: number the new uniques (ascending current order), copy their crops, expire, append
-__global__ void k_match_update(const CcFrame* __restrict__ frames, const int* __restrict__ counts, int f,
-                               const int* __restrict__ act_in, int* __restrict__ act_out, int* __restrict__ scal,
-                               unsigned long long* __restrict__ scal64,
-                               int* u_min_x, int* u_max_x, int* u_min_y, int* u_max_y, int* u_size, int* u_last,
-                               int* u_first_frame, int* u_first_label, unsigned long long* u_crop_off, uint32_t* arena,
-                               int MU, int MA, unsigned long long AW, int max_gap, int MP, int MI) {
-    __shared__ int sm[33];
-    __shared__ unsigned long long s_arena;
+// M2a: matched CCs refresh their unique's last-seen frame (:104) -- must be complete before the expiry pass reads it
+__global__ void k_match_refresh(const CcFrame* __restrict__ frames, const int* __restrict__ counts, int f, const int* __restrict__ scal,
+                                int* __restrict__ u_last) {
     const CcFrame fr = frames[f];
-    const int n_kept = counts[f * 4 + 2];
-    const int img_idx = scal[2], n_uniq0 = scal[0], n_act0 = scal[1];
-    if (threadIdx.x == 0) {
-        s_arena = scal64[1];
-        if (scal[4] > MP || scal[5] > MI) atomicOr(&scal[3], 16);       // candidate work lists overflowed
-    }
-    // 0. matched CCs refresh their unique's last-seen frame (:104) before the expiry pass reads it
-    for (int c = threadIdx.x; c < n_kept; c += blockDim.x) {
+    const int n_kept = counts[f * 4 + 2], img_idx = scal[2];
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n_kept; c += gridDim.x * blockDim.x) {
         const int u = fr.match_unique[c];
         if (u != MATCH_NONE) u_last[u] = img_idx;
     }
-    __syncthreads();
-    // 1. expiry of the previously active uniques (:127-145; not on frame 0) -> act_out[0..keep)
-    int kept_act = 0;
-    for (int i0 = 0; i0 < n_act0; i0 += blockDim.x) {
-        int i = i0 + threadIdx.x;
-        int u = (i < n_act0) ? act_in[i] : -1;
-        int keep = (u >= 0) && (img_idx == 0 || img_idx - u_last[u] < max_gap);
-        int tot;
-        int ex = block_excl_scan(keep, sm, &tot);
-        __syncthreads();
-        if (keep) act_out[kept_act + ex] = u;
-        kept_act += tot;
-    }
-    // 2. new uniques (:111-124)
-    int n_new = 0;
+}
+
+__device__ __forceinline__ uint2 pack_box(int x0, int x1, int y0, int y1) {
+    return make_uint2((uint32_t)x0 | ((uint32_t)y0 << 16), ((uint32_t)x1 | ((uint32_t)y1 << 16)) | BOX_BIAS);
+}
+
+// M2b: block 0 numbers the new uniques in ascending current-CC order (:111-124), creates them and copies their crops
+// into the arena (first-seen instance, never updated); the other blocks run the expiry pass (:127-145; not on frame 0)
+// as an unordered compaction of the active list.  The last block out publishes the scalars of the next frame.
+#define MU_THREADS 1024
+#define MU_ITEMS 8
+__global__ void __launch_bounds__(MU_THREADS)
+k_match_update(const CcFrame* __restrict__ frames, const int* __restrict__ counts, int f,
+               const int* __restrict__ act_in, const uint2* __restrict__ box_in, int* __restrict__ act_out, uint2* __restrict__ box_out,
+               int* __restrict__ scal, unsigned long long* __restrict__ scal64,
+               int* u_min_x, int* u_max_x, int* u_min_y, int* u_max_y, int* u_size, int* u_last,
+               int* u_first_frame, int* u_first_label, unsigned long long* u_crop_off, int* __restrict__ newlist,
+               int MU, int MA, unsigned long long AW, int max_gap, int MP, int MI) {
+    __shared__ int sm[33];
+    const CcFrame fr = frames[f];
+    const int n_kept = counts[f * 4 + 2];
+    const int img_idx = scal[2], n_uniq0 = scal[0], n_act0 = scal[1];
+    const int tid = threadIdx.x;
     bool over = false;
-    for (int c0 = 0; c0 < n_kept; c0 += blockDim.x) {
-        int c = c0 + threadIdx.x;
-        int isnew = (c < n_kept) && (fr.match_unique[c] == MATCH_NONE);
-        int words = 0, l = 0;
-        if (isnew) {
-            l = fr.kept_label[c] - 1;
-            words = ((fr.t_max_x[l] >> 5) - (fr.t_min_x[l] >> 5) + 1) * (fr.t_max_y[l] - fr.t_min_y[l] + 1);
+    if (blockIdx.x == 0) {
+        // every thread owns MU_ITEMS consecutive current CCs per round: all their loads are in flight together and
+        // one block scan per round ranks the new ones in ascending order
+        int n_new = 0;
+        for (int c0 = 0; c0 < n_kept; c0 += MU_THREADS * MU_ITEMS) {
+            const int cb = c0 + tid * MU_ITEMS;
+            unsigned newmask = 0;
+#pragma unroll
+            for (int k = 0; k < MU_ITEMS; ++k)
+                if (cb + k < n_kept && fr.match_unique[cb + k] == MATCH_NONE) newmask |= 1u << k;
+            int tot;
+            int rank = n_new + block_excl_scan(__popc(newmask), sm, &tot);
+            while (newmask) {
+                const int k = __ffs(newmask) - 1; newmask &= newmask - 1;
+                const int c = cb + k;
+                const int l = fr.kept_label[c] - 1;
+                const int x0 = fr.t_min_x[l], x1 = fr.t_max_x[l], y0 = fr.t_min_y[l], y1 = fr.t_max_y[l];
+                const int words = ((x1 >> 5) - (x0 >> 5) + 1) * (y1 - y0 + 1);
+                const int u = n_uniq0 + rank;
+                const int ai = atomicAdd(&scal[7], 1);
+                const unsigned long long off = atomicAdd(&scal64[1], (unsigned long long)words);
+                if (u < MU && ai < MA && off + words <= AW) {
+                    u_min_x[u] = x0; u_max_x[u] = x1; u_min_y[u] = y0; u_max_y[u] = y1;
+                    u_size[u] = fr.t_count[l]; u_last[u] = img_idx; u_first_frame[u] = img_idx; u_first_label[u] = l + 1;
+                    u_crop_off[u] = off;
+                    act_out[ai] = u; box_out[ai] = pack_box(x0, x1, y0, y1);
+                    fr.match_unique[c] = u;
+                    newlist[rank] = c;
+                } else { over = true; if (rank < MA) newlist[rank] = -1; }
+                ++rank;
+            }
+            n_new += tot;
         }
-        int tot, wtot;
-        int ex = block_excl_scan(isnew, sm, &tot);
-        int wex = block_excl_scan(words, sm, &wtot);
-        __syncthreads();
-        if (isnew) {
-            int u = n_uniq0 + n_new + ex;
-            int ai = kept_act + n_new + ex;
-            unsigned long long off = s_arena + (unsigned long long)wex;
-            if (u < MU && ai < MA && off + words <= AW) {
-                u_min_x[u] = fr.t_min_x[l]; u_max_x[u] = fr.t_max_x[l]; u_min_y[u] = fr.t_min_y[l]; u_max_y[u] = fr.t_max_y[l];
-                u_size[u] = fr.t_count[l]; u_last[u] = img_idx; u_first_frame[u] = img_idx; u_first_label[u] = l + 1;
-                u_crop_off[u] = off;
-                act_out[ai] = u;
-                fr.match_unique[c] = u;
-            } else over = true;
+        if (tid == 0) {
+            scal[8] = n_new; scal[9] = min(n_new, MA);                   // [9]: crop copies for k_match_copy
+            if (scal[4] > MP || scal[5] > MI) atomicOr(&scal[3], 16);     // candidate work lists overflowed
         }
-        __syncthreads();
-        n_new += tot;
-        if (threadIdx.x == 0) s_arena += (unsigned long long)wtot;
-        __syncthreads();
+    } else {
+        const int lane = tid & 31;
+        for (int i0 = (blockIdx.x - 1) * MU_THREADS; i0 < n_act0; i0 += (gridDim.x - 1) * MU_THREADS) {
+            const int i = i0 + tid;
+            const int u = (i < n_act0) ? act_in[i] : -1;
+            const bool keep = (u >= 0) && (img_idx == 0 || img_idx - u_last[u] < max_gap);
+            const unsigned bal = __ballot_sync(0xffffffffu, keep);
+            if (bal == 0) continue;
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&scal[7], __popc(bal));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (keep) {
+                const int ai = base + __popc(bal & ((1u << lane) - 1u));
+                if (ai < MA) { act_out[ai] = u; box_out[ai] = box_in[i]; } else over = true;
+            }
+        }
     }
-    // 3. copy the crops of the new uniques into the arena (first-seen instance, never updated): warp per CC
-    for (int c = threadIdx.x >> 5; c < n_kept; c += (blockDim.x >> 5)) {
-        int u = fr.match_unique[c];
-        if (u < n_uniq0 || u >= MU) continue;
-        int l = fr.kept_label[c] - 1;
-        int words = ((fr.t_max_x[l] >> 5) - (fr.t_min_x[l] >> 5) + 1) * (fr.t_max_y[l] - fr.t_min_y[l] + 1);
+    if (__syncthreads_or(over) && tid == 0) atomicOr(&scal[3], 8);
+    if (tid == 0) {
+        __threadfence();
+        if (atomicAdd(&scal[6], 1) == (int)gridDim.x - 1) {              // last block out
+            __threadfence();
+            const int n_new = ((volatile int*)scal)[8], n_act = ((volatile int*)scal)[7];
+            scal[0] = min(n_uniq0 + n_new, MU);
+            scal[1] = min(n_act, MA);
+            scal[2] = img_idx + 1;
+            scal[4] = 0; scal[5] = 0; scal[6] = 0; scal[7] = 0; scal[8] = 0;   // empty work lists for the next frame
+        }
+    }
+}
+
+// M2c: the crops of the new uniques go into the arena (first-seen instance, never updated): warp per new unique
+__global__ void k_match_copy(const CcFrame* __restrict__ frames, int f, const int* __restrict__ scal, const int* __restrict__ newlist,
+                             const unsigned long long* __restrict__ u_crop_off, uint32_t* __restrict__ arena) {
+    const CcFrame fr = frames[f];
+    const int n = scal[9], lane = threadIdx.x & 31;
+    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += (gridDim.x * blockDim.x) >> 5) {
+        const int c = newlist[i];
+        if (c < 0) continue;
+        const int l = fr.kept_label[c] - 1;
+        const int words = ((fr.t_max_x[l] >> 5) - (fr.t_min_x[l] >> 5) + 1) * (fr.t_max_y[l] - fr.t_min_y[l] + 1);
         const uint32_t* src = fr.crops + fr.kept_crop_off[c];
-        uint32_t* dst = arena + u_crop_off[u];
-        for (int i = threadIdx.x & 31; i < words; i += 32) dst[i] = src[i];
+        uint32_t* dst = arena + u_crop_off[fr.match_unique[c]];
+        for (int k = lane; k < words; k += 32) dst[k] = src[k];
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        if (over) atomicOr(&scal[3], 8);
-        scal[0] = min(n_uniq0 + n_new, MU);
-        scal[1] = min(kept_act + n_new, MA);
-        scal[2] = img_idx + 1;
-        scal[4] = 0; scal[5] = 0;                        // empty work lists for the next frame
-        scal64[1] = s_arena;
+}
+
+// packed boxes of the current active list (after an import)
+__global__ void k_rebuild_boxes(const int* __restrict__ act, const int* __restrict__ scal, const int* u_min_x, const int* u_max_x,
+                                const int* u_min_y, const int* u_max_y, uint2* __restrict__ box) {
+    const int n = scal[1];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int u = act[i];
+        box[i] = pack_box(u_min_x[u], u_max_x[u], u_min_y[u], u_max_y[u]);
     }
 }
 
@@ -1152,7 +1252,7 @@ extern "C" int CC_AgeBoundaries(int* labels, float* ages, int width, int height,
 // ---- estimator ------------------------------------------------------------------------------
 extern "C" am_estimator* am_est_create(int width, int height, double min_recall, double min_precision, int max_gap,
                                        int max_uniques, int max_active, long long arena_words) {
-    if (width <= 0 || height <= 0) return nullptr;
+    if (width <= 0 || height <= 0 || width > 32767 || height > 32767) return nullptr;      // packed 15-bit boxes
     am_estimator* e = new am_estimator();
     e->W = width; e->H = height; e->max_gap = max_gap; e->min_recall = min_recall; e->min_precision = min_precision;
     e->MU = max_uniques > 0 ? max_uniques : (1 << 20);
@@ -1164,6 +1264,7 @@ extern "C" am_estimator* am_est_create(int width, int height, double min_recall,
     size_t o_i[8]; for (int i = 0; i < 8; ++i) o_i[i] = add((size_t)e->MU * 4);
     size_t o_off = add((size_t)e->MU * 8);
     size_t o_a0 = add((size_t)e->MA * 4), o_a1 = add((size_t)e->MA * 4);
+    size_t o_b0 = add((size_t)e->MA * 8), o_b1 = add((size_t)e->MA * 8), o_nl = add((size_t)e->MA * 4);
     size_t o_tmp = add((size_t)e->MA * 8);
     size_t o_sc = add(64), o_sc64 = add(64);
     e->MP = 1 << 20; e->MI = 1 << 21;
@@ -1178,6 +1279,7 @@ extern "C" am_estimator* am_est_create(int width, int height, double min_recall,
     e->u_size = (int*)(b + o_i[4]); e->u_last = (int*)(b + o_i[5]); e->u_first_frame = (int*)(b + o_i[6]); e->u_first_label = (int*)(b + o_i[7]);
     e->u_crop_off = (unsigned long long*)(b + o_off);
     e->act[0] = (int*)(b + o_a0); e->act[1] = (int*)(b + o_a1); e->cur = 0;
+    e->box[0] = (uint2*)(b + o_b0); e->box[1] = (uint2*)(b + o_b1); e->newlist = (int*)(b + o_nl);
     e->d_scal = (int*)(b + o_sc); e->d_scal64 = (unsigned long long*)(b + o_sc64);
     e->arena = (uint32_t*)(b + o_ar);
     e->pair_cu = (int2*)(b + o_pcu); e->pair_m = (int*)(b + o_pm); e->items = (int2*)(b + o_it);
@@ -1197,14 +1299,17 @@ extern "C" int am_est_add_frames(am_estimator* e, am_cc_ctx* c, int first, int n
     cudaStream_t st = S(stream);
     for (int f = first; f < first + n; ++f) {
         int* a_in = e->act[e->cur]; int* a_out = e->act[e->cur ^ 1];
-        k_match_pairs<<<am_div_up(c->MK, 8), 256, 0, st>>>(c->d_frames, c->d_counts, f, a_in, e->d_scal, e->u_min_x, e->u_max_x, e->u_min_y,
-                                                         e->u_max_y, e->pair_cu, e->pair_m, e->items, e->MP, e->MI, e->d_scal64);
+        uint2* b_in = e->box[e->cur]; uint2* b_out = e->box[e->cur ^ 1];
+        k_match_pairs<<<148 * 4, MP_THREADS, 0, st>>>(c->d_frames, c->d_counts, f, a_in, b_in, e->d_scal, e->pair_cu, e->pair_m, e->items,
+                                                    e->MP, e->MI, e->d_scal64);
         k_match_overlap<<<148 * 4, 256, 0, st>>>(c->d_frames, f, e->d_scal, e->u_min_x, e->u_max_x, e->u_min_y, e->u_max_y, e->u_crop_off,
                                                  e->arena, e->pair_cu, e->pair_m, e->items, e->MP, e->MI);
         k_match_select<<<148, 256, 0, st>>>(c->d_frames, f, e->d_scal, e->u_size, e->pair_cu, e->pair_m, e->MP, e->min_recall, e->min_precision);
-        k_match_update<<<1, 1024, 0, st>>>(c->d_frames, c->d_counts, f, a_in, a_out, e->d_scal, e->d_scal64, e->u_min_x, e->u_max_x,
-                                           e->u_min_y, e->u_max_y, e->u_size, e->u_last, e->u_first_frame, e->u_first_label,
-                                           e->u_crop_off, e->arena, e->MU, e->MA, e->AW, e->max_gap, e->MP, e->MI);
+        k_match_refresh<<<32, 256, 0, st>>>(c->d_frames, c->d_counts, f, e->d_scal, e->u_last);
+        k_match_update<<<1 + 32, MU_THREADS, 0, st>>>(c->d_frames, c->d_counts, f, a_in, b_in, a_out, b_out, e->d_scal, e->d_scal64,
+                                                     e->u_min_x, e->u_max_x, e->u_min_y, e->u_max_y, e->u_size, e->u_last, e->u_first_frame,
+                                                     e->u_first_label, e->u_crop_off, e->newlist, e->MU, e->MA, e->AW, e->max_gap, e->MP, e->MI);
+        k_match_copy<<<64, 256, 0, st>>>(c->d_frames, f, e->d_scal, e->newlist, e->u_crop_off, e->arena);
         e->cur ^= 1;
     }
     AM_CUDA(cudaGetLastError());
@@ -1280,6 +1385,7 @@ extern "C" int am_est_import(am_estimator* e, int n_active, int n_unique, int im
     unsigned long long sc64[2] = {tempo_count, (unsigned long long)crop_words};
     AM_CUDA(cudaMemcpyAsync(e->d_scal, sc, 16, cudaMemcpyHostToDevice, S(stream)));
     AM_CUDA(cudaMemcpyAsync(e->d_scal64, sc64, 16, cudaMemcpyHostToDevice, S(stream)));
+    k_rebuild_boxes<<<64, 256, 0, S(stream)>>>(e->act[e->cur], e->d_scal, e->u_min_x, e->u_max_x, e->u_min_y, e->u_max_y, e->box[e->cur]);
     AM_CUDA(cudaStreamSynchronize(S(stream)));
     return AM_OK;
 }
@@ -1299,6 +1405,7 @@ extern "C" int am_est_import_dev(am_estimator* e, const int* d_buf, void* stream
     k_import_dev_meta<<<1, 1024, 0, S(stream)>>>(d_buf, e->act[e->cur], e->d_scal, e->d_scal64, e->u_min_x, e->u_max_x, e->u_min_y, e->u_max_y,
                                                  e->u_size, e->u_last, e->u_first_frame, e->u_first_label, e->u_crop_off, e->MU, e->MA, e->AW);
     k_import_dev_crops<<<148, 256, 0, S(stream)>>>(d_buf, e->arena, e->AW);
+    k_rebuild_boxes<<<64, 256, 0, S(stream)>>>(e->act[e->cur], e->d_scal, e->u_min_x, e->u_max_x, e->u_min_y, e->u_max_y, e->box[e->cur]);
     AM_CUDA(cudaGetLastError());
     return AM_OK;
 }
