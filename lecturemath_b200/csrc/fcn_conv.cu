@@ -311,11 +311,15 @@ __device__ __forceinline__ void epi_unit(const ConvParams& p, const uint32_t (&v
             if (ok[1]) *(uint4*)(o + offs[1]) = pk[1];
         }
     } else if (f32fast) {
-        // fp32 heads / logits: the row's N columns are contiguous in memory (n = sx*Cout + co)
-        float* o = (float*)p.out + base + n0 + j0;
+        // fp32 heads / logits: the N columns of one output row are contiguous in memory (n = sx*Cout + co); with 2-D packing
+        // the second half of the columns is the next image row (a 16-column unit never straddles: Sx*Cout % 16 == 0)
+        const int n = n0 + j0, half = p.Sx * p.Cout;
+        const int sy = (p.Sy == 2 && n >= half) ? 1 : 0;
+        if (sy != 0 && !sy1_ok) return;
+        float* o = (float*)p.out + base + (long long)sy * p.out_sy + (n - sy * half);
 #pragma unroll
         for (int i = 0; i < 16; i += 4) {
-            if (n0 + j0 + i >= p.Ntot) break;
+            if (n + i >= p.Ntot) break;
             float4 f;
             f.x = __uint_as_float(v[i]) + sbias[j0 + i]; f.y = __uint_as_float(v[i + 1]) + sbias[j0 + i + 1];
             f.z = __uint_as_float(v[i + 2]) + sbias[j0 + i + 2]; f.w = __uint_as_float(v[i + 3]) + sbias[j0 + i + 3];
@@ -529,7 +533,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv_gemm(const __grid_cons
         const bool vec8 = (p.Cout & 7) == 0 && !p.out_f32;
         // 16-byte alignment of every address the fast path forms (8-element granularity of base and strides)
         const bool vec16 = (p.Cout & 15) == 0 && !p.out_f32 && ((p.out_coff | p.out_sx | (int)(p.out_sy & 7) | (int)(p.out_sn & 7)) & 7) == 0;
-        const bool f32fast = p.out_f32 && p.out_sx == p.Cout && p.Sy == 1 && p.out_coff == 0 && ((p.Ntot | (int)p.out_sy | (int)p.out_sn) & 3) == 0;
+        const bool f32fast = p.out_f32 && p.out_sx == p.Cout && (p.Sy == 1 || ((p.Sx * p.Cout) & 15) == 0) && p.out_coff == 0 &&
+                             ((p.Ntot | (int)p.out_sy | (int)p.out_sn) & 3) == 0;
         int slot = 0; uint32_t ps = 0;
         while (true) {
             const int w = sched_next(schedFull, schedEmpty, sched_w, slot, ps, lane);

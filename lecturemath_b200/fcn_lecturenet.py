@@ -315,7 +315,7 @@ class FCNPlan:
         o = (pk - k) // 2
         wh[1:4, :, o:o + k, o:o + k] = wr_
         f0 = self.flops
-        self._conv(wh, torch.cat([bt_, br_]), [(self.u[0], ident(upc[0]))], None, act=0, cap=8, f32_out=self.heads)
+        self._conv(wh, torch.cat([bt_, br_]), [(self.u[0], ident(upc[0]))], None, act=0, cap=16, f32_out=self.heads)
         self.flops = f0 + 2 * H * W * upc[0] * (pk * pk + 3 * k * k)     # algorithmic: 7x7x1 + 3x3x3, not the padded GEMM
         self.op_flops[len(self.ops) - 1] = self.flops - f0
         self.ops.append(("heads_post", None))
@@ -325,7 +325,7 @@ class FCNPlan:
         w, b = cbn("conv_pixels_2")
         self._conv(w, b, [(self.px1, [3 + c for c in range(pm1)]), (self.diff, dmap)], self.px2, act=1)
         w, b = cbn("conv_out")
-        self._conv(w, b, [(self.px2, [3 + c for c in range(pm2)]), (self.diff, dmap)], None, act=0, cap=32, f32_out=self.logits)
+        self._conv(w, b, [(self.px2, [3 + c for c in range(pm2)]), (self.diff, dmap)], None, act=0, cap=64, f32_out=self.logits)
         self.ops.append(("threshold", None))
 
     @staticmethod
@@ -372,7 +372,7 @@ class FCNPlan:
         nrows, cin_total, KH, KW = w.shape
         first = srcs[0][0]
         Hin, Win = first.H, first.W
-        S, Sy, NT, MT = self._pick_config(Win, Hin, nrows, [buf.C for buf, _ in srcs], KW, KH, cap, allow_sy=f32_out is None)
+        S, Sy, NT, MT = self._pick_config(Win, Hin, nrows, [buf.C for buf, _ in srcs], KW, KH, cap)
         packed, bias, ntot, ntot_pad = pack_weights(w, b, [(buf.C, cmap) for buf, cmap in srcs], S, self.rowrun, NT, Sy)
         Himg, KHc = Hin, KH
         Hin, KH = (Himg + Sy - 1) // Sy, KHc + Sy - 1          # GEMM row units per frame column, Toeplitz-extended vertical taps
