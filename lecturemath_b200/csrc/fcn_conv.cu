@@ -362,8 +362,13 @@ __device__ __forceinline__ int sched_next(uint32_t schedFull, uint32_t schedEmpt
 }
 
 // kMT = M-tiles per work item, kRES = weights resident in shared memory (compile-time so the single-warp issue loops stay short)
+// kMT = 4 (four issuer warps, warps 1..4) takes the epilogue down to 12 warps (8..19) so that the CTA stays at 640 threads
+// (96 registers each: 20 warps is what the register file holds).
 template <int kMT, bool kRES>
 __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv_gemm(const __grid_constant__ ConvParams p) {
+    constexpr int kEpiFirst = (kMT == 4) ? 8 : 4;                      // first epilogue warp (multiple of 4: TMEM lane quarters)
+    constexpr int kEpiWarps = (CONV_THREADS / 32) - kEpiFirst;
+    constexpr int kEpiPerQ = kEpiWarps / 4;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve: [A ring][B ring | resident B][bias][barriers][tmem ptr]
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -388,8 +393,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv_gemm(const __grid_cons
         // every MMA issuer (one per M-tile) commits to the empty / accumulator-full barriers
         for (int i = 0; i < p.stagesA; ++i) { mbar_init(fullA + 8 * i, 1); mbar_init(emptyA + 8 * i, kMT); }
         for (int i = 0; i < p.stagesB; ++i) { mbar_init(fullB + 8 * i, 1); mbar_init(emptyB + 8 * i, kMT); }
-        for (int i = 0; i < 2; ++i) { mbar_init(accFull + 8 * i, kMT); mbar_init(accEmpty + 8 * i, EPI_WARPS); }
-        for (int i = 0; i < SCHED_DEPTH; ++i) { mbar_init(schedFull + 8 * i, 1); mbar_init(schedEmpty + 8 * i, kMT + EPI_WARPS); }
+        for (int i = 0; i < 2; ++i) { mbar_init(accFull + 8 * i, kMT); mbar_init(accEmpty + 8 * i, kEpiWarps); }
+        for (int i = 0; i < SCHED_DEPTH; ++i) { mbar_init(schedFull + 8 * i, 1); mbar_init(schedEmpty + 8 * i, kMT + kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         tma_prefetch_desc(&p.tmA[0]);
         if (p.nseg > 1) tma_prefetch_desc(&p.tmA[1]);
@@ -430,8 +435,9 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv_gemm(const __grid_cons
             w_next = sched_fetch(p.work_counter, lane);                  // latency hidden behind this item's loads
             const int st = w / p.nNB, nb = w - st * p.nNB;
             const int n0 = nb * p.NT;
-            const TileCoord tc0 = decode_tile(p, st * kMT);
-            const TileCoord tc1 = decode_tile(p, st * kMT + (kMT - 1));
+            TileCoord tcs[kMT];
+#pragma unroll
+            for (int i = 0; i < kMT; ++i) tcs[i] = decode_tile(p, st * kMT + i);
             int chunk = 0;
             for (int s = 0; s < p.nseg; ++s) {
                 const CUtensorMap* tm = &p.tmA[s];
@@ -442,8 +448,9 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv_gemm(const __grid_cons
                         if (elect_one()) {
                             const uint32_t dst = sA0 + bytesA * sa, bar = fullA + 8 * sa;
                             mbar_expect_tx(bar, bytesA);
-                            tma_load_4d(dst, tm, bar, ck * 64, tc0.r0 + c1, tc0.y0 * p.ystep - p.padY, tc0.frame);
-                            if (kMT == 2) tma_load_4d(dst + bytesA1, tm, bar, ck * 64, tc1.r0 + c1, tc1.y0 * p.ystep - p.padY, tc1.frame);
+#pragma unroll
+                            for (int i = 0; i < kMT; ++i)
+                                tma_load_4d(dst + bytesA1 * i, tm, bar, ck * 64, tcs[i].r0 + c1, tcs[i].y0 * p.ystep - p.padY, tcs[i].frame);
                         }
                         __syncwarp();
                         if (++sa == p.stagesA) { sa = 0; pa ^= 1; }
@@ -462,7 +469,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv_gemm(const __grid_cons
                 }
             }
         }
-    } else if (warp == 1 || (warp == 2 && kMT == 2)) {
+    } else if (warp >= 1 && warp <= kMT) {
         // ===================== MMA issuer of M-tile `mt` (warp-uniform, elected lane issues) =====================
         // Everything the loop needs is hoisted into (uniform) registers: an issuing warp is latency bound, so each
         // extra instruction per tcgen05.mma shows up directly when N is small (one MMA = N/2 tensor cycles).
@@ -516,12 +523,12 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv_gemm(const __grid_cons
             __syncwarp();
             if (++as == acc_stages) { as = 0; pacc ^= 1; }
         }
-    } else if (warp < 4) {
-        // idle warps (2 when kMT == 1, 3 always)
+    } else if (warp < kEpiFirst) {
+        // idle warps
     } else {
         // ===================== epilogue (warps 4..) =====================
         const int q = warp & 3;                          // TMEM lane quarter this warp may access
-        const int h = (warp - 4) >> 2;                   // which share of the 16-column groups (0 .. EPI_PER_Q-1)
+        const int h = (warp - kEpiFirst) >> 2;           // which share of the 16-column groups (0 .. kEpiPerQ-1)
         const int m = q * 32 + lane;
         const int yy = m >> p.logRT, rr = m & (p.RT - 1);
         // bias of this CTA's N block -> smem (reloaded per work item only when there are several N blocks)
@@ -542,9 +549,9 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv_gemm(const __grid_cons
             const int st = w / p.nNB, nb = w - st * p.nNB;
             const int n0 = nb * p.NT;
             if (nb != bias_nb) {
-                asm volatile("bar.sync 1, %0;" ::"r"(EPI_WARPS * 32));     // everyone finished reading the previous bias
-                for (int i = threadIdx.x - 128; i < p.NT; i += EPI_WARPS * 32) sbias[i] = __ldg(p.bias + n0 + i);
-                asm volatile("bar.sync 1, %0;" ::"r"(EPI_WARPS * 32));
+                asm volatile("bar.sync 1, %0;" ::"r"(kEpiWarps * 32));     // everyone finished reading the previous bias
+                for (int i = threadIdx.x - kEpiFirst * 32; i < p.NT; i += kEpiWarps * 32) sbias[i] = __ldg(p.bias + n0 + i);
+                asm volatile("bar.sync 1, %0;" ::"r"(kEpiWarps * 32));
                 bias_nb = nb;
             }
             mbar_wait(accFull + 8 * as, pacc);
@@ -556,12 +563,17 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv_gemm(const __grid_cons
             int cur_mt = -1;
             bool row_ok = false, sy1_ok = true;
             long long base = 0;
+            auto tile_of = [&](int g) -> int {               // M-tile of unit g (units are laid out tile after tile)
+                if (kMT == 1) return 0;
+                if (kMT == 2) return g >= units_per_tile ? 1 : 0;
+                return g / units_per_tile;
+            };
             auto unit_addr = [&](int g) -> uint32_t {
-                const int mt = g >= units_per_tile ? 1 : 0;
+                const int mt = tile_of(g);
                 return tacc + (uint32_t)(mt * p.NTc + (g - mt * units_per_tile) * 16);
             };
             auto enter = [&](int g) -> int {                 // (re)compute the row's output base when the M-tile changes; returns j0
-                const int mt = g >= units_per_tile ? 1 : 0;
+                const int mt = tile_of(g);
                 if (mt != cur_mt) {
                     cur_mt = mt;
                     const TileCoord tc = decode_tile(p, st * kMT + mt);
@@ -577,13 +589,13 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv_gemm(const __grid_cons
             if (g < units) tmem_ld16_async(unit_addr(g), va);
             while (g < units) {
                 tmem_wait16(va);
-                int g2 = g + EPI_PER_Q;
+                int g2 = g + kEpiPerQ;
                 if (g2 < units) tmem_ld16_async(unit_addr(g2), vb);
                 { const int j0 = enter(g); if (row_ok) epi_unit(p, va, sbias, n0, j0, base, vec16, vec8, f32fast, sy1_ok); }
                 g = g2;
                 if (g >= units) break;
                 tmem_wait16(vb);
-                g2 = g + EPI_PER_Q;
+                g2 = g + kEpiPerQ;
                 if (g2 < units) tmem_ld16_async(unit_addr(g2), va);
                 { const int j0 = enter(g); if (row_ok) epi_unit(p, vb, sbias, n0, j0, base, vec16, vec8, f32fast, sy1_ok); }
                 g = g2;
@@ -729,7 +741,9 @@ static int conv_prepare(const am_conv_desc* d, am_conv_plan* plan) {
     const bool res2 = can_res && fixed + allB + 2 * 2 * bytesA1 <= budget;
     const bool res1 = can_res && fixed + allB + 3 * bytesA1 <= budget;
     int resident, MT;
-    if ((d->flags & AM_CONV_FORCE_MT2) && tmem2) { MT = 2; resident = res2 ? 1 : 0; }         // the planner decided
+    const bool res4 = can_res && fixed + allB + 2 * 4 * bytesA1 <= budget;
+    if ((d->flags & AM_CONV_FORCE_MT4) && 4 * p.NTc <= 512) { MT = 4; resident = res4 ? 1 : 0; }  // the planner decided
+    else if ((d->flags & AM_CONV_FORCE_MT2) && tmem2) { MT = 2; resident = res2 ? 1 : 0; }
     else if (d->flags & AM_CONV_NO_MT2) { MT = 1; resident = res1 ? 1 : 0; }
     else if (res2 && many) { resident = 1; MT = 2; }
     else if (res1 && (d->NT >= 128 || !many)) { resident = 1; MT = 1; }
@@ -737,7 +751,7 @@ static int conv_prepare(const am_conv_desc* d, am_conv_plan* plan) {
     else { resident = res1 ? 1 : 0; MT = 1; }
     int sa, sb;
     if (resident) {
-        sb = 1; sa = MT == 2 ? 2 : 3;
+        sb = 1; sa = MT >= 2 ? 2 : 3;
         while (sa < 8 && fixed + allB + (size_t)(sa + 1) * MT * bytesA1 <= budget) ++sa;
     } else {
         sa = 2; sb = 2;
@@ -748,7 +762,7 @@ static int conv_prepare(const am_conv_desc* d, am_conv_plan* plan) {
             if (!grew) break;
         }
         if (fixed + bytesA1 * MT * sa + bytesB * sb > budget) {
-            if (MT == 2) { MT = 1; sa = 2; sb = 2; }
+            if (MT >= 2) { MT = 1; sa = 2; sb = 2; }
             if (fixed + bytesA1 * sa + bytesB * sb > budget) return AM_ERR_ARG;
         }
     }
@@ -765,13 +779,14 @@ static int conv_prepare(const am_conv_desc* d, am_conv_plan* plan) {
 
 typedef void (*conv_kernel_t)(const ConvParams);
 static int conv_launch(const am_conv_plan* plan, void* stream) {
-    static const conv_kernel_t kernels[4] = {k_conv_gemm<1, false>, k_conv_gemm<1, true>, k_conv_gemm<2, false>, k_conv_gemm<2, true>};
+    static const conv_kernel_t kernels[6] = {k_conv_gemm<1, false>, k_conv_gemm<1, true>, k_conv_gemm<2, false>, k_conv_gemm<2, true>,
+                                             k_conv_gemm<4, false>, k_conv_gemm<4, true>};
     static bool attr_set = false;
     if (!attr_set) {
-        for (int i = 0; i < 4; ++i) AM_CUDA(cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+        for (int i = 0; i < 6; ++i) AM_CUDA(cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
         attr_set = true;
     }
-    const conv_kernel_t k = kernels[(plan->p.MT == 2 ? 2 : 0) + (plan->p.residentB ? 1 : 0)];
+    const conv_kernel_t k = kernels[(plan->p.MT == 4 ? 4 : plan->p.MT == 2 ? 2 : 0) + (plan->p.residentB ? 1 : 0)];
     k<<<plan->grid, CONV_THREADS, plan->smem, (cudaStream_t)stream>>>(plan->p);
     AM_CUDA(cudaGetLastError());
     return AM_OK;

@@ -9,7 +9,9 @@ binary_treshold, apply_sigmoid) (:430-505), prepare_image (:607-618).
 The torch.nn modules below are parameter CONTAINERS only (same construction order as the reference, so the same
 seed yields the same random-init weights); no torch op runs in forward/binarize."""
 import ctypes
+import json
 import math
+import os
 
 import numpy as np
 import torch
@@ -149,8 +151,25 @@ def pack_weights(w, bias, segs, S, rowrun, NT, Sy=1):
     return packed, b, ntot, ntot_pad
 
 
+TUNED_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tuned_plans.json")
+_TUNED = None
+
+
+def tuned_table():
+    """{"B<batch>_<H>x<W>": {layer name: [S, Sy, NT, MT]}} measured on a B200 by tools/autotune_fcn.py (per-layer CUDA-event
+    timings of every feasible packing / tiling); layers or shapes without an entry fall back to the cycle model."""
+    global _TUNED
+    if _TUNED is None:
+        _TUNED = {}
+        if os.path.exists(TUNED_PATH):
+            with open(TUNED_PATH) as f:
+                _TUNED = json.load(f)
+    return _TUNED
+
+
 SMEM_BUDGET = 226 * 1024
-AM_CONV_NO_MT2, AM_CONV_FORCE_MT2 = 2, 4
+AM_CONV_NO_MT2, AM_CONV_FORCE_MT2, AM_CONV_FORCE_MT4 = 2, 4, 8
+MT_FLAGS = {1: AM_CONV_NO_MT2, 2: AM_CONV_FORCE_MT2, 4: AM_CONV_FORCE_MT4}
 L2_BYTES_PER_CLK_SM = 42.0        # ~6300 B/clk chip-wide L2->SM throughput / 148 SMs (B300_MICROARCH.md)
 EPI_CLK_PER_COL = 43.0            # epilogue cycles per accumulator column of a 128-row tile (16 warps; ~26 SASS instr/element)
 EPI_CLK_PER_TILE = 600.0          # fixed epilogue cost per tile (barrier round trip, tile decode)
@@ -197,9 +216,9 @@ def layer_cost(nr, h, ntot, runs, kh, batch, nt=None, mt=None, sy=1, n_sm=148):
         ntc *= 2
     if mt is None:
         mt = 2 if (n_mtiles * nnb >= 4 * n_sm and 2 * ntc <= 512) else 1
-    if mt == 2 and 2 * ntc > 512:
+    if mt * ntc > 512:
         return None
-    resident = nnb == 1 and fixed + bytes_b_all + (4 if mt == 2 else 3) * bytes_a <= SMEM_BUDGET
+    resident = nnb == 1 and fixed + bytes_b_all + (2 * mt if mt >= 2 else 3) * bytes_a <= SMEM_BUDGET
     if not resident and fixed + 2 * mt * bytes_a + 2 * bytes_b > SMEM_BUDGET:
         return None
     acc_stages = 2 if 2 * mt * ntc <= 512 else 1
@@ -212,7 +231,7 @@ def layer_cost(nr, h, ntot, runs, kh, batch, nt=None, mt=None, sy=1, n_sm=148):
             per_dy = max(mt * ks * t_mma, ks * ISSUE_CLK_PER_MMA + ISSUE_CLK_PER_DY[0 if resident else 1])   # one issuer per M-tile
             mma += kh * per_dy + ISSUE_CLK_PER_CHUNK
     l2 = (mt * chunks * bytes_a + (0 if resident else bytes_b_all)) / L2_BYTES_PER_CLK_SM
-    epi = mt * (EPI_CLK_PER_COL * nt + EPI_CLK_PER_TILE)
+    epi = mt * (EPI_CLK_PER_COL * nt + EPI_CLK_PER_TILE) * (16.0 / 12.0 if mt == 4 else 1.0)      # MT = 4 leaves 12 epilogue warps
     item = max(mma, l2, epi) if acc_stages == 2 else max(mma + epi, l2)
     n_items = math.ceil(n_mtiles / mt) * nnb
     total = math.ceil(n_items / n_sm) * item
@@ -278,6 +297,7 @@ class FCNPlan:
         self.keep = []          # keeps packed weights alive
         self.ops = []           # (kind, payload)
         self.op_flops = {}      # op index -> algorithmic FLOPs per frame of that conv launch
+        self.specs = {}         # layer name -> what _conv / _tconv were given (+ op index, chosen cfg): autotuning builds variants
         self.flops = 0
 
         def cbn(name):
@@ -290,11 +310,11 @@ class FCNPlan:
         for i in range(5):
             w, b = cbn("conv_down_block_%d" % (i + 1))
             cmap = [0, 1, 2] + [-1] * 5 if i == 0 else ident(src.C)
-            self._conv(w, b, [(src, cmap)], self.d[i], act=1)
+            self._conv("conv_down_block_%d" % (i + 1), w, b, [(src, cmap)], self.d[i], act=1)
             self.ops.append(("pool", (self.d[i], self.p[i])))
             src = self.p[i]
         w, b = cbn("mid_block")
-        self._conv(w, b, [(src, ident(src.C))], self.mid, act=1)
+        self._conv("mid_block", w, b, [(src, ident(src.C))], self.mid, act=1)
         # decoder
         src = self.mid
         for lvl in range(4, -1, -1):
@@ -302,10 +322,11 @@ class FCNPlan:
             bn = "upsample_block_%d.0" % (lvl + 1)
             wt, bt = fold_bn(sd[name + ".weight"], sd[name + ".bias"], sd[bn + ".weight"], sd[bn + ".bias"],
                              sd[bn + ".running_mean"], sd[bn + ".running_var"], out_dim=1)
-            self._tconv(wt, bt, src, self.t[lvl])
+            self._tconv(name, wt, bt, src, self.t[lvl])
             w, b = cbn("conv_up_block_%d" % (lvl + 1))
             cu = self.t[lvl].C
-            self._conv(w, b, [(self.t[lvl], ident(cu)), (self.d[lvl], [cu + c for c in range(self.d[lvl].C)])], self.u[lvl], act=1)
+            self._conv("conv_up_block_%d" % (lvl + 1), w, b, [(self.t[lvl], ident(cu)), (self.d[lvl], [cu + c for c in range(self.d[lvl].C)])],
+                       self.u[lvl], act=1)
             src = self.u[lvl]
         # heads: text mask (pk x pk, 1 ch) and reconstruction (k x k, 3 ch) share one pk x pk GEMM with 4 columns
         wt_, bt_ = cbn("conv_text_mask_out")
@@ -315,17 +336,17 @@ class FCNPlan:
         o = (pk - k) // 2
         wh[1:4, :, o:o + k, o:o + k] = wr_
         f0 = self.flops
-        self._conv(wh, torch.cat([bt_, br_]), [(self.u[0], ident(upc[0]))], None, act=0, cap=16, f32_out=self.heads)
+        self._conv("heads", wh, torch.cat([bt_, br_]), [(self.u[0], ident(upc[0]))], None, act=0, cap=16, f32_out=self.heads)
         self.flops = f0 + 2 * H * W * upc[0] * (pk * pk + 3 * k * k)     # algorithmic: 7x7x1 + 3x3x3, not the padded GEMM
         self.op_flops[len(self.ops) - 1] = self.flops - f0
         self.ops.append(("heads_post", None))
         dmap = [0, 1, 2] + [-1] * 5
         w, b = cbn("conv_pixels_1")       # reference input order: (diff 0..2, x_up1)  (:383)
-        self._conv(w, b, [(self.u[0], [3 + c for c in range(upc[0])]), (self.diff, dmap)], self.px1, act=1)
+        self._conv("conv_pixels_1", w, b, [(self.u[0], [3 + c for c in range(upc[0])]), (self.diff, dmap)], self.px1, act=1)
         w, b = cbn("conv_pixels_2")
-        self._conv(w, b, [(self.px1, [3 + c for c in range(pm1)]), (self.diff, dmap)], self.px2, act=1)
+        self._conv("conv_pixels_2", w, b, [(self.px1, [3 + c for c in range(pm1)]), (self.diff, dmap)], self.px2, act=1)
         w, b = cbn("conv_out")
-        self._conv(w, b, [(self.px2, [3 + c for c in range(pm2)]), (self.diff, dmap)], None, act=0, cap=64, f32_out=self.logits)
+        self._conv("conv_out", w, b, [(self.px2, [3 + c for c in range(pm2)]), (self.diff, dmap)], None, act=0, cap=64, f32_out=self.logits)
         self.ops.append(("threshold", None))
 
     @staticmethod
@@ -346,13 +367,11 @@ class FCNPlan:
         return 2 * macs
 
     # -------------------------------------------------------------------------------------------------
-    def _pick_config(self, width, height, cout, seg_cs, KW, KH, cap=None, allow_sy=True):
-        """(S, Sy, NT, MT) minimising the cycle model: S / Sy = output pixels per GEMM row in x / y, NT = UMMA N per CTA,
-        MT = M-tiles per work item."""
-        if not self.rowrun:
-            return 1, 1, choose_nt(cout), None
-        best = None
-        sy_options = (1, 2) if allow_sy and KH > 1 and height >= 2 else (1,)
+    def _candidates(self, width, height, cout, seg_cs, KW, KH, cap=None):
+        """Every feasible (S, Sy, NT, MT) with its modelled cycles, best first: S / Sy = output pixels per GEMM row in x / y,
+        NT = UMMA N per CTA, MT = M-tiles per work item."""
+        out = []
+        sy_options = (1, 2) if KH > 1 and height >= 2 else (1,)
         if "sy" in self.ov and self.ov["sy"] in sy_options:
             sy_options = (self.ov["sy"],)
         for sy in sy_options:
@@ -361,23 +380,52 @@ class FCNPlan:
                 if s == 1 or (width % s == 0 and s * sy * cout <= 256):
                     runs = [(KW + s - 1) * c_ for c_ in seg_cs]
                     for nt in nt_candidates(s * sy * cout):
-                        for mt in (1, 2):
+                        for mt in (1, 2, 4):
                             c = layer_cost(width // s, height, s * sy * cout, runs, KH, self.B, nt=nt, mt=mt, sy=sy)
-                            if c is not None and (best is None or c["clk"] < best[0] * 0.97):   # near ties: keep the earlier (less padding)
-                                best = (c["clk"], s, sy, nt, mt)
+                            if c is not None:
+                                out.append((c["clk"], s, sy, nt, mt))
                 s *= 2
+        return out
+
+    def _pick_config(self, name, width, height, cout, seg_cs, KW, KH, cap=None):
+        """Configuration of layer `name`: explicit override, else the measured table (tuned_plans.json), else the model."""
+        if not self.rowrun:
+            return 1, 1, choose_nt(cout), None
+        forced = self.ov.get("cfg", {}).get(name)
+        if forced is None and "sy" not in self.ov and "mt" not in self.ov and not self.ov.get("no_tuned"):
+            forced = tuned_table().get("B%d_%dx%d" % (self.B, self.H, self.W), {}).get(name)
+        if forced is not None:
+            return tuple(forced)
+        best = None
+        cands = self._candidates(width, height, cout, seg_cs, KW, KH, cap)
+        if "mt" in self.ov and any(c[4] == self.ov["mt"] for c in cands):       # tests: force the M-tiles per work item where feasible
+            cands = [c for c in cands if c[4] == self.ov["mt"]]
+        for c in cands:
+            if best is None or c[0] < best[0] * 0.97:            # near ties: keep the earlier (less padding)
+                best = c
         return best[1], best[2], best[3], best[4]
 
-    def _conv(self, w, b, srcs, dst, act, cap=None, f32_out=None):
+    def _conv(self, name, w, b, srcs, dst, act, cap=None, f32_out=None):
+        nrows, cin_total, KH, KW = w.shape
+        first = srcs[0][0]
+        cfg = self._pick_config(name, first.W, first.H, nrows, [buf.C for buf, _ in srcs], KW, KH, cap)
+        self.specs[name] = dict(kind="conv", w=w, b=b, srcs=srcs, dst=dst, act=act, cap=cap, f32_out=f32_out, op=len(self.ops), cfg=cfg)
+        d, keep = self._conv_desc(w, b, srcs, dst, act, f32_out, cfg)
+        self.keep += keep
+        self.ops.append(("conv", d))
+        self.op_flops[len(self.ops) - 1] = 2 * first.H * first.W * nrows * cin_total * KH * KW
+        self.flops += 2 * first.H * first.W * nrows * cin_total * KH * KW
+
+    def _conv_desc(self, w, b, srcs, dst, act, f32_out, cfg):
+        """Kernel descriptor (+ the packed tensors it points to) of one convolution for configuration cfg = (S, Sy, NT, MT)."""
         nrows, cin_total, KH, KW = w.shape
         first = srcs[0][0]
         Hin, Win = first.H, first.W
-        S, Sy, NT, MT = self._pick_config(Win, Hin, nrows, [buf.C for buf, _ in srcs], KW, KH, cap)
+        S, Sy, NT, MT = cfg
         packed, bias, ntot, ntot_pad = pack_weights(w, b, [(buf.C, cmap) for buf, cmap in srcs], S, self.rowrun, NT, Sy)
         Himg, KHc = Hin, KH
         Hin, KH = (Himg + Sy - 1) // Sy, KHc + Sy - 1          # GEMM row units per frame column, Toeplitz-extended vertical taps
         packed, bias = packed.to(self.device), bias.to(self.device)
-        self.keep += [packed, bias]
         d = ConvDesc()
         d.nseg = len(srcs)
         for i, (buf, _) in enumerate(srcs):
@@ -404,23 +452,63 @@ class FCNPlan:
             d.out_sx, d.out_sy, d.out_sn = dst.C, dst.Wp * dst.C, dst.H * dst.Wp * dst.C
             d.out_padx, d.out_coff = dst.pad, 0
         d.Cout, d.Sy, d.Sx, d.act = nrows, Sy, S, act
-        d.flags = 0 if MT is None else (AM_CONV_FORCE_MT2 if MT == 2 else AM_CONV_NO_MT2)
-        self.ops.append(("conv", d))
-        self.op_flops[len(self.ops) - 1] = 2 * Himg * Win * nrows * cin_total * KHc * KW
-        self.flops += 2 * Himg * Win * nrows * cin_total * KHc * KW
+        d.flags = 0 if MT is None else MT_FLAGS[MT]
+        return d, [packed, bias]
 
-    def _tconv(self, wt, bt, src, dst):
+    def conv_candidates(self, name):
+        """[(modelled cycles, S, Sy, NT, MT)] of a recorded layer, best first (tools/autotune_fcn.py)."""
+        sp = self.specs[name]
+        if sp["kind"] == "tconv":
+            src, cout = sp["src"], sp["wt"].shape[1]
+            out = []
+            for nt in nt_candidates(4 * cout):
+                for mt in (1, 2, 4):
+                    c = layer_cost(src.W, src.H, 4 * cout, [src.C], 1, self.B, nt=nt, mt=mt)
+                    if c is not None:
+                        out.append((c["clk"], 1, 1, nt, mt))
+            return sorted(out)
+        w, srcs = sp["w"], sp["srcs"]
+        return sorted(self._candidates(srcs[0][0].W, srcs[0][0].H, w.shape[0], [buf.C for buf, _ in srcs], w.shape[3], w.shape[2], sp["cap"]))
+
+    def conv_variant(self, name, cfg):
+        """Descriptor of layer `name` under another configuration, reading and writing the plan's own buffers."""
+        sp = self.specs[name]
+        if sp["kind"] == "tconv":
+            return self._tconv_desc(sp["wt"], sp["bt"], sp["src"], sp["dst"], cfg[2], cfg[3])[:2]
+        return self._conv_desc(sp["w"], sp["b"], sp["srcs"], sp["dst"], sp["act"], sp["f32_out"], tuple(cfg))
+
+    def _tconv(self, name, wt, bt, src, dst):
         """ConvTranspose2d(k=2,s=2) + BN + GELU as a 1x1 GEMM with N = (sy,sx,co); odd output sizes get the
         bias-only row/column (output_padding, FCN_lecturenet.py:280) from a border fill."""
         cin, cout = wt.shape[0], wt.shape[1]
+        forced = self.ov.get("cfg", {}).get(name)
+        if forced is None and self.rowrun and "sy" not in self.ov and "mt" not in self.ov and not self.ov.get("no_tuned"):
+            forced = tuned_table().get("B%d_%dx%d" % (self.B, self.H, self.W), {}).get(name)
+        if forced is not None:
+            NT, MT = forced[2], forced[3]
+        else:
+            best = None
+            cands = [(nt, mt) for nt in nt_candidates(4 * cout) for mt in (1, 2, 4)
+                     if layer_cost(src.W, src.H, 4 * cout, [src.C], 1, self.B, nt=nt, mt=mt) is not None]
+            if "mt" in self.ov and any(mt == self.ov["mt"] for _, mt in cands):
+                cands = [c for c in cands if c[1] == self.ov["mt"]]
+            for nt, mt in cands:
+                    c = layer_cost(src.W, src.H, 4 * cout, [src.C], 1, self.B, nt=nt, mt=mt)
+                    if c is not None and (best is None or c["clk"] < best[0] * 0.97):
+                        best = (c["clk"], nt, mt)
+            NT, MT = best[1], best[2]
+        self.specs[name] = dict(kind="tconv", wt=wt, bt=bt, src=src, dst=dst, op=len(self.ops), cfg=(1, 1, NT, MT))
+        d, keep, gelu_b = self._tconv_desc(wt, bt, src, dst, NT, MT)
+        self.ops.append(("conv", d))
+        self.keep += keep + [gelu_b]
+        self.op_flops[len(self.ops) - 1] = 2 * src.H * src.W * 4 * cout * cin
+        if dst.H > 2 * src.H or dst.W > 2 * src.W:
+            self.ops.append(("border", (dst, 2 * src.H, 2 * src.W, gelu_b)))
+        self.flops += 2 * src.H * src.W * 4 * cout * cin
+
+    def _tconv_desc(self, wt, bt, src, dst, NT, MT):
+        cin, cout = wt.shape[0], wt.shape[1]
         w = wt.permute(2, 3, 1, 0).reshape(4 * cout, cin, 1, 1).contiguous()      # n = (sy*2+sx)*Cout + co
-        best = None
-        for nt in nt_candidates(4 * cout):
-            for mt in (1, 2):
-                c = layer_cost(src.W, src.H, 4 * cout, [src.C], 1, self.B, nt=nt, mt=mt)
-                if c is not None and (best is None or c["clk"] < best[0] * 0.97):
-                    best = (c["clk"], nt, mt)
-        NT, MT = best[1], best[2]
         packed, bias, ntot, ntot_pad = pack_weights(w, bt.repeat(4), [(src.C, list(range(src.C)))], 1, self.rowrun, NT)
         packed, bias = packed.to(self.device), bias.to(self.device)
         d = ConvDesc()
@@ -438,14 +526,9 @@ class FCNPlan:
         d.out_sx, d.out_sy, d.out_sn = dst.C, dst.Wp * dst.C, dst.H * dst.Wp * dst.C
         d.out_padx, d.out_coff = dst.pad, 0
         d.Cout, d.Sy, d.Sx, d.act = cout, 2, 2, 1
-        d.flags = AM_CONV_FORCE_MT2 if MT == 2 else AM_CONV_NO_MT2
-        self.ops.append(("conv", d))
+        d.flags = MT_FLAGS[MT]
         gelu_b = (0.5 * bt.double() * (1.0 + torch.erf(bt.double() / math.sqrt(2.0)))).float().to(torch.bfloat16).to(self.device)
-        self.keep += [packed, bias, gelu_b]
-        self.op_flops[len(self.ops) - 1] = 2 * src.H * src.W * 4 * cout * cin
-        if dst.H > 2 * src.H or dst.W > 2 * src.W:
-            self.ops.append(("border", (dst, 2 * src.H, 2 * src.W, gelu_b)))
-        self.flops += 2 * src.H * src.W * 4 * cout * cin
+        return d, [packed, bias], gelu_b
 
     # -------------------------------------------------------------------------------------------------
     def _conv_plan(self, i, desc):
