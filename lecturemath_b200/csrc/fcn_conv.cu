@@ -619,6 +619,263 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv_gemm(const __grid_cons
     }
 }
 
+// ================================================================================================
+// CTA-pair variant (cta_group::2).  Two CTAs of a cluster (= the two SMs of a TPC) run ONE tcgen05.mma of M = 256:
+// every CTA keeps its own A tiles (its own 128 GEMM rows) and accumulators, but only HALF of each weight tile
+// (NT/2 rows of B) -- the tensor cores of both SMs read both halves.  That halves the shared-memory operand
+// traffic of B per SM (the bound of the M = N = 128 layers: 4 KB of A + 4 KB of B per K = 16 step at 128 B/clk
+// is exactly the tensor time; with a pair it is 4 + 2 KB) and the L2 -> shared-memory weight traffic.
+// Structure = k_conv_gemm<2, false> per CTA (two M-tiles, two issuer warps, streamed weights), with
+//   * a work item = 4 M-tiles (2 per CTA) x one N block, statically strided over the clusters;
+//   * TMA loads of BOTH CTAs completing on the leader's (rank 0) full barriers (.cta_group::2 + mapa);
+//   * the leader's issuer warps issuing tcgen05.mma.cta_group::2 and multicasting their commits to the
+//     empty / accumulator-full barriers of both CTAs;
+//   * the peer's epilogue warps arriving remotely on the leader's accumulator-empty barriers.
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_id_x() { uint32_t r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_count_x() { uint32_t r; asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+    uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma2_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar_cluster, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"((unsigned long long)tm), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar_cluster, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"((unsigned long long)tm), "r"(bar_cluster), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc2_commit(uint32_t bar) {            // arrives on `bar` (same offset) in both CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc2_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) k_conv_gemm_pair(const __grid_constant__ ConvParams p) {
+    constexpr int kMT = 2;                               // M-tiles per CTA (4 per work item)
+    constexpr int kEpiFirst = 4, kEpiWarps = (CONV_THREADS / 32) - kEpiFirst, kEpiPerQ = kEpiWarps / 4;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bytesA1 = (uint32_t)(p.ystep * (p.YT - 1) + p.KH) * p.RT * 128u;
+    const uint32_t bytesA = bytesA1 * kMT;
+    const uint32_t bytesBh = (uint32_t)(p.NT >> 1) * 128u;               // this CTA's half of a weight tile
+    const uint32_t sA0 = smem_base;
+    const uint32_t sB0 = sA0 + bytesA * p.stagesA;
+    const uint32_t sBias = sB0 + ((bytesBh * (uint32_t)p.stagesB + 1023u) & ~1023u);
+    const uint32_t bar0 = sBias + (((uint32_t)p.NT * 4u + 127u) & ~127u);
+    const uint32_t fullA = bar0, emptyA = fullA + 8 * p.stagesA, fullB = emptyA + 8 * p.stagesA, emptyB = fullB + 8 * p.stagesB;
+    const uint32_t accFull = emptyB + 8 * p.stagesB, accEmpty = accFull + 16;
+    const uint32_t tmem_slot = accEmpty + 16;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int n_work = ((p.n_mtiles + 2 * kMT - 1) / (2 * kMT)) * p.nNB;
+    const int w_first = (int)cluster_id_x(), w_step = (int)cluster_count_x();
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < p.stagesA; ++i) { mbar_init(fullA + 8 * i, 1); mbar_init(emptyA + 8 * i, kMT); }
+        for (int i = 0; i < p.stagesB; ++i) { mbar_init(fullB + 8 * i, 1); mbar_init(emptyB + 8 * i, kMT); }
+        for (int i = 0; i < 2; ++i) { mbar_init(accFull + 8 * i, kMT); mbar_init(accEmpty + 8 * i, 2 * kEpiWarps); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        tma_prefetch_desc(&p.tmA[0]);
+        if (p.nseg > 1) tma_prefetch_desc(&p.tmA[1]);
+        tma_prefetch_desc(&p.tmB);
+    }
+    if (warp == 1) {                                     // the same warp of both CTAs allocates the pair's tensor memory
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                  // barriers of both CTAs initialised before any remote signal
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0) {
+        // ===================== TMA producer: own A tiles, own half of every weight tile; completes on the leader =====================
+        int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+        const uint32_t fullA_l = mapa_rank(fullA, 0), fullB_l = mapa_rank(fullB, 0);
+        for (int w = w_first; w < n_work; w += w_step) {
+            const int st = w / p.nNB, nb = w - st * p.nNB;
+            const int n0 = nb * p.NT + (int)rank * (p.NT >> 1);
+            TileCoord tcs[kMT];
+#pragma unroll
+            for (int i = 0; i < kMT; ++i) tcs[i] = decode_tile(p, st * 2 * kMT + (int)rank * kMT + i);
+            int chunk = 0;
+            for (int s = 0; s < p.nseg; ++s) {
+                const CUtensorMap* tm = &p.tmA[s];
+                for (int kx = 0; kx < p.seg_nkx[s]; ++kx) {
+                    const int c1 = p.seg_c1off[s] + kx * p.seg_c1step[s];
+                    for (int ck = 0; ck < p.seg_nck[s]; ++ck, ++chunk) {
+                        mbar_wait_uniform(emptyA + 8 * sa, pa ^ 1);
+                        if (elect_one()) {
+                            const uint32_t dst = sA0 + bytesA * sa;
+                            if (rank == 0) mbar_expect_tx(fullA + 8 * sa, 2 * bytesA);       // both CTAs' boxes
+#pragma unroll
+                            for (int i = 0; i < kMT; ++i)
+                                tma2_load_4d(dst + bytesA1 * i, tm, fullA_l + 8 * sa, ck * 64, tcs[i].r0 + c1, tcs[i].y0 * p.ystep - p.padY, tcs[i].frame);
+                        }
+                        __syncwarp();
+                        if (++sa == p.stagesA) { sa = 0; pa ^= 1; }
+                        for (int dy = 0; dy < p.KH; ++dy) {
+                            mbar_wait_uniform(emptyB + 8 * sb, pb ^ 1);
+                            if (elect_one()) {
+                                if (rank == 0) mbar_expect_tx(fullB + 8 * sb, 2 * bytesBh);
+                                tma2_load_2d(sB0 + bytesBh * sb, &p.tmB, fullB_l + 8 * sb, 0, (chunk * p.KH + dy) * p.Ntot_pad + n0);
+                            }
+                            __syncwarp();
+                            if (++sb == p.stagesB) { sb = 0; pb ^= 1; }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp >= 1 && warp <= kMT) {
+        if (rank == 0) {
+            // ===================== MMA issuer of M-tile pair `mt` (leader CTA only) =====================
+            const int mt = warp - 1;
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NT >> 3) << 17) | ((256u >> 4) << 24);
+            const int KH = p.KH, stagesA = p.stagesA, stagesB = p.stagesB, acc_stages = p.acc_stages, nseg = p.nseg;
+            const uint32_t NTc = (uint32_t)p.NTc;
+            const uint32_t dy_step = ((uint32_t)p.RT * 128u) >> 4, b_step = bytesBh >> 4, a_step = bytesA >> 4;
+            const uint32_t a_lo0 = desc_lo(sA0 + bytesA1 * (uint32_t)mt), b_lo0 = desc_lo(sB0);
+            const uint64_t hiA = desc_hi_sw128(1024u * (uint32_t)p.ystep), hiB = desc_hi_sw128(1024u);
+            int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+            int as = 0; uint32_t pacc = 0;
+            for (int w = w_first; w < n_work; w += w_step) {
+                mbar_wait_uniform(accEmpty + 8 * as, pacc ^ 1);          // both CTAs' epilogues drained this accumulator stage
+                tc_fence_after();
+                const uint32_t td = tmem_base + (uint32_t)(as * kMT + mt) * NTc;
+                uint32_t acc = 0;
+                for (int s = 0; s < nseg; ++s) {
+                    const int nck = p.seg_nck[s], klast = p.seg_klast[s] >> 4;
+                    for (int kc = p.seg_nkx[s] * nck, ck = 0; kc > 0; --kc) {
+                        const int ksteps = (ck == nck - 1) ? klast : 4;
+                        if (++ck == nck) ck = 0;
+                        mbar_wait_uniform(fullA + 8 * sa, pa);
+                        tc_fence_after();
+                        uint32_t alo = a_lo0 + a_step * (uint32_t)sa;
+                        for (int dy = 0; dy < KH; ++dy) {
+                            mbar_wait_uniform(fullB + 8 * sb, pb);
+                            tc_fence_after();
+                            const uint32_t blo = b_lo0 + b_step * (uint32_t)sb;
+                            if (elect_one()) {
+                                tc2_mma_bf16(td, hiA | alo, hiB | blo, idesc, acc);
+                                if (ksteps > 1) tc2_mma_bf16(td, hiA | (alo + 2), hiB | (blo + 2), idesc, 1);
+                                if (ksteps > 2) tc2_mma_bf16(td, hiA | (alo + 4), hiB | (blo + 4), idesc, 1);
+                                if (ksteps > 3) tc2_mma_bf16(td, hiA | (alo + 6), hiB | (blo + 6), idesc, 1);
+                                tc2_commit(emptyB + 8 * sb);
+                            }
+                            __syncwarp();
+                            acc = 1;
+                            alo += dy_step;
+                            if (++sb == stagesB) { sb = 0; pb ^= 1; }
+                        }
+                        if (elect_one()) tc2_commit(emptyA + 8 * sa);
+                        __syncwarp();
+                        if (++sa == stagesA) { sa = 0; pa ^= 1; }
+                    }
+                }
+                if (elect_one()) tc2_commit(accFull + 8 * as);
+                __syncwarp();
+                if (++as == acc_stages) { as = 0; pacc ^= 1; }
+            }
+        }
+    } else if (warp < kEpiFirst) {
+        // idle
+    } else {
+        // ===================== epilogue: this CTA's two M-tiles =====================
+        const int q = warp & 3;
+        const int h = (warp - kEpiFirst) >> 2;
+        const int m = q * 32 + lane;
+        const int yy = m >> p.logRT, rr = m & (p.RT - 1);
+        float* sbias = (float*)(smem_raw + (sBias - smem_u32(smem_raw)));
+        const uint32_t accEmpty_l = mapa_rank(accEmpty, 0);
+        int bias_nb = -1;
+        int as = 0; uint32_t pacc = 0;
+        const int units_per_tile = p.NT >> 4;
+        const int units = units_per_tile * kMT;
+        const bool vec8 = (p.Cout & 7) == 0 && !p.out_f32;
+        const bool vec16 = (p.Cout & 15) == 0 && !p.out_f32 && ((p.out_coff | p.out_sx | (int)(p.out_sy & 7) | (int)(p.out_sn & 7)) & 7) == 0;
+        const bool f32fast = p.out_f32 && p.out_sx == p.Cout && (p.Sy == 1 || ((p.Sx * p.Cout) & 15) == 0) && p.out_coff == 0 &&
+                             ((p.Ntot | (int)p.out_sy | (int)p.out_sn) & 3) == 0;
+        for (int w = w_first; w < n_work; w += w_step) {
+            const int st = w / p.nNB, nb = w - st * p.nNB;
+            const int n0 = nb * p.NT;
+            if (nb != bias_nb) {
+                asm volatile("bar.sync 1, %0;" ::"r"(kEpiWarps * 32));
+                for (int i = threadIdx.x - kEpiFirst * 32; i < p.NT; i += kEpiWarps * 32) sbias[i] = __ldg(p.bias + n0 + i);
+                asm volatile("bar.sync 1, %0;" ::"r"(kEpiWarps * 32));
+                bias_nb = nb;
+            }
+            mbar_wait(accFull + 8 * as, pacc);
+            tc_fence_after();
+            const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * kMT * p.NTc);
+            uint32_t va[16], vb[16];
+            int cur_mt = -1;
+            bool row_ok = false, sy1_ok = true;
+            long long base = 0;
+            auto unit_addr = [&](int g) -> uint32_t {
+                const int mt = g >= units_per_tile ? 1 : 0;
+                return tacc + (uint32_t)(mt * p.NTc + (g - mt * units_per_tile) * 16);
+            };
+            auto enter = [&](int g) -> int {
+                const int mt = g >= units_per_tile ? 1 : 0;
+                if (mt != cur_mt) {
+                    cur_mt = mt;
+                    const TileCoord tc = decode_tile(p, st * 2 * kMT + (int)rank * kMT + mt);
+                    const int y = tc.y0 + yy, r = tc.r0 + rr;
+                    row_ok = tc.valid && (y < p.Hin) && (r < p.nR);
+                    base = (long long)tc.frame * p.out_sn + (long long)(p.Sy * y) * p.out_sy + (long long)(p.Sx * r + p.out_padx) * p.out_sx + p.out_coff;
+                    if (p.Sy * y >= p.out_H || p.Sx * r + p.Sx > p.out_W) row_ok = false;
+                    sy1_ok = p.Sy * y + 1 < p.out_H;
+                }
+                return (g - mt * units_per_tile) * 16;
+            };
+            int g = h;
+            if (g < units) tmem_ld16_async(unit_addr(g), va);
+            while (g < units) {
+                tmem_wait16(va);
+                int g2 = g + kEpiPerQ;
+                if (g2 < units) tmem_ld16_async(unit_addr(g2), vb);
+                { const int j0 = enter(g); if (row_ok) epi_unit(p, va, sbias, n0, j0, base, vec16, vec8, f32fast, sy1_ok); }
+                g = g2;
+                if (g >= units) break;
+                tmem_wait16(vb);
+                g2 = g + kEpiPerQ;
+                if (g2 < units) tmem_ld16_async(unit_addr(g2), va);
+                { const int j0 = enter(g); if (row_ok) epi_unit(p, vb, sbias, n0, j0, base, vec16, vec8, f32fast, sy1_ok); }
+                g = g2;
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { if (rank == 0) mbar_arrive(accEmpty + 8 * as); else mbar_arrive_cluster(accEmpty_l + 8 * as); }
+            if (++as == p.acc_stages) { as = 0; pacc ^= 1; }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    cluster_sync_all();                                  // nobody leaves while the pair still reads its shared / tensor memory
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -657,6 +914,7 @@ struct am_conv_plan {
     ConvParams p;
     size_t smem;
     int grid;
+    int pair;            // 1: k_conv_gemm_pair (cta_group::2 clusters of two CTAs)
     int* d_counter;      // 2 ints, zero between launches
 };
 
@@ -706,10 +964,13 @@ static int conv_prepare(const am_conv_desc* d, am_conv_plan* plan) {
         if (rc) return rc;
         total_chunks += p.seg_nkx[s] * p.seg_nck[s];
     }
+    const bool pair = (d->flags & AM_CONV_CTA_PAIR) != 0;
+    if (pair && (d->NT % 16 != 0 || sm_count() < 2)) return AM_ERR_ARG;
+    plan->pair = pair ? 1 : 0;
     {
         unsigned long long dims[2] = {64ull, (unsigned long long)total_chunks * d->KH * d->Ntot_pad};
         unsigned long long strides[1] = {128ull};
-        unsigned box[2] = {64u, (unsigned)d->NT};
+        unsigned box[2] = {64u, (unsigned)(pair ? d->NT / 2 : d->NT)};       // a CTA pair splits every weight tile in two
         int rc = encode_map(&p.tmB, (void*)d->weights, 2, dims, strides, box);
         if (rc) return rc;
     }
@@ -730,6 +991,27 @@ static int conv_prepare(const am_conv_desc* d, am_conv_plan* plan) {
     const size_t bytesA1 = (size_t)box_rows * d->RT * 128, bytesB = (size_t)d->NT * 128;
     const size_t fixed = 1024 /*align*/ + 1024 /*bias (<= 256 floats)*/ + 512 /*barriers*/;
     const size_t budget = 226 * 1024;
+    if (pair) {          // two M-tiles per CTA, streamed half weight tiles
+        if (2 * p.NTc > 512) return AM_ERR_ARG;
+        const size_t bytesBh = bytesB / 2;
+        int sa = 2, sb = 2;
+        if (fixed + bytesA1 * 2 * sa + bytesBh * sb > budget) return AM_ERR_ARG;
+        while (true) {
+            bool grew = false;
+            if (sb < 3 * d->KH && sb < 12 && fixed + bytesA1 * 2 * sa + bytesBh * (sb + 1) <= budget) { ++sb; grew = true; }
+            if (sa < 4 && fixed + bytesA1 * 2 * (sa + 1) + bytesBh * sb <= budget) { ++sa; grew = true; }
+            if (!grew) break;
+        }
+        p.residentB = 0; p.MT = 2; p.stagesA = sa; p.stagesB = sb;
+        p.acc_stages = (2 * 2 * p.NTc <= 512) ? 2 : 1;
+        p.tmem_cols = 32; while (p.tmem_cols < p.acc_stages * 2 * p.NTc) p.tmem_cols <<= 1;
+        p.n_work = ((p.n_mtiles + 3) / 4) * p.nNB;
+        plan->smem = 1024 + bytesA1 * 2 * sa + ((bytesBh * sb + 1023) & ~(size_t)1023) + 1024 + 512;
+        if (plan->smem > 227 * 1024) return AM_ERR_ARG;
+        const int clusters = p.n_work < sm_count() / 2 ? p.n_work : sm_count() / 2;
+        plan->grid = 2 * clusters;
+        return AM_OK;
+    }
     const size_t allB = bytesB * (size_t)total_chunks * d->KH;
     // Mode choice (mirrored by fcn_lecturenet.layer_cost):
     //   MT = 2 (two M-tiles per work item, one MMA issuer warp each) whenever there is enough work to keep every SM busy;
@@ -785,6 +1067,13 @@ static int conv_launch(const am_conv_plan* plan, void* stream) {
     if (!attr_set) {
         for (int i = 0; i < 6; ++i) AM_CUDA(cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
         attr_set = true;
+    }
+    if (plan->pair) {
+        static bool pair_attr = false;
+        if (!pair_attr) { AM_CUDA(cudaFuncSetAttribute(k_conv_gemm_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024))); pair_attr = true; }
+        k_conv_gemm_pair<<<plan->grid, CONV_THREADS, plan->smem, (cudaStream_t)stream>>>(plan->p);      // __cluster_dims__(2,1,1)
+        AM_CUDA(cudaGetLastError());
+        return AM_OK;
     }
     const conv_kernel_t k = kernels[(plan->p.MT == 4 ? 4 : plan->p.MT == 2 ? 2 : 0) + (plan->p.residentB ? 1 : 0)];
     k<<<plan->grid, CONV_THREADS, plan->smem, (cudaStream_t)stream>>>(plan->p);

@@ -168,8 +168,10 @@ def tuned_table():
 
 
 SMEM_BUDGET = 226 * 1024
-AM_CONV_NO_MT2, AM_CONV_FORCE_MT2, AM_CONV_FORCE_MT4 = 2, 4, 8
-MT_FLAGS = {1: AM_CONV_NO_MT2, 2: AM_CONV_FORCE_MT2, 4: AM_CONV_FORCE_MT4}
+AM_CONV_NO_MT2, AM_CONV_FORCE_MT2, AM_CONV_FORCE_MT4, AM_CONV_CTA_PAIR = 2, 4, 8, 16
+MT_PAIR = 22            # configuration code: CTA pair (cta_group::2), two M-tiles per CTA, four per work item
+MT_FLAGS = {1: AM_CONV_NO_MT2, 2: AM_CONV_FORCE_MT2, 4: AM_CONV_FORCE_MT4, MT_PAIR: AM_CONV_CTA_PAIR}
+MT_OPTIONS = (1, 2, 4, MT_PAIR)
 L2_BYTES_PER_CLK_SM = 42.0        # ~6300 B/clk chip-wide L2->SM throughput / 148 SMs (B300_MICROARCH.md)
 EPI_CLK_PER_COL = 43.0            # epilogue cycles per accumulator column of a 128-row tile (16 warps; ~26 SASS instr/element)
 EPI_CLK_PER_TILE = 600.0          # fixed epilogue cost per tile (barrier round trip, tile decode)
@@ -200,6 +202,11 @@ def layer_cost(nr, h, ntot, runs, kh, batch, nt=None, mt=None, sy=1, n_sm=148):
     rules (resident weights, accumulator stages).  Calibrated against profiles/ (r01): narrow layers are bound by the
     MMA-issuing warps, single-stage accumulators serialise main loop and epilogue.  Returns None when infeasible."""
     nt = nt or choose_nt(ntot)
+    pair = mt == MT_PAIR
+    if pair:                                      # per CTA it is the mt = 2 kernel with half of every weight tile
+        mt = 2
+        if nt % 16:
+            return None
     ntot_pad = ((ntot + nt - 1) // nt) * nt
     nnb = ntot_pad // nt
     if sy == 2:                                   # 2-D packing: `h` image rows -> ceil(h/2) GEMM row units, kh + 1 Toeplitz taps, RT = 8
@@ -218,11 +225,14 @@ def layer_cost(nr, h, ntot, runs, kh, batch, nt=None, mt=None, sy=1, n_sm=148):
         mt = 2 if (n_mtiles * nnb >= 4 * n_sm and 2 * ntc <= 512) else 1
     if mt * ntc > 512:
         return None
-    resident = nnb == 1 and fixed + bytes_b_all + (2 * mt if mt >= 2 else 3) * bytes_a <= SMEM_BUDGET
+    if pair:
+        bytes_b //= 2
+        bytes_b_all //= 2
+    resident = not pair and nnb == 1 and fixed + bytes_b_all + (2 * mt if mt >= 2 else 3) * bytes_a <= SMEM_BUDGET
     if not resident and fixed + 2 * mt * bytes_a + 2 * bytes_b > SMEM_BUDGET:
         return None
     acc_stages = 2 if 2 * mt * ntc <= 512 else 1
-    t_mma = max(nt / 2.0, (4096 + 32 * nt) / 128.0)                  # tensor floor vs smem operand read, per K=16 step
+    t_mma = max(nt / 2.0, (4096 + (16 if pair else 32) * nt) / 128.0)  # tensor floor vs smem operand read, per K=16 step
     mma = 0.0
     for r in runs:
         nck = (r + 63) // 64
@@ -234,6 +244,8 @@ def layer_cost(nr, h, ntot, runs, kh, batch, nt=None, mt=None, sy=1, n_sm=148):
     epi = mt * (EPI_CLK_PER_COL * nt + EPI_CLK_PER_TILE) * (16.0 / 12.0 if mt == 4 else 1.0)      # MT = 4 leaves 12 epilogue warps
     item = max(mma, l2, epi) if acc_stages == 2 else max(mma + epi, l2)
     n_items = math.ceil(n_mtiles / mt) * nnb
+    if pair:
+        n_items = math.ceil(n_mtiles / 4) * nnb * 2                  # per-CTA items, strided over n_sm / 2 clusters
     total = math.ceil(n_items / n_sm) * item
     return {"clk": total, "item": item, "mma": mma, "l2": l2, "epi": epi, "resident": resident, "mt": mt, "nt": nt,
             "acc_stages": acc_stages, "items": n_items}
@@ -380,7 +392,7 @@ class FCNPlan:
                 if s == 1 or (width % s == 0 and s * sy * cout <= 256):
                     runs = [(KW + s - 1) * c_ for c_ in seg_cs]
                     for nt in nt_candidates(s * sy * cout):
-                        for mt in (1, 2, 4):
+                        for mt in MT_OPTIONS:
                             c = layer_cost(width // s, height, s * sy * cout, runs, KH, self.B, nt=nt, mt=mt, sy=sy)
                             if c is not None:
                                 out.append((c["clk"], s, sy, nt, mt))
@@ -462,7 +474,7 @@ class FCNPlan:
             src, cout = sp["src"], sp["wt"].shape[1]
             out = []
             for nt in nt_candidates(4 * cout):
-                for mt in (1, 2, 4):
+                for mt in MT_OPTIONS:
                     c = layer_cost(src.W, src.H, 4 * cout, [src.C], 1, self.B, nt=nt, mt=mt)
                     if c is not None:
                         out.append((c["clk"], 1, 1, nt, mt))
@@ -488,7 +500,7 @@ class FCNPlan:
             NT, MT = forced[2], forced[3]
         else:
             best = None
-            cands = [(nt, mt) for nt in nt_candidates(4 * cout) for mt in (1, 2, 4)
+            cands = [(nt, mt) for nt in nt_candidates(4 * cout) for mt in MT_OPTIONS
                      if layer_cost(src.W, src.H, 4 * cout, [src.C], 1, self.B, nt=nt, mt=mt) is not None]
             if "mt" in self.ov and any(mt == self.ov["mt"] for _, mt in cands):
                 cands = [c for c in cands if c[1] == self.ov["mt"]]

@@ -20,20 +20,23 @@ def _sig(a):
 
 
 @pytest.mark.parametrize("tag", ["tiny", "full"])
-@pytest.mark.parametrize("mode", ["rowrun", "kx", "sy2", "mt1", "mt2", "mt4"])
+@pytest.mark.parametrize("mode", ["rowrun", "kx", "sy2", "mt1", "mt2", "mt4", "mt22"])
 def test_forward_vs_reference_golden(golden, tag, mode):
     """mode: rowrun = planner's choice, kx = one TMA load per horizontal tap, sy2 = 2-D (row-pair) packing forced,
-    mtN = N M-tiles per work item (N MMA issuer warps) forced wherever TMEM / shared memory allow."""
+    mtN = N M-tiles per work item (N MMA issuer warps) forced wherever TMEM / shared memory allow; mt22 = CTA pairs
+    (cta_group::2 clusters, M = 256 MMAs)."""
     z = golden("fcn_forward.npz")
     net = golden_net(tag, z).cuda()
     net.rowrun = mode != "kx"
-    net.plan_overrides = {"sy": 2} if mode == "sy2" else ({"mt": int(mode[2])} if mode.startswith("mt") else None)
+    net.plan_overrides = {"sy": 2} if mode == "sy2" else ({"mt": int(mode[2:])} if mode.startswith("mt") else None)
     frame = z["frame_bgr"]
     plan = net.binarize_frames(frame[None], want_others=True)
     torch.cuda.synchronize()
     if mode.startswith("mt"):
-        n_forced = sum(1 for i, (k, _) in enumerate(plan.ops) if k == "conv" and plan.conv_plan_info(i)[0] == int(mode[2]))
-        assert n_forced >= 8, "only %d conv launches run with MT = %s" % (n_forced, mode[2])
+        want = int(mode[2:])
+        n_forced = sum(1 for i, (k, d) in enumerate(plan.ops) if k == "conv" and
+                       ((d.flags & 16) != 0 if want == 22 else ((d.flags & 16) == 0 and plan.conv_plan_info(i)[0] == want)))
+        assert n_forced >= 8, "only %d conv launches run with MT = %d" % (n_forced, want)
     p = _sig(plan.logits[0].cpu().numpy())
     assert np.abs(p - _sig(z[tag + "_logit"])).max() < PROB_TOL
     assert np.abs(_sig(plan.text_logit[0].cpu().numpy()) - _sig(z[tag + "_text_logit"])).max() < PROB_TOL
