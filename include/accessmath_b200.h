@@ -119,6 +119,19 @@ int am_est_import(am_estimator* est, int n_active, int n_unique, int img_idx, un
 int am_est_export_dev(am_estimator* est, int* d_buf, long long capacity_words, void* stream);
 int am_est_import_dev(am_estimator* est, const int* d_buf, void* stream);
 
+/* ===== 5b. Frame-shard hand-off over NVLink peer memory (one process per GPU) ===
+ * Every rank owns a mailbox (cudaMalloc'ed: receive buffer + flags) that its ring neighbours map through CUDA IPC.  The
+ * sender's am_est_export_dev stores straight into the successor's mailbox; stream memory operations publish / await the
+ * chunk counter, so no SM spins while a rank waits. */
+#define AM_P2P_HANDLE_BYTES 64
+void* am_p2p_alloc(long long bytes);                         /* zero-filled device memory that can be exported */
+int am_p2p_free(void* d_ptr);
+int am_p2p_export_handle(void* d_ptr, void* h_handle);       /* h_handle[AM_P2P_HANDLE_BYTES] for the neighbours */
+void* am_p2p_open_handle(const void* h_handle);              /* neighbour's mailbox mapped into this process */
+int am_p2p_close_handle(void* d_peer_ptr);
+int am_stream_write32(void* d_flag, unsigned value, void* stream);      /* stream-ordered store, local or peer address */
+int am_stream_wait_geq32(void* d_flag, unsigned value, void* stream);   /* stream waits until the flag reached value */
+
 /* ===== 6. FCN-LectureNet binarizer (tcgen05 implicit GEMM) ===================================
  * Replaces the PyTorch arithmetic of FCN_LectureNet.forward / binarize
  * (R/AccessMath/lecturenet_v1/FCN_lecturenet.py:260-323, 364-403, 430-467) and the frame pre/post

@@ -44,6 +44,13 @@ SIGNATURES = {
     "am_est_import": (c_int, [c_void_p, c_int, c_int, c_int, c_ull, c_void_p, c_void_p, c_ll, c_void_p]),
     "am_est_export_dev": (c_int, [c_void_p, c_void_p, c_ll, c_void_p]),
     "am_est_import_dev": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "am_p2p_alloc": (c_void_p, [c_ll]),
+    "am_p2p_free": (c_int, [c_void_p]),
+    "am_p2p_export_handle": (c_int, [c_void_p, c_void_p]),
+    "am_p2p_open_handle": (c_void_p, [c_void_p]),
+    "am_p2p_close_handle": (c_int, [c_void_p]),
+    "am_stream_write32": (c_int, [c_void_p, ctypes.c_uint, c_void_p]),
+    "am_stream_wait_geq32": (c_int, [c_void_p, ctypes.c_uint, c_void_p]),
     "am_conv_gemm": (c_int, [c_void_p, c_void_p]),
     "am_conv_plan_create": (c_void_p, [c_void_p]),
     "am_conv_plan_destroy": (None, [c_void_p]),

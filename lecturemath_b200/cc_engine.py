@@ -10,6 +10,8 @@ import torch
 from . import _lib
 
 MIN_CC_PIXELS = 20        # R/AccessMath/preprocessing/content/labeler.py:22
+LABEL_LAUNCHES = 3            # am_cc_label_batch: k_strip_label, k_resolve, k_crop_fill (+1 with a label image)
+MATCH_LAUNCHES_PER_FRAME = 6  # am_est_add_frames: k_match_pairs, _overlap, _select, _refresh, _update, _copy
 
 
 def _stream():
@@ -183,6 +185,13 @@ class Estimator:
     def import_dev(self, buf):
         """Asynchronous: replace this estimator's state by the active set packed in `buf`."""
         _lib.check(self.lib.am_est_import_dev(self.h, _p(buf), _stream()), "am_est_import_dev")
+
+    def export_dev_ptr(self, ptr, words):
+        """export_dev into raw device memory (e.g. the ring successor's mailbox mapped through CUDA IPC)."""
+        _lib.check(self.lib.am_est_export_dev(self.h, ctypes.c_void_p(ptr), int(words), _stream()), "am_est_export_dev")
+
+    def import_dev_ptr(self, ptr):
+        _lib.check(self.lib.am_est_import_dev(self.h, ctypes.c_void_p(ptr), _stream()), "am_est_import_dev")
 
     def import_state(self, header, meta, crops):
         n_act, words, n_unique, img_idx, tempo = [int(v) for v in header[:5]]

@@ -9,10 +9,14 @@ Multi-GPU: contiguous frame ranges per rank, no data-path collect
 temporal matching is a sequential scan whose carried state is the ACTIVE unique-CC set, so ranks form a chain:
 rank r receives (active set, next unique index, img_idx, tempo_count) from r-1, matches its shard, sends to r+1.
 """
+import ctypes
+import os
+
 import numpy as np
 import torch
 
-from .cc_engine import CCEngine, Estimator
+from . import _lib
+from .cc_engine import CCEngine, Estimator, LABEL_LAUNCHES, MATCH_LAUNCHES_PER_FRAME
 
 
 class ContentExtractor:
@@ -36,11 +40,11 @@ class ContentExtractor:
         plan.run(torch.cuda.current_stream().cuda_stream, False, 128, timing)
         self.launches += plan.launches_per_run
         eng.label(plan.bits, want_labels=False, sync=False)
-        self.launches += 12
+        self.launches += LABEL_LAUNCHES
         if not match:
             return None
         self.est.add_frames(eng, 0, self.batch)
-        self.launches += 4 * self.batch
+        self.launches += MATCH_LAUNCHES_PER_FRAME * self.batch
         return None
 
     def read_rows(self):
@@ -104,6 +108,39 @@ def recv_active_set(src, device=None):
     return h, meta, crops
 
 
+class PeerMailbox:
+    """This rank's mailbox (receive buffer + `ready` / `ack` flags in cudaMalloc'ed memory) and the mapped mailboxes of its
+    ring neighbours (csrc/p2p.cu).  Layout: int32[words] buffer, then at byte +0 the `ready` counter (written by the
+    predecessor: chunk n has landed), at +64 the `ack` counter (written by the successor: chunk n has been imported)."""
+
+    def __init__(self, words, rank, world, device):
+        import ctypes
+        import torch.distributed as dist
+        self.lib, self.words = _lib.lib(), int(words)
+        with torch.cuda.device(device):
+            self.ptr = self.lib.am_p2p_alloc(self.words * 4 + 256)
+            if not self.ptr:
+                raise _lib.AccessMathB200Error("am_p2p_alloc failed")
+            h = ctypes.create_string_buffer(64)
+            _lib.check(self.lib.am_p2p_export_handle(self.ptr, h), "am_p2p_export_handle")
+            handles = [None] * world
+            dist.all_gather_object(handles, bytes(h.raw))
+            self.succ = self.lib.am_p2p_open_handle(handles[(rank + 1) % world])
+            self.pred = self.succ if world == 2 else self.lib.am_p2p_open_handle(handles[(rank - 1) % world])
+        if not self.succ or not self.pred:
+            raise _lib.AccessMathB200Error("cudaIpcOpenMemHandle failed: no peer access between the ring neighbours")
+        fl = self.words * 4
+        self.my_recv, self.my_ready, self.my_ack = self.ptr, self.ptr + fl, self.ptr + fl + 64
+        self.succ_recv, self.succ_ready, self.pred_ack = self.succ, self.succ + fl, self.pred + fl + 64
+        self.n_recv = self.n_send = 0
+
+    def wait(self, flag, value, stream):
+        _lib.check(self.lib.am_stream_wait_geq32(flag, value, stream), "am_stream_wait_geq32")
+
+    def post(self, flag, value, stream):
+        _lib.check(self.lib.am_stream_write32(flag, value, stream), "am_stream_write32")
+
+
 class StreamingExtractor:
     """The hot path over a stream of frame batches, optionally as one rank of a multi-GPU ring.
 
@@ -114,15 +151,18 @@ class StreamingExtractor:
     Multi-GPU sharding: global chunk c = s * world + rank (chunks of `batch` consecutive frames, round-robin over the
     ranks); the active unique-CC set travels rank -> rank+1 around the ring once per chunk, which keeps the matching of
     the whole video ONE ordered scan (bit-exact) while every rank's FCN work is independent.  The hand-off
-    is one fixed-capacity buffer (am_est_export_dev / am_est_import_dev): nothing synchronises the host.  The blocking
-    recv self-staggers the ranks by (match + hand-off) per ring position after the first round, after which no rank
-    waits: a rank's predecessor finished matching chunk c-1 while this rank was still in its own FCN.
-    (A second stream for the matching was measured and rejected: the persistent conv kernels fill every SM's registers
-    and shared memory, so side-stream kernels only start at conv-kernel boundaries and ~40 small launches per batch
-    then lag more than a whole step behind.)"""
+    is one fixed-capacity buffer (am_est_export_dev / am_est_import_dev): nothing synchronises the host.
+    handoff = "p2p" (default): the export kernels store straight into the successor's mailbox over NVLink peer memory
+    (CUDA IPC) and stream memory operations publish / await the chunk counter (PeerMailbox, csrc/p2p.cu) -- no kernel is
+    resident while a rank waits, and nobody waits except for the data dependency itself (match c-1 -> match c), i.e. the
+    ring needs world * (match time) <= one FCN step.  handoff = "nccl": torch.distributed send/recv on the compute
+    stream (NCCL's p2p kernels spin on an SM until the peer arrives; with the persistent conv kernels that costs the
+    sender a whole step position, measured 85 % scaling at 8 GPUs).
+    (The matching itself stays on the compute stream: the persistent conv kernels fill every SM's registers and shared
+    memory, so side-stream kernels would only start at conv-kernel boundaries.)"""
 
     def __init__(self, net, width, height, min_recall=0.85, min_precision=0.85, max_gap=85, batch=8, rank=0, world=1,
-                 device=None, handoff_words=8 << 20, row_capacity=1 << 16, depth=2):
+                 device=None, handoff_words=1 << 20, row_capacity=1 << 16, depth=2, handoff=None):
         self.net, self.width, self.height, self.batch = net, width, height, batch
         self.rank, self.world, self.depth = rank, world, depth
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
@@ -134,7 +174,10 @@ class StreamingExtractor:
         self.ev_matched = [torch.cuda.Event() for _ in range(depth)]
         self.rows = [torch.zeros((row_capacity, 8), dtype=torch.int32, device=self.device) for _ in range(depth)]
         self.offs = [torch.zeros((batch + 1,), dtype=torch.int32, device=self.device) for _ in range(depth)]
-        if world > 1:
+        self.handoff = handoff or os.environ.get("AM_B200_HANDOFF", "p2p")
+        if world > 1 and self.handoff == "p2p":
+            self.mail = PeerMailbox(handoff_words, rank, world, self.device)
+        elif world > 1:
             self.buf_send = torch.zeros(handoff_words, dtype=torch.int32, device=self.device)
             self.buf_recv = torch.zeros(handoff_words, dtype=torch.int32, device=self.device)
         self.step = 0
@@ -147,18 +190,35 @@ class StreamingExtractor:
         s, k = self.step, self.step % self.depth
         plan, eng = self.plan, self.engines[k]
         main = torch.cuda.current_stream(self.device)
+        need_recv = self.world > 1 and not (self.rank == 0 and s == 0)
+        need_send = self.world > 1 and not (last and self.rank == self.world - 1)
         plan.frames.copy_(frames, non_blocking=True)
         plan.run(main.cuda_stream, False, 128, timing)
         eng.label(plan.bits, want_labels=False, sync=False)
-        self.launches += plan.launches_per_run + 12
-        if self.world > 1 and not (self.rank == 0 and s == 0):
+        self.launches += plan.launches_per_run + LABEL_LAUNCHES
+        st = ctypes.c_void_p(main.cuda_stream)
+        if need_recv and self.handoff == "p2p":
+            m = self.mail
+            m.n_recv += 1
+            m.wait(m.my_ready, m.n_recv, st)            # the predecessor's chunk has landed in this rank's mailbox
+            self.est.import_dev_ptr(m.my_recv)
+            m.post(m.pred_ack, m.n_recv, st)            # ... and may be overwritten
+            self.launches += 3
+        elif need_recv:
             dist.recv(self.buf_recv, src=(self.rank - 1) % self.world)
             self.est.import_dev(self.buf_recv)
-            self.launches += 2
+            self.launches += 3
         self.est.add_frames(eng, 0, self.batch)
         eng.pack_rows_into(self.rows[k], self.offs[k], self.batch)
-        self.launches += 4 * self.batch + 2
-        if self.world > 1 and not (last and self.rank == self.world - 1):
+        self.launches += MATCH_LAUNCHES_PER_FRAME * self.batch + 2
+        if need_send and self.handoff == "p2p":
+            m = self.mail
+            m.n_send += 1
+            m.wait(m.my_ack, m.n_send - 1, st)          # the successor has imported the previous chunk
+            self.est.export_dev_ptr(m.succ_recv, m.words)   # P2P stores into the successor's mailbox
+            m.post(m.succ_ready, m.n_send, st)
+            self.launches += 2
+        elif need_send:
             self.est.export_dev(self.buf_send)
             dist.send(self.buf_send, dst=(self.rank + 1) % self.world)
             self.launches += 2
