@@ -16,7 +16,9 @@ for f in /tmp/prof/convsrc_$tag.ncu-rep /tmp/prof/conv_$tag.ncu-rep; do
   [ -f $f ] && [ $(stat -c %s $f) -lt 12000000 ] && cp $f $out/
 done
 du -sh $out
-# CC-only stage on dense glyph masks (BASELINE configs[3]): launch list + full metrics of every CC kernel of one batch
-python tools/profile_step.py --cc-only --steps 2 > $out/plain_cc_$tag.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 200 --csv --log-file $out/launches_cc_$tag.csv python tools/profile_step.py --cc-only --steps 2 > $out/ncu4_$tag.log 2>&1
+# CC-only stage on dense glyph masks (BASELINE configs[3]): per-kernel time + DRAM bytes of label/stats/crops (148-frame batch, the
+# third = warm iteration is summarised) and of the temporal matching (32 frames)
+python tools/cc_bench.py --batches 148 --iters 1 --no-match > $out/plain_cc_$tag.log 2>&1 && \
+ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 40 --csv --log-file $out/launches_cc_$tag.csv python tools/cc_bench.py --batches 148 --iters 1 --no-match > $out/ncu4_$tag.log 2>&1
+ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 120 --csv --log-file $out/launches_match_$tag.csv python tools/cc_bench.py --batches 32 --iters 1 > $out/ncu5_$tag.log 2>&1
 du -sh $out

@@ -55,8 +55,57 @@ def conv_table(tag, layers):
     return out
 
 
+def kernel_rows(path):
+    """[(kernel, {metric: value})] in launch order from an ncu --csv launch list with several metrics."""
+    rows = list(csv.reader(open(path)))
+    hdr = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
+    H = rows[hdr]
+    ii, ki, mi, ui, vi = H.index("ID"), H.index("Kernel Name"), H.index("Metric Name"), H.index("Metric Unit"), H.index("Metric Value")
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1.0, "ms": 1e3}
+    out = collections.OrderedDict()
+    for r in rows[hdr + 1:]:
+        if len(r) <= vi:
+            continue
+        d = out.setdefault(r[ii], [re.sub(r"\(.*", "", r[ki]), {}])
+        d[1][r[mi]] = float(r[vi].replace(",", "")) * scale.get(r[ui], 1.0)
+    return list(out.values())
+
+
+def cc_summary(tag, prefix, batch=148, match_frames=32):
+    """CC stage: per-kernel time and DRAM traffic of the last (warm) label iteration, and of the matching frames."""
+    lab = kernel_rows(os.path.join(G, "launches_cc_%s.csv" % tag))
+    last = [i for i, (k, _) in enumerate(lab) if k.startswith("k_strip_label")][-1]
+    seq = lab[last:last + 3]
+    lines = ["kernel,launches,total_us,dram_MB,frames"]
+    tot_b = tot_us = 0.0
+    for k, m in seq:
+        b = m.get("dram__bytes_read.sum", 0) + m.get("dram__bytes_write.sum", 0)
+        tot_b += b; tot_us += m["gpu__time_duration.sum"]
+        lines.append("%s,1,%.1f,%.2f,%d" % (k, m["gpu__time_duration.sum"], b / 1e6, batch))
+    mt = kernel_rows(os.path.join(G, "launches_match_%s.csv" % tag))
+    agg = collections.OrderedDict()
+    for k, m in mt:
+        if k.startswith("k_match"):
+            a = agg.setdefault(k, [0, 0.0, 0.0])
+            a[0] += 1; a[1] += m["gpu__time_duration.sum"]; a[2] += m.get("dram__bytes_read.sum", 0) + m.get("dram__bytes_write.sum", 0)
+    for k, (n, us, b) in agg.items():
+        lines.append("%s,%d,%.1f,%.2f,%d" % (k, n, us, b / 1e6, n))
+    with open(prefix + "_cc_launches.csv", "w") as f:
+        f.write("\n".join(lines) + "\n")
+        f.write("\n# label rows: python tools/cc_bench.py --batches %d --iters 1 --no-match (third iteration); match rows: --batches %d "
+                "--iters 1 (launch counts = frames matched); ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,"
+                "dram__bytes_write.sum --clock-control none\n" % (batch, match_frames))
+    with open(os.path.join(REPO, "profiles", "cc_traffic.json"), "w") as f:
+        json.dump({"dram_bytes_per_frame": tot_b / batch, "label_us_per_frame_under_ncu": tot_us / batch, "batch": batch,
+                   "source": os.path.basename(prefix) + "_cc_launches.csv",
+                   "note": "dram__bytes_read.sum + dram__bytes_write.sum of k_strip_label + k_resolve + k_crop_fill, per frame"}, f)
+    print("wrote", prefix + "_cc_launches.csv")
+
+
 def main():
     tag, prefix = sys.argv[1], sys.argv[2]
+    if os.path.exists(os.path.join(G, "launches_cc_%s.csv" % tag)) and os.path.exists(os.path.join(G, "launches_match_%s.csv" % tag)):
+        cc_summary(tag, prefix)
     os.makedirs(os.path.dirname(prefix), exist_ok=True)
     step = launches(tag)
     agg = collections.OrderedDict()
