@@ -75,9 +75,12 @@ def make_net():
     return FCN_LectureNet.CreateFromConfig(Configuration.from_file(CONF), 3, False).eval()
 
 
+CHALK = False
+
+
 def frame_pool(n, seed):
     from lecturemath_b200 import synth
-    return np.stack(list(synth.whiteboard_frames(n, H, W, seed=seed)))
+    return np.stack(list(synth.whiteboard_frames(n, H, W, seed=seed, chalk=CHALK)))
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -324,12 +327,16 @@ def run_ours(args):
         line = {"metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
                 "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16", "data": "synthetic",
-                "config": {"workload": "1080p synthetic whiteboard video, binarize + CC label/stats + temporal match on B200 "
-                                       "(BASELINE configs[1])", "frames_per_step_per_gpu": B, "frame": [H, W],
+                "config": {"workload": ("1080p synthetic whiteboard video, binarize + CC label/stats + temporal match on B200 "
+                                        "(BASELINE configs[1])") if (H, W) == (1080, 1920) else
+                                       ("%dx%d synthetic %s video, binarize (FCN at %dx%d) + CC label/stats + temporal match at full size "
+                                        "(NOT the headline workload)" % (W, H, "chalkboard" if CHALK else "whiteboard", sx.plan.W, sx.plan.H)),
+                           "frames_per_step_per_gpu": B, "frame": [H, W],
                            "weights": "random-init seed 0 (FCN_LectureNet.conf widths)", "l2": "256 MB flush write between steps",
                            "parallelism": "frame chunks of %d round-robin over %d GPU(s); temporal matching is one ordered scan, its "
-                                          "active-set state handed rank to rank over NCCL p2p (ring, self-staggering)"
-                                          % (B, world),
+                                          "active-set state handed rank to rank over %s"
+                                          % (B, world, "NVLink peer memory (CUDA-IPC mailboxes, stream memory ops)" if sx.handoff == "p2p"
+                                             else "NCCL p2p (ring, self-staggering)"),
                            "ink_pct": round(ink_pct, 2), "ccs_per_frame": round(n_cc / max(K * B, 1), 1),
                            "unique_ccs": int(fin[0].item()), "tempo_count": int(fin[1].item())},
                 "clocks": sampler.summary(), "roofline": roof, "roofline_cc_stage": cc_roof, "cpu_baseline": cpu,
@@ -365,9 +372,15 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cc-stage", action="store_true", help="skip the secondary CC-stage roofline measurement")
     ap.add_argument("--layer-table", default=None, help="write per-layer conv timings (json) here")
+    ap.add_argument("--frame-size", default=None, help="WxH other than the headline 1920x1080, e.g. 3840x2160 (BASELINE configs[4]: "
+                    "chalkboard frames, FCN at the LANCZOS-halved size, CC stage at full size); not the headline line")
     ap.add_argument("--traffic", type=float, default=None,
                     help="dram__bytes_read+write per conv launch (bytes, from profiles/ ncu --set full) to report in roofline.traffic")
     args = ap.parse_args()
+    if args.frame_size:
+        global H, W, CHALK
+        W, H = (int(v) for v in args.frame_size.lower().split("x"))
+        CHALK = W * H > 2500000
     if args.impl == "reference":
         run_reference(args)
     else:

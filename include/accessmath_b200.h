@@ -203,6 +203,19 @@ int am_fcn_heads_post(const float* d_heads, const uint8_t* d_bgr, int batch, int
  * (FCN_lecturenet.py:452-467 followed by `255 - binary`, FCN_lecturenet_binarizer.py:54) */
 int am_fcn_threshold_pack(const float* d_logits, int batch, int height, int width, int threshold, uint32_t* d_bits, void* stream);
 
+/* ----- frames above 2.5 MP (4K video): FCN_LectureNet.binarize halves them until they fit and resizes the masks back -----
+ * number of halvings and the FCN working size of a width x height frame: `while w*h > 2500000: w, h = int(w/2), int(h/2)`
+ * (FCN_lecturenet.py:434-437).  Host-only helper, no device needed. */
+int am_fcn_working_size(int width, int height, int* out_width, int* out_height);
+/* PIL.Image.resize((out_w, out_h), PIL.Image.LANCZOS) on uint8 interleaved images [B][H][W][channels] (channels <= 4), bit-identical
+ * to Pillow's fixed-point two-pass resampler (FCN_lecturenet.py:436; algorithm: Pillow libImaging/Resample.c) */
+int am_lanczos_resize_u8(const uint8_t* d_in, int batch, int in_h, int in_w, int channels, int out_h, int out_w,
+                         uint8_t* d_out, void* stream);
+/* cv2.resize(mask, (out_w, out_h), interpolation=cv2.INTER_NEAREST) on bit-packed masks (FCN_lecturenet.py:481-486; the ink
+ * inversion `255 - binary` commutes with it) */
+int am_bits_resize_nearest(const uint32_t* d_bits, int batch, int in_h, int in_w, int out_h, int out_w,
+                           uint32_t* d_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,296 @@
+// resize.cu -- the > 2.5 MP branch of FCN_LectureNet.binarize on the device (sm_100a), bit-identical to the third-party
+// operators the reference calls there:
+//   * am_lanczos_resize_u8   = PIL.Image.resize((w, h), LANCZOS) on uint8 interleaved images
+//                              (R/AccessMath/lecturenet_v1/FCN_lecturenet.py:434-437).  Pillow's algorithm (libImaging/Resample.c):
+//                              per output position a window [center - support, center + support) of Lanczos-3 weights computed in
+//                              double, normalised and rounded to 22-bit fixed point; a horizontal pass rounded to uint8, then a
+//                              vertical pass.  The tables are built on the host with the same libm calls, both passes are fused in
+//                              one kernel (tile + halo staged in shared memory, horizontal result kept in shared memory).
+//   * am_bits_resize_nearest = cv2.resize(mask, (w, h), interpolation=INTER_NEAREST) on bit-packed masks (FCN_lecturenet.py:481-486):
+//                              source index = min(floor(dst * (1 / (dsize / (double) ssize))), ssize - 1) per axis.
+// Both are single-pass HBM-bound kernels; at 3840x2160 they move 31 MB / 1.3 MB per frame next to ~1.3 ms of FCN tensor time.
+#include "am_common.cuh"
+#include "../../include/accessmath_b200.h"
+#include <cmath>
+#include <map>
+#include <mutex>
+#include <tuple>
+#include <vector>
+
+namespace {
+
+constexpr int kPrecisionBits = 32 - 8 - 2;       // Pillow: PRECISION_BITS
+constexpr int kTW = 64, kTH = 16;                // output tile of one CTA
+constexpr int kThreads = 256;
+
+struct AxisTable {                               // host copy + device copy of one axis' bounds / coefficients
+    std::vector<int> bounds, coef;
+    int ksize = 0, max_span = 0;                 // max_span: input positions touched by `tile` consecutive outputs
+    int *d_bounds = nullptr, *d_coef = nullptr;
+};
+
+double sinc_filter(double x) {
+    if (x == 0.0) return 1.0;
+    x = x * M_PI;
+    return sin(x) / x;
+}
+double lanczos_filter(double x) {
+    if (-3.0 <= x && x < 3.0) return sinc_filter(x) * sinc_filter(x / 3);
+    return 0.0;
+}
+
+// Resample.c precompute_coeffs + normalize_coeffs_8bpc for box = (0, in_size)
+void build_axis(int in_size, int out_size, int tile, AxisTable& t) {
+    const float in0 = 0.0f, in1 = (float)in_size;
+    double scale = (double)(in1 - in0) / out_size, filterscale = scale;
+    if (filterscale < 1.0) filterscale = 1.0;
+    const double support = 3.0 * filterscale;
+    const int ksize = (int)ceil(support) * 2 + 1;
+    t.ksize = ksize;
+    t.bounds.assign((size_t)out_size * 2, 0);
+    t.coef.assign((size_t)out_size * ksize, 0);
+    std::vector<double> k(ksize);
+    for (int xx = 0; xx < out_size; ++xx) {
+        const double center = in0 + (xx + 0.5) * scale, ss = 1.0 / filterscale;
+        double ww = 0.0;
+        int xmin = (int)(center - support + 0.5);
+        if (xmin < 0) xmin = 0;
+        int xmax = (int)(center + support + 0.5);
+        if (xmax > in_size) xmax = in_size;
+        xmax -= xmin;
+        for (int x = 0; x < xmax; ++x) {
+            const double w = lanczos_filter((x + xmin - center + 0.5) * ss);
+            k[x] = w;
+            ww += w;
+        }
+        for (int x = 0; x < xmax; ++x) {
+            if (ww != 0.0) k[x] /= ww;
+            t.coef[(size_t)xx * ksize + x] = k[x] < 0 ? (int)(-0.5 + k[x] * (1 << kPrecisionBits)) : (int)(0.5 + k[x] * (1 << kPrecisionBits));
+        }
+        t.bounds[2 * xx] = xmin;
+        t.bounds[2 * xx + 1] = xmax;
+    }
+    if (in_size == out_size) {                   // Pillow skips the pass: a single unit tap reproduces the input exactly
+        for (int xx = 0; xx < out_size; ++xx) {
+            t.bounds[2 * xx] = xx; t.bounds[2 * xx + 1] = 1;
+            for (int x = 0; x < ksize; ++x) t.coef[(size_t)xx * ksize + x] = x == 0 ? (1 << kPrecisionBits) : 0;
+        }
+    }
+    t.max_span = 0;
+    for (int o0 = 0; o0 < out_size; o0 += tile) {
+        const int o1 = (o0 + tile < out_size ? o0 + tile : out_size) - 1;
+        int lo = t.bounds[2 * o0], hi = 0;
+        for (int o = o0; o <= o1; ++o) {
+            if (t.bounds[2 * o] < lo) lo = t.bounds[2 * o];
+            if (t.bounds[2 * o] + t.bounds[2 * o + 1] > hi) hi = t.bounds[2 * o] + t.bounds[2 * o + 1];
+        }
+        if (hi - lo > t.max_span) t.max_span = hi - lo;
+    }
+}
+
+int upload(AxisTable& t) {
+    AM_CUDA(cudaMalloc(&t.d_bounds, t.bounds.size() * sizeof(int)));
+    AM_CUDA(cudaMalloc(&t.d_coef, t.coef.size() * sizeof(int)));
+    AM_CUDA(cudaMemcpy(t.d_bounds, t.bounds.data(), t.bounds.size() * sizeof(int), cudaMemcpyHostToDevice));
+    AM_CUDA(cudaMemcpy(t.d_coef, t.coef.data(), t.coef.size() * sizeof(int), cudaMemcpyHostToDevice));
+    return AM_OK;
+}
+
+std::mutex g_mu;
+std::map<std::tuple<int, int, int, int>, AxisTable*> g_axes;          // (device, in, out, tile) -> table, lives until exit
+std::map<std::tuple<int, int, int>, int*> g_nn;                       // (device, src, dst) -> nearest source offsets
+
+int axis_table(int in_size, int out_size, int tile, AxisTable** out) {
+    int dev = 0;
+    AM_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto key = std::make_tuple(dev, in_size, out_size, tile);
+    auto it = g_axes.find(key);
+    if (it == g_axes.end()) {
+        AxisTable* t = new AxisTable();
+        build_axis(in_size, out_size, tile, *t);
+        int rc = upload(*t);
+        if (rc) { delete t; return rc; }
+        it = g_axes.emplace(key, t).first;
+    }
+    *out = it->second;
+    return AM_OK;
+}
+
+// resize.cpp resizeNN: x_ofs[x] = min(cvFloor(x * ifx), ssize - 1), ifx = 1 / (dsize / (double) ssize)
+int nearest_table(int src, int dst, int** out) {
+    int dev = 0;
+    AM_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto key = std::make_tuple(dev, src, dst);
+    auto it = g_nn.find(key);
+    if (it == g_nn.end()) {
+        std::vector<int> ofs(dst);
+        const double inv_scale = dst / (double)src, ifx = 1.0 / inv_scale;
+        for (int x = 0; x < dst; ++x) {
+            int s = (int)floor(x * ifx);
+            ofs[x] = s < src - 1 ? s : src - 1;
+        }
+        int* d = nullptr;
+        AM_CUDA(cudaMalloc(&d, (size_t)dst * sizeof(int)));
+        AM_CUDA(cudaMemcpy(d, ofs.data(), (size_t)dst * sizeof(int), cudaMemcpyHostToDevice));
+        it = g_nn.emplace(key, d).first;
+    }
+    *out = it->second;
+    return AM_OK;
+}
+
+__device__ __forceinline__ int clip8(int acc) {
+    int v = acc >> kPrecisionBits;                                     // arithmetic shift, as Pillow's clip8()
+    return v < 0 ? 0 : (v > 255 ? 255 : v);
+}
+
+// One CTA = one kTH x kTW output tile of one frame.  Shared memory: the input window (rows x row_bytes, loaded as aligned
+// 32-bit words) and the horizontally resampled window (rows x kTW*C uint8).
+__global__ void __launch_bounds__(kThreads)
+k_lanczos_resize(const uint8_t* __restrict__ in, int lead, long long total_bytes, int in_h, int in_w, int C,
+                 const int* __restrict__ bx, const int* __restrict__ kx, int ksx,
+                 const int* __restrict__ by, const int* __restrict__ ky, int ksy,
+                 int out_h, int out_w, uint8_t* __restrict__ out, int win_words, int win_rows) {
+    extern __shared__ uint32_t smem[];
+    uint32_t* win = smem;                                              // [win_rows][win_words]
+    uint8_t* hbuf = (uint8_t*)(smem + (size_t)win_rows * win_words);   // [win_rows][kTW * C]
+    const int f = blockIdx.z, oy0 = blockIdx.y * kTH, ox0 = blockIdx.x * kTW;
+    const int oy1 = min(oy0 + kTH, out_h), ox1 = min(ox0 + kTW, out_w);
+    // input window of this tile (bounds are monotone in the output index)
+    const int x_lo = bx[2 * ox0], x_hi = bx[2 * (ox1 - 1)] + bx[2 * (ox1 - 1) + 1];
+    const int y_lo = by[2 * oy0], y_hi = by[2 * (oy1 - 1)] + by[2 * (oy1 - 1) + 1];
+    const int rows = y_hi - y_lo;
+    const long long frame0 = lead + (long long)f * in_h * in_w * C;    // `in` is 4-byte aligned, the images start `lead` bytes in
+    // phase 0: stage rows [y_lo, y_hi) x bytes [x_lo*C, x_hi*C) through aligned word loads
+    for (int r = threadIdx.x / 32; r < rows; r += kThreads / 32) {
+        const long long b0 = frame0 + ((long long)(y_lo + r) * in_w + x_lo) * C, b1 = b0 + (long long)(x_hi - x_lo) * C;
+        const long long a0 = b0 & ~3LL;
+        const int nw = (int)((b1 - a0 + 3) >> 2);
+        for (int w = threadIdx.x & 31; w < nw; w += 32) {
+            const long long a = a0 + 4LL * w;
+            uint32_t v;
+            if (a + 4 <= total_bytes) v = *(const uint32_t*)(in + a);
+            else {
+                v = 0;
+                for (int j = 0; j < 4; ++j) if (a + j < total_bytes) v |= (uint32_t)in[a + j] << (8 * j);
+            }
+            win[(size_t)r * win_words + w] = v;
+        }
+    }
+    __syncthreads();
+    // phase 1: horizontal pass -> hbuf (uint8, as ImagingResampleHorizontal_8bpc)
+    const int tw = ox1 - ox0, twc = tw * C;
+    for (int i = threadIdx.x; i < rows * twc; i += kThreads) {
+        const int r = i / twc, j = i - r * twc, ox = j / C, c = j - ox * C;
+        const int xmin = bx[2 * (ox0 + ox)], n = bx[2 * (ox0 + ox) + 1];
+        const int* k = kx + (size_t)(ox0 + ox) * ksx;
+        const long long b0 = frame0 + ((long long)(y_lo + r) * in_w + x_lo) * C;
+        const uint8_t* row = (const uint8_t*)(win + (size_t)r * win_words) + (int)(b0 & 3) + (xmin - x_lo) * C + c;
+        int acc = 1 << (kPrecisionBits - 1);
+        for (int t = 0; t < n; ++t) acc += (int)row[t * C] * k[t];
+        hbuf[(size_t)r * (kTW * C) + j] = (uint8_t)clip8(acc);
+    }
+    __syncthreads();
+    // phase 2: vertical pass (ImagingResampleVertical_8bpc), coalesced row-segment stores
+    const int th = oy1 - oy0;
+    for (int i = threadIdx.x; i < th * twc; i += kThreads) {
+        const int oy = i / twc, j = i - oy * twc;
+        const int ymin = by[2 * (oy0 + oy)], n = by[2 * (oy0 + oy) + 1];
+        const int* k = ky + (size_t)(oy0 + oy) * ksy;
+        const uint8_t* col = hbuf + (size_t)(ymin - y_lo) * (kTW * C) + j;
+        int acc = 1 << (kPrecisionBits - 1);
+        for (int t = 0; t < n; ++t) acc += (int)col[(size_t)t * (kTW * C)] * k[t];
+        out[(((long long)f * out_h + oy0 + oy) * out_w + ox0) * C + j] = (uint8_t)clip8(acc);
+    }
+}
+
+__device__ __forceinline__ uint32_t spread16(uint32_t x) {            // abcd -> 0a0b0c0d
+    x = (x | (x << 8)) & 0x00ff00ffu;
+    x = (x | (x << 4)) & 0x0f0f0f0fu;
+    x = (x | (x << 2)) & 0x33333333u;
+    x = (x | (x << 1)) & 0x55555555u;
+    return x;
+}
+
+// one thread per output word; exact2x: every source bit is doubled in x (and every row in y through y_ofs)
+__global__ void k_bits_resize_nearest(const uint32_t* __restrict__ src, int in_h, int wpr_in, int out_h, int out_w, int wpr_out,
+                                      const int* __restrict__ x_ofs, const int* __restrict__ y_ofs, int exact2x,
+                                      uint32_t* __restrict__ dst) {
+    const int f = blockIdx.z, oy = blockIdx.y, ow = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ow >= wpr_out) return;
+    const uint32_t* row = src + ((size_t)f * in_h + y_ofs[oy]) * wpr_in;
+    uint32_t v = 0;
+    if (exact2x) {
+        if (ow * 32 < out_w) {
+            const uint32_t h = (row[ow >> 1] >> (16 * (ow & 1))) & 0xffffu, s = spread16(h);
+            v = s | (s << 1);
+            const int rem = out_w - ow * 32;
+            if (rem < 32) v &= (1u << rem) - 1u;
+        }
+    } else {
+        for (int b = 0; b < 32; ++b) {
+            const int ox = ow * 32 + b;
+            if (ox < out_w) {
+                const int sx = x_ofs[ox];
+                v |= ((row[sx >> 5] >> (sx & 31)) & 1u) << b;
+            }
+        }
+    }
+    dst[((size_t)f * out_h + oy) * wpr_out + ow] = v;
+}
+
+}  // namespace
+
+extern "C" int am_fcn_working_size(int width, int height, int* out_width, int* out_height) {
+    int n = 0;
+    while ((long long)width * height > 2500000LL) {                    // FCN_lecturenet.py:435-437: int(w / 2), int(h / 2)
+        width = width / 2;
+        height = height / 2;
+        ++n;
+    }
+    if (out_width) *out_width = width;
+    if (out_height) *out_height = height;
+    return n;
+}
+
+extern "C" int am_lanczos_resize_u8(const uint8_t* d_in, int batch, int in_h, int in_w, int channels, int out_h, int out_w,
+                                    uint8_t* d_out, void* stream) {
+    if (!d_in || !d_out || batch <= 0 || in_h <= 0 || in_w <= 0 || out_h <= 0 || out_w <= 0 || channels < 1 || channels > 4)
+        return AM_ERR_ARG;
+    AxisTable *tx = nullptr, *ty = nullptr;
+    int rc = axis_table(in_w, out_w, kTW, &tx);
+    if (rc) return rc;
+    rc = axis_table(in_h, out_h, kTH, &ty);
+    if (rc) return rc;
+    const int win_words = (tx->max_span * channels + 3 + 3) / 4 + 1, win_rows = ty->max_span;
+    const size_t smem = (size_t)win_rows * win_words * 4 + (size_t)win_rows * kTW * channels;
+    if (smem > 200 * 1024) {
+        fprintf(stderr, "[accessmath_b200] am_lanczos_resize_u8: scale too large for one tile (%zu B of shared memory)\n", smem);
+        return AM_ERR_ARG;
+    }
+    if (smem > 48 * 1024) AM_CUDA(cudaFuncSetAttribute(k_lanczos_resize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(am_div_up(out_w, kTW), am_div_up(out_h, kTH), batch);
+    const int lead = (int)((uintptr_t)d_in & 3);
+    k_lanczos_resize<<<grid, kThreads, smem, (cudaStream_t)stream>>>(d_in - lead, lead, lead + (long long)batch * in_h * in_w * channels, in_h, in_w,
+                                                                    channels, tx->d_bounds, tx->d_coef, tx->ksize, ty->d_bounds, ty->d_coef,
+                                                                    ty->ksize, out_h, out_w, d_out, win_words, win_rows);
+    AM_CUDA(cudaGetLastError());
+    return AM_OK;
+}
+
+extern "C" int am_bits_resize_nearest(const uint32_t* d_bits, int batch, int in_h, int in_w, int out_h, int out_w,
+                                      uint32_t* d_out, void* stream) {
+    if (!d_bits || !d_out || batch <= 0 || in_h <= 0 || in_w <= 0 || out_h <= 0 || out_w <= 0) return AM_ERR_ARG;
+    int *xo = nullptr, *yo = nullptr;
+    int rc = nearest_table(in_w, out_w, &xo);
+    if (rc) return rc;
+    rc = nearest_table(in_h, out_h, &yo);
+    if (rc) return rc;
+    const int wpr_in = am_words_per_row_impl(in_w), wpr_out = am_words_per_row_impl(out_w);
+    dim3 grid(am_div_up(wpr_out, 128), out_h, batch);
+    k_bits_resize_nearest<<<grid, 128, 0, (cudaStream_t)stream>>>(d_bits, in_h, wpr_in, out_h, out_w, wpr_out, xo, yo,
+                                                                out_w == 2 * in_w ? 1 : 0, d_out);
+    AM_CUDA(cudaGetLastError());
+    return AM_OK;
+}

@@ -33,14 +33,9 @@ class FCN_LectureNet_Binarizer:
         self.frame_count += 1
         net = self.lecture_net
         h, w = frame.shape[:2]
-        if w * h > 2500000:                                              # rare path: reference semantics via binarize()
-            from PIL import Image
-            pil = Image.fromarray(cv2.cvtColor(frame, cv2.COLOR_RGB2BGR))
-            binary, text_mask, rec_img = net.binarize(pil, return_others=True, force_binary=True)
-            binary = 255 - binary
-        else:
-            plan = net.binarize_frames(np.ascontiguousarray(frame)[None], want_others=self.keep_others)
-            binary, text_mask, rec_img = net.masks_from_plan(plan, 0, self.keep_others)
+        # frames above 2.5 MP: binarize_frames halves them (LANCZOS) and resizes the mask back (NEAREST) on the device
+        plan = net.binarize_frames(np.ascontiguousarray(frame)[None], want_others=self.keep_others)
+        binary, text_mask, rec_img = net.masks_from_plan(plan, 0, self.keep_others)
         flag, raw_data = cv2.imencode(".png", binary)
         self.last_binary, self.last_text, self.last_rec = binary, text_mask, rec_img
         self.compressed_frames.append(raw_data)

@@ -680,10 +680,33 @@ class FCN_LectureNet:
         logits (B,H,W) fp32 and the bit-packed INK mask (B,H,WPR), all on the device.  The fused fast path."""
         t = torch.from_numpy(frames_bgr) if isinstance(frames_bgr, np.ndarray) else frames_bgr
         B, H, W, _ = t.shape
+        if W * H > 2500000:                                              # :434-437 / :481-494 on the device (csrc/resize.cu)
+            from .large_frames import LargeView
+            ad = self.large_adapter(B, H, W)
+            plan = self.plan(B, ad.fcn_height, ad.fcn_width)
+            with torch.cuda.device(self._device):
+                st = torch.cuda.current_stream().cuda_stream
+                ad.frames.copy_(t, non_blocking=True)
+                ad.downscale(plan.frames, st)
+                plan.run(st, want_others, threshold)
+                ad.upscale_bits(plan.bits, st)
+            return LargeView(plan, ad)
         plan = self.plan(B, H, W)
         plan.frames.copy_(t, non_blocking=True)
         plan.run(torch.cuda.current_stream().cuda_stream, want_others, threshold)
         return plan
+
+    def large_adapter(self, B, H, W):
+        """Device-side 2.5 MP guard for (B, H, W) frames (LANCZOS halving in, NEAREST mask resize out)."""
+        from .large_frames import LargeFrameAdapter
+        if self._device is None:
+            _lib.lib()
+            self.cuda()
+        key = ("large", B, H, W)
+        if key not in self._plans:
+            with torch.cuda.device(self._device):
+                self._plans[key] = LargeFrameAdapter(B, H, W, self._device)
+        return self._plans[key]
 
     def masks_from_plan(self, plan, f, want_others=True, threshold=128):
         """Reference-format host outputs of frame f: ink mask uint8 (ink = 255, i.e. after `255 - binary`),
@@ -697,7 +720,12 @@ class FCN_LectureNet:
         t = (torch.sigmoid(plan.text_logit[f]).cpu().numpy() * 255).astype(np.uint8)
         text_mask = np.where(t >= threshold, 255, 0).astype(np.uint8)
         rec = plan.rec[f].cpu().numpy() * 0.5 + 0.5
-        return binary, text_mask, np.clip(rec[:, :, ::-1] * 255, 0, 255).astype(np.uint8)
+        rec_img = np.clip(rec[:, :, ::-1] * 255, 0, 255).astype(np.uint8)
+        if text_mask.shape != (plan.H, plan.W):                          # > 2.5 MP frame: the diagnostic outputs follow :487-494
+            import cv2
+            text_mask = cv2.resize(text_mask, (plan.W, plan.H), interpolation=cv2.INTER_NEAREST)
+            rec_img = cv2.resize(rec_img, (plan.W, plan.H), interpolation=cv2.INTER_NEAREST)
+        return binary, text_mask, rec_img
 
     @staticmethod
     def prepare_image(PIL_image):
@@ -719,11 +747,10 @@ class FCN_LectureNet:
         import PIL.Image
         o_width, o_height = PIL_image.size
         width, height = o_width, o_height
-        while width * height > 2500000:                                  # :434-437 (host PIL, as the reference)
-            PIL_image = PIL_image.resize((int(width / 2), int(height / 2)), PIL.Image.LANCZOS)
-            width, height = PIL_image.size
         rgb = np.asarray(PIL_image.convert("RGB"), dtype=np.uint8)
         plan = self.binarize_frames(np.ascontiguousarray(rgb[None, :, :, ::-1]), want_others=return_others)
+        if width * height > 2500000:                                     # :434-437 ran on the device (am_lanczos_resize_u8)
+            width, height = plan.adapter.fcn_width, plan.adapter.fcn_height
         res = plan.logits[0]
         text = plan.text_logit[0] if return_others else None
         if apply_sigmoid:                                                # :452-454

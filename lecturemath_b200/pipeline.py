@@ -25,21 +25,31 @@ class ContentExtractor:
         self.net, self.width, self.height, self.batch = net, width, height, batch
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
         net.cuda(self.device.index)
-        self.plan = net.plan(batch, height, width)
+        self.large = net.large_adapter(batch, height, width)             # > 2.5 MP frames: FCN at the halved size, CC at full size
+        self.plan = net.plan(batch, self.large.fcn_height, self.large.fcn_width)
+        self.frames_in = self.large.frames if self.large.active else self.plan.frames
         self.engine = CCEngine(width, height, batch, device=self.device)
         self.est = Estimator(width, height, min_recall, min_precision, max_gap, max_uniques, max_active, arena_words, device=self.device)
         self.pinned_in = torch.empty((batch, height, width, 3), dtype=torch.uint8).pin_memory()
         self.launches = 0
 
+    def _binarize(self, timing=None):
+        """frames_in -> bit-packed ink mask at the frame size (device)."""
+        st = torch.cuda.current_stream().cuda_stream
+        if self.large.active:
+            self.large.downscale(self.plan.frames, st)
+        self.plan.run(st, False, 128, timing)
+        self.launches += self.plan.launches_per_run + self.large.launches_per_run
+        return self.large.upscale_bits(self.plan.bits, st) if self.large.active else self.plan.bits
+
     # ---- device-resident step (inputs already in HBM) ------------------------------------------------
     def step_device(self, frames_dev=None, match=True, timing=None):
         """One pass of the hot path over one batch.  Returns (rows, offsets) device tensors when match=True."""
-        plan, eng = self.plan, self.engine
+        eng = self.engine
         if frames_dev is not None:
-            plan.frames.copy_(frames_dev, non_blocking=True)
-        plan.run(torch.cuda.current_stream().cuda_stream, False, 128, timing)
-        self.launches += plan.launches_per_run
-        eng.label(plan.bits, want_labels=False, sync=False)
+            self.frames_in.copy_(frames_dev, non_blocking=True)
+        self.bits = self._binarize(timing)
+        eng.label(self.bits, want_labels=False, sync=False)
         self.launches += LABEL_LAUNCHES
         if not match:
             return None
@@ -63,13 +73,13 @@ class ContentExtractor:
         if not t.is_pinned():                                            # pageable input: stage through pinned memory
             self.pinned_in.copy_(t)
             t = self.pinned_in
-        self.plan.frames.copy_(t, non_blocking=True)
+        self.frames_in.copy_(t, non_blocking=True)
         self.step_device(None, match=True)
         return self.read_rows()
 
     def masks_host(self):
         """uint8 (batch, H, W) ink masks (255 = ink) of the last batch, in the reference's format."""
-        return self.engine.unpack(self.plan.bits).cpu().numpy()
+        return self.engine.unpack(self.bits).cpu().numpy()
 
     # ---- frame-shard chain ------------------------------------------------------------------------------
     def recv_state(self, src):
@@ -167,7 +177,9 @@ class StreamingExtractor:
         self.rank, self.world, self.depth = rank, world, depth
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
         net.cuda(self.device.index)
-        self.plan = net.plan(batch, height, width)
+        self.large = net.large_adapter(batch, height, width)             # > 2.5 MP frames: FCN at the halved size, CC at full size
+        self.plan = net.plan(batch, self.large.fcn_height, self.large.fcn_width)
+        self.frames_in = self.large.frames if self.large.active else self.plan.frames
         self.engines = [CCEngine(width, height, batch, device=self.device) for _ in range(depth)]
         self.est_params = (min_recall, min_precision, max_gap)
         self.est = Estimator(width, height, min_recall, min_precision, max_gap, device=self.device)
@@ -192,10 +204,13 @@ class StreamingExtractor:
         main = torch.cuda.current_stream(self.device)
         need_recv = self.world > 1 and not (self.rank == 0 and s == 0)
         need_send = self.world > 1 and not (last and self.rank == self.world - 1)
-        plan.frames.copy_(frames, non_blocking=True)
+        self.frames_in.copy_(frames, non_blocking=True)
+        if self.large.active:                                            # FCN_lecturenet.py:434-437 on the device
+            self.large.downscale(plan.frames, main.cuda_stream)
         plan.run(main.cuda_stream, False, 128, timing)
-        eng.label(plan.bits, want_labels=False, sync=False)
-        self.launches += plan.launches_per_run + LABEL_LAUNCHES
+        self.bits = self.large.upscale_bits(plan.bits, main.cuda_stream) if self.large.active else plan.bits   # :481-486
+        eng.label(self.bits, want_labels=False, sync=False)
+        self.launches += plan.launches_per_run + self.large.launches_per_run + LABEL_LAUNCHES
         st = ctypes.c_void_p(main.cuda_stream)
         if need_recv and self.handoff == "p2p":
             m = self.mail
@@ -253,7 +268,7 @@ class StreamingExtractor:
         return self.est.state()
 
     def masks_host(self):
-        return self.engines[0].unpack(self.plan.bits).cpu().numpy()
+        return self.engines[0].unpack(self.bits).cpu().numpy()
 
 
 def shard_ranges(n_frames, world):
