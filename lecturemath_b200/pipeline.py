@@ -180,6 +180,12 @@ class StreamingExtractor:
         self.large = net.large_adapter(batch, height, width)             # > 2.5 MP frames: FCN at the halved size, CC at full size
         self.plan = net.plan(batch, self.large.fcn_height, self.large.fcn_width)
         self.frames_in = self.large.frames if self.large.active else self.plan.frames
+        # host frames arrive through a copy stream into two alternating device buffers, so the H2D copy of batch s overlaps
+        # the kernels of batch s-1 (the copy engines are free even while the persistent conv kernels own every SM)
+        self.inbuf = [self.frames_in, torch.empty_like(self.frames_in)]
+        self.copy_stream = torch.cuda.Stream(self.device)
+        self.ev_in_ready = [torch.cuda.Event() for _ in range(2)]
+        self.ev_in_free = [None, None]
         self.engines = [CCEngine(width, height, batch, device=self.device) for _ in range(depth)]
         self.est_params = (min_recall, min_precision, max_gap)
         self.est = Estimator(width, height, min_recall, min_precision, max_gap, device=self.device)
@@ -204,10 +210,25 @@ class StreamingExtractor:
         main = torch.cuda.current_stream(self.device)
         need_recv = self.world > 1 and not (self.rank == 0 and s == 0)
         need_send = self.world > 1 and not (last and self.rank == self.world - 1)
-        self.frames_in.copy_(frames, non_blocking=True)
+        kin = s & 1
+        src = self.inbuf[kin]
+        if frames.is_cuda:
+            src.copy_(frames, non_blocking=True)
+        else:                                                            # pinned host frames: H2D on the copy stream
+            with torch.cuda.stream(self.copy_stream):
+                if self.ev_in_free[kin] is not None:
+                    self.copy_stream.wait_event(self.ev_in_free[kin])    # batch s-2 no longer reads this buffer
+                src.copy_(frames, non_blocking=True)
+                self.ev_in_ready[kin].record(self.copy_stream)
+            main.wait_event(self.ev_in_ready[kin])
         if self.large.active:                                            # FCN_lecturenet.py:434-437 on the device
-            self.large.downscale(plan.frames, main.cuda_stream)
+            self.large.downscale(plan.frames, main.cuda_stream, src=src)
+        else:
+            plan.frames = src
         plan.run(main.cuda_stream, False, 128, timing)
+        if self.ev_in_free[kin] is None:
+            self.ev_in_free[kin] = torch.cuda.Event()
+        self.ev_in_free[kin].record(main)
         self.bits = self.large.upscale_bits(plan.bits, main.cuda_stream) if self.large.active else plan.bits   # :481-486
         eng.label(self.bits, want_labels=False, sync=False)
         self.launches += plan.launches_per_run + self.large.launches_per_run + LABEL_LAUNCHES
