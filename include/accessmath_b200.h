@@ -216,6 +216,38 @@ int am_lanczos_resize_u8(const uint8_t* d_in, int batch, int in_h, int in_w, int
 int am_bits_resize_nearest(const uint32_t* d_bits, int batch, int in_h, int in_w, int out_h, int out_w,
                            uint32_t* d_out, void* stream);
 
+/* ===== 7. Stage 03: CC grouping on the device-resident unique-CC tables =====================
+ * Pixel work of R/AccessMath/preprocessing/content/cc_stability_estimator.py:166-681 (called by
+ * R/pre_ST3D_v3.0_03_cc_grouping.py:41-101).  The order-dependent list / dictionary logic between these steps
+ * (split_stable_cc_by_gaps, compute_groups, compute_conflicting_groups ...) is host code in lecturemath_b200/cc_grouping.py. */
+typedef struct am_unique_view {            /* DEVICE pointers, index = unique CC */
+    const int *min_x, *max_x, *min_y, *max_y, *size;
+    const unsigned long long* crop_off;    /* word offset of the unique's first-seen crop in `arena` */
+    const uint32_t* arena;                 /* bit-packed crops: word-aligned rows at their absolute x */
+    int n;
+} am_unique_view;
+/* the tables a live estimator already holds in HBM (zero copy; valid until am_est_destroy).  Synchronises to read n. */
+int am_est_unique_view(am_estimator* est, am_unique_view* out, void* stream);
+/* compute_overlapping_stable_cc (:245-306; IntervalIndex.find_matches interval_index.py:42-99 + getOverlapFMeasure
+ * connected_component.py:202-250): all position pairs a < b of the n listed uniques (d_ids[a] = index into the view, listed in
+ * ascending stage-03 index) whose inclusive bounding boxes intersect, in ascending (a, b) order: d_pairs[k] = (a, b, matched
+ * pixels).  *h_n_pairs = number of pairs; returns 3 (capacity) without writing when it exceeds `capacity` -- call again with a
+ * larger buffer.  Synchronises. */
+int am_group_overlaps(const am_unique_view* v, const int* d_ids, int n, int* d_pairs, long long capacity,
+                      long long* h_n_pairs, void* stream);
+/* compute_group_images (:575-636) for n_seg (group, time segment) items: d_seg[s] = (min_x, max_x, min_y, max_y of the group,
+ * member_begin, member_end), d_members[m] = (index into the view, frames the CC is seen in inside the segment, > 0);
+ * image = ((double) votes / (double) max votes >= threshold), bit-packed like a crop at word offset d_out_off[s] of d_out. */
+int am_group_images(const am_unique_view* v, int n_seg, const int* d_seg, const int* d_members, double threshold,
+                    const unsigned long long* d_out_off, uint32_t* d_out, void* stream);
+/* rebuilt_binary_frame (:174-179) and the clean channel of frames_from_groups (:638-681): zero d_out (uint8
+ * [n_frames][height][width], frames frame0 .. frame0+n_frames-1), then for every item k add 255 (uint8 wrap-around, as numpy `+=`)
+ * at the set pixels of bit-packed image d_item_img[k] (box d_boxes[img] = min_x, max_x, min_y, max_y; words at d_img_off[img] of
+ * d_imgs) into frame d_item_frame[k].  d_out must be accessible up to the next 4-byte boundary past its end. */
+int am_paint_frames(int n_items, const int* d_item_frame, const int* d_item_img, const int* d_boxes,
+                    const unsigned long long* d_img_off, const uint32_t* d_imgs, int frame0, int n_frames, int height, int width,
+                    uint8_t* d_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

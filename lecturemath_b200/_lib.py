@@ -62,6 +62,10 @@ SIGNATURES = {
     "am_fcn_heads_post": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "am_fcn_threshold_pack": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "am_fcn_working_size": (c_int, [c_int, c_int, c_void_p, c_void_p]),
+    "am_est_unique_view": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "am_group_overlaps": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_ll, c_void_p, c_void_p]),
+    "am_group_images": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_double, c_void_p, c_void_p, c_void_p]),
+    "am_paint_frames": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "am_lanczos_resize_u8": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "am_bits_resize_nearest": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
 }

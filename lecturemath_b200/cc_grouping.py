@@ -1,0 +1,328 @@
+"""Stage 03 (CC grouping) behind the reference's estimator methods.
+
+R/pre_ST3D_v3.0_03_cc_grouping.py:41-101 calls, on the estimator that stage 02 produced:
+    rebuilt_binary_images, split_stable_cc_by_gaps, get_stable_cc_idxs, compute_overlapping_stable_cc, compute_groups,
+    compute_groups_temporal_information, compute_conflicting_groups, compute_group_images, frames_from_groups
+(R/AccessMath/preprocessing/content/cc_stability_estimator.py:166-681).  GroupingMixin gives CCStabilityEstimator the same
+methods, same arguments, same result shapes.  All pixel work runs on the B200 over the bit-packed unique-CC crops that
+stage 02 left in HBM (csrc/grouping.cu: am_group_overlaps, am_group_images, am_paint_frames); what stays here is the
+order-dependent list / dictionary bookkeeping whose ORDER is part of the reference's result (group numbering, list order).
+There is no CPU path for the pixel work: without the library / a device these methods raise."""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from .connected_component import pack_crop, unpack_crop
+
+
+class UniqueView(ctypes.Structure):
+    """am_unique_view (include/accessmath_b200.h)."""
+    _fields_ = [("min_x", ctypes.c_void_p), ("max_x", ctypes.c_void_p), ("min_y", ctypes.c_void_p), ("max_y", ctypes.c_void_p),
+                ("size", ctypes.c_void_p), ("crop_off", ctypes.c_void_p), ("arena", ctypes.c_void_p), ("n", ctypes.c_int)]
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _dev(a, dtype):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=dtype)).cuda()
+
+
+def _packed(cc):
+    if getattr(cc, "_packed", None) is None:
+        cc._packed = pack_crop(cc.img, int(cc.min_x), int(cc.max_x), int(cc.min_y), int(cc.max_y))
+    return cc._packed
+
+
+def _crop_words(cc):
+    return ((int(cc.max_x) >> 5) - (int(cc.min_x) >> 5) + 1) * (int(cc.max_y) - int(cc.min_y) + 1)
+
+
+class GroupingMixin:
+    # ---- device view of the unique CCs ------------------------------------------------------------------------
+    def _unique_view(self):
+        """(UniqueView, obj_index): obj_index[u] = row of the view that holds unique u's box / crop.  Zero copy while the
+        stage-02 estimator is alive on this device; otherwise (unpickled object) the packed crops are uploaded once."""
+        n = len(self.unique_cc_objects)
+        cached = getattr(self, "_view_cache", None)
+        if cached is not None and cached[2] == n:
+            return cached[0], cached[1]
+        first, obj_index = {}, np.zeros(n, dtype=np.int32)
+        for u, cc in enumerate(self.unique_cc_objects):               # split_stable_cc_by_gaps appends aliases of the same object
+            obj_index[u] = first.setdefault(id(cc), u)
+        lib = _lib.lib()
+        view, keep = UniqueView(), None
+        est = getattr(self, "_est", None)
+        if est is not None and getattr(est, "h", None):
+            _lib.check(lib.am_est_unique_view(est.h, ctypes.byref(view), _stream()), "am_est_unique_view")
+            if view.n < int(obj_index.max(initial=-1)) + 1:
+                raise _lib.AccessMathB200Error("device estimator holds %d uniques, the host state %d" % (view.n, n))
+        else:
+            ccs = [self.unique_cc_objects[u] for u in sorted(first.values())]
+            rows = sorted(first.values())
+            remap = {u: i for i, u in enumerate(rows)}
+            obj_index = np.array([remap[int(v)] for v in obj_index], dtype=np.int32)
+            words = np.array([_crop_words(c) for c in ccs], dtype=np.int64)
+            offs = np.concatenate([[0], np.cumsum(words)]).astype(np.uint64)
+            arena = np.concatenate([_packed(c) for c in ccs]) if ccs else np.zeros(1, np.uint32)
+            cols = [_dev([int(getattr(c, k)) for c in ccs], np.int32) for k in ("min_x", "max_x", "min_y", "max_y", "size")]
+            keep = cols + [_dev(offs[:-1], np.uint64), _dev(arena.view(np.int32), np.int32)]
+            for name, t in zip(("min_x", "max_x", "min_y", "max_y", "size", "crop_off", "arena"), keep):
+                setattr(view, name, t.data_ptr())
+            view.n = len(ccs)
+        self._view_cache = (view, obj_index, n, keep)
+        return view, obj_index
+
+    # ---- :166-179 ---------------------------------------------------------------------------------------------
+    def rebuilt_binary_images(self, chunk=64):
+        out = []
+        for f0 in range(0, len(self.cc_idx_per_frame), chunk):
+            rows = self.cc_idx_per_frame[f0:f0 + chunk]
+            ccs = [(t, cc) for t, row in enumerate(rows) for _, cc in row]
+            out.extend(self._paint(len(rows), [t for t, _ in ccs], [c for _, c in ccs]))
+        return out
+
+    def rebuilt_binary_frame(self, frame_ccs):
+        return self._paint(1, [0] * len(frame_ccs), [cc for _, cc in frame_ccs])[0]
+
+    def _paint(self, n_frames, item_frame, ccs):
+        """uint8 frames with `+= 255` at every set pixel of every (frame, crop) item -- am_paint_frames."""
+        lib = _lib.lib()
+        out = torch.empty(n_frames * self.height * self.width + 8, dtype=torch.uint8, device="cuda")
+        if ccs:
+            words = np.array([_crop_words(c) for c in ccs], dtype=np.int64)
+            offs = np.concatenate([[0], np.cumsum(words)])[:-1].astype(np.uint64)
+            imgs = _dev(np.concatenate([_packed(c) for c in ccs]).view(np.int32), np.int32)
+            boxes = _dev([(int(c.min_x), int(c.max_x), int(c.min_y), int(c.max_y)) for c in ccs], np.int32)
+            d_frame, d_img, d_off = _dev(item_frame, np.int32), _dev(np.arange(len(ccs)), np.int32), _dev(offs, np.uint64)
+            args = (len(ccs), d_frame.data_ptr(), d_img.data_ptr(), boxes.data_ptr(), d_off.data_ptr(), imgs.data_ptr())
+        else:
+            args = (0, None, None, None, None, None)
+        _lib.check(lib.am_paint_frames(*args, 0, n_frames, self.height, self.width, out.data_ptr(), _stream()), "am_paint_frames")
+        host = out[:n_frames * self.height * self.width].cpu().numpy().reshape(n_frames, self.height, self.width)
+        return [host[t] for t in range(n_frames)]
+
+    # ---- :181-228 (list bookkeeping; no arithmetic) ----------------------------------------------------------------
+    def split_stable_cc_by_gaps(self, max_gap, stable_min_frames):
+        split = 0
+        for u in range(len(self.unique_cc_objects)):
+            frames = self.unique_cc_frames[u]
+            cuts = [i for i in range(1, len(frames)) if frames[i][0] - frames[i - 1][0] > max_gap]
+            if not cuts or len(frames) < stable_min_frames:
+                continue
+            edges = [0] + cuts + [len(frames)]
+            self.unique_cc_frames[u] = frames[:cuts[0]]
+            for a, b in zip(edges[1:-1], edges[2:]):
+                new_u = len(self.unique_cc_objects)
+                self.unique_cc_objects.append(self.unique_cc_objects[u])
+                self.unique_cc_frames.append(frames[a:b])
+                for t, _ in frames[a:b]:
+                    row = self.cc_idx_per_frame[t]
+                    k = next((i for i, (uk, _) in enumerate(row) if uk == u), None)      # the FIRST instance with the old index
+                    if k is not None:
+                        row[k] = (new_u, row[k][1])
+            split += 1
+        return split
+
+    def get_stable_cc_idxs(self, min_stable_frames):                         # :230-236
+        return [u for u, f in enumerate(self.unique_cc_frames) if len(f) >= min_stable_frames]
+
+    def get_temporal_index(self):                                            # :238-243
+        return [[u for u, _ in row] for row in self.cc_idx_per_frame]
+
+    # ---- :245-306 ---------------------------------------------------------------------------------------------
+    def stable_overlaps_device(self, stable_idxs):
+        """int64 array [n_pairs][3] = (idx_cc1, idx_cc2, matched pixels), idx_cc1 < idx_cc2 ascending: every pair of stable
+        uniques whose inclusive bounding boxes intersect (am_group_overlaps)."""
+        lib = _lib.lib()
+        view, obj_index = self._unique_view()
+        ids = np.asarray(stable_idxs, dtype=np.int64)
+        if len(ids) < 2:
+            return np.zeros((0, 3), dtype=np.int64)
+        assert np.all(np.diff(ids) > 0), "stable_idxs must be ascending (get_stable_cc_idxs)"
+        d_ids = _dev(obj_index[ids], np.int32)
+        cap = max(1024, 8 * len(ids))
+        while True:
+            pairs = torch.empty((cap, 3), dtype=torch.int32, device="cuda")
+            n = ctypes.c_longlong(0)
+            rc = lib.am_group_overlaps(ctypes.byref(view), d_ids.data_ptr(), len(ids), pairs.data_ptr(), cap, ctypes.byref(n), _stream())
+            if rc == 3:
+                cap = int(n.value)
+                continue
+            _lib.check(rc, "am_group_overlaps")
+            break
+        p = pairs[:n.value].cpu().numpy().astype(np.int64)
+        p[:, 0], p[:, 1] = ids[p[:, 0]], ids[p[:, 1]]
+        return p
+
+    def compute_overlapping_stable_cc(self, stable_idxs, temporal_window):
+        n = len(self.unique_cc_objects)
+        all_ov, time_ov, total = [[] for _ in range(n)], [[] for _ in range(n)], 0
+        first = [f[0][0] for f in self.unique_cc_frames]
+        last = [f[-1][0] for f in self.unique_cc_frames]
+        for u1, u2, match in self.stable_overlaps_device(stable_idxs).tolist():
+            if match == 0:                                                   # recall == precision == 0.0 (:283)
+                continue
+            s1, s2 = self.unique_cc_objects[u1].size, self.unique_cc_objects[u2].size
+            recall, precision = match / float(s1), match / float(s2)        # connected_component.py:239-240 (fp64)
+            matched = int(s1 * recall)                                       # :284
+            all_ov[u1].append((u2, matched, s2, s1))
+            all_ov[u2].append((u1, matched, s1, s2))
+            if last[u1] + temporal_window >= first[u2] and last[u2] >= first[u1] - temporal_window:
+                time_ov[u1].append((u2, recall, precision))
+                time_ov[u2].append((u1, precision, recall))
+                total += 1
+        return time_ov, total, all_ov
+
+    # ---- :308-413 (sequential merge; the numbering of the groups is part of the result) ---------------------------------
+    def compute_groups(self, stable_idxs, overlapping_cc, min_recall, t_fmeasure, t_time_IOU):
+        groups, owner = [], {}
+        for u1 in stable_idxs:
+            g = owner.get(u1)
+            if g is None:
+                g = owner[u1] = len(groups)
+                groups.append([u1])
+            for u2, recall, _ in overlapping_cc[u1]:
+                if recall < min_recall:
+                    continue
+                other = owner.get(u2)
+                if other is None:
+                    owner[u2] = g
+                    groups[g].append(u2)
+                elif other != g:
+                    for m in groups[other]:
+                        owner[m] = g
+                    groups[g].extend(groups[other])
+                    groups[other] = []
+        final = [grp for grp in groups if grp]
+        return final, {m: g for g, grp in enumerate(final) for m in grp}
+
+    # ---- :415-444 ---------------------------------------------------------------------------------------------
+    def compute_groups_temporal_information(self, cc_groups):
+        n_frames = len(self.cc_idx_per_frame)
+        ages, per_frame = {}, [[] for _ in range(n_frames)]
+        for g, grp in enumerate(cc_groups):
+            if not grp:
+                continue
+            marks = sorted({self.unique_cc_frames[u][0][0] for u in grp} | {self.unique_cc_frames[u][-1][0] for u in grp})
+            ages[g] = marks
+            for t in range(marks[0], min(marks[-1] + 1, n_frames)):
+                per_frame[t].append(g)
+        return ages, per_frame
+
+    # ---- :446-500 ---------------------------------------------------------------------------------------------
+    def compute_conflicting_groups(self, stable_idxs, all_overlapping_cc, n_groups, group_idx_per_cc):
+        conflicts = {g: {} for g in range(n_groups)}
+        for u1 in stable_idxs:
+            cc1 = self.unique_cc_objects[u1]
+            for u2, matched, size2, size1 in all_overlapping_cc[u1]:
+                if u1 >= u2 or group_idx_per_cc[u1] == group_idx_per_cc[u2]:
+                    continue
+                cc2 = self.unique_cc_objects[u2]
+                inter = cc1.getOverlapArea(cc2)
+                entry = {"matched": matched, "unmatched": size1 + size2 - matched * 2,
+                         "area_union": cc1.getBoxArea() + cc2.getBoxArea() - inter, "area_intersection": inter}
+                g1, g2 = group_idx_per_cc[u1], group_idx_per_cc[u2]
+                for a, b in ((g1, g2), (g2, g1)):
+                    slot = conflicts[a].get(b)
+                    if slot is None:
+                        conflicts[a][b] = dict(entry)
+                    else:
+                        for k, v in entry.items():
+                            slot[k] += v
+        return conflicts
+
+    # ---- :575-636 ---------------------------------------------------------------------------------------------
+    def compute_group_images(self, cc_groups, group_ages, segment_threshold):
+        lib = _lib.lib()
+        view, obj_index = self._unique_view()
+        bounds, seg_rows, members, seg_key = {}, [], [], []
+        for g, grp in enumerate(cc_groups):
+            if not grp:
+                continue
+            ccs = [self.unique_cc_objects[u] for u in grp]
+            box = (min(c.min_x for c in ccs), max(c.max_x for c in ccs), min(c.min_y for c in ccs), max(c.max_y for c in ccs))
+            bounds[g] = box
+            times = [np.fromiter((t for t, _ in self.unique_cc_frames[u]), dtype=np.int64) for u in grp]
+            marks = group_ages[g]
+            for s, (t0, t1) in enumerate(zip(marks[:-1], marks[1:])):
+                begin = len(members)
+                for u, ts in zip(grp, times):
+                    seen = int(np.count_nonzero((ts >= t0) & (ts <= t1)))
+                    if seen:
+                        members.append((int(obj_index[u]), seen))
+                seg_rows.append(tuple(int(v) for v in box) + (begin, len(members)))
+                seg_key.append((g, s))
+        images = {g: [] for g in bounds}
+        self._group_device = None
+        if not seg_rows:
+            return images, bounds
+        seg = np.array(seg_rows, dtype=np.int32).reshape(-1, 6)
+        words = ((seg[:, 1] >> 5) - (seg[:, 0] >> 5) + 1).astype(np.int64) * (seg[:, 3] - seg[:, 2] + 1)
+        offs = np.concatenate([[0], np.cumsum(words)]).astype(np.uint64)
+        d_seg, d_mem, d_off = _dev(seg, np.int32), _dev(np.array(members, dtype=np.int32).reshape(-1, 2), np.int32), _dev(offs[:-1], np.uint64)
+        d_out = torch.empty(int(offs[-1]) + 1, dtype=torch.int32, device="cuda")
+        _lib.check(lib.am_group_images(ctypes.byref(view), len(seg), d_seg.data_ptr(), d_mem.data_ptr(), float(segment_threshold),
+                                       d_off.data_ptr(), d_out.data_ptr(), _stream()), "am_group_images")
+        bits = d_out.cpu().numpy().view(np.uint32)
+        for i, (g, s) in enumerate(seg_key):
+            x0, x1, y0, y1 = (int(v) for v in seg[i, :4])
+            images[g].append(unpack_crop(bits[int(offs[i]):int(offs[i + 1])], x0, x1, y0, y1))
+        # kept on the device for frames_from_groups: segment boxes, word offsets, bit-packed images
+        self._group_device = ({k: i for i, k in enumerate(seg_key)}, _dev(seg[:, :4], np.int32), d_off, d_out)
+        return images, bounds
+
+    # ---- :638-681 ---------------------------------------------------------------------------------------------
+    def frames_from_groups(self, cc_groups, group_boundaries, groups_per_frame, group_ages, group_images, save_prefix=None,
+                           stable_min_frames=3, show_unstable=True, chunk=64):
+        """-> list of PNG-encoded clean binary frames (channel 0 of the reference's canvas).  The stable groups are painted on
+        the device from the images compute_group_images left there; `save_prefix` debugging dumps are not supported."""
+        import cv2
+        if save_prefix is not None:
+            raise NotImplementedError("frames_from_groups(save_prefix=...) writes debugging PNGs; only the returned frames are produced here")
+        lib = _lib.lib()
+        dev = getattr(self, "_group_device", None)
+        if dev is None:
+            dev = self._upload_group_images(group_images, group_boundaries)
+        seg_index, d_boxes, d_off, d_imgs = dev
+        seg_of = [0] * len(cc_groups)
+        items = []                                                           # (frame, segment row)
+        for t, present in enumerate(groups_per_frame):
+            for g in present:
+                marks = group_ages[g]
+                while marks[seg_of[g] + 1] < t:
+                    seg_of[g] += 1
+                items.append((t, seg_index[(g, seg_of[g])]))
+        items = np.array(items, dtype=np.int32).reshape(-1, 2)
+        clean, n_frames = [], len(groups_per_frame)
+        for f0 in range(0, n_frames, chunk):
+            nf = min(chunk, n_frames - f0)
+            sel = items[(items[:, 0] >= f0) & (items[:, 0] < f0 + nf)]
+            out = torch.empty(nf * self.height * self.width + 8, dtype=torch.uint8, device="cuda")
+            if len(sel):
+                d_f, d_i = _dev(sel[:, 0], np.int32), _dev(sel[:, 1], np.int32)
+                args = (len(sel), d_f.data_ptr(), d_i.data_ptr(), d_boxes.data_ptr(), d_off.data_ptr(), d_imgs.data_ptr())
+            else:
+                args = (0, None, None, None, None, None)
+            _lib.check(lib.am_paint_frames(*args, f0, nf, self.height, self.width, out.data_ptr(), _stream()), "am_paint_frames")
+            host = out[:nf * self.height * self.width].cpu().numpy().reshape(nf, self.height, self.width)
+            for t in range(nf):
+                clean.append(cv2.imencode(".png", host[t])[1])               # the 03 -> 04 wire format (:677-678)
+        return clean
+
+    def _upload_group_images(self, group_images, group_boundaries):
+        """Group images supplied by the caller (e.g. after unpickling): pack and upload them."""
+        keys, boxes, chunks = [], [], []
+        for g in sorted(group_images):
+            x0, x1, y0, y1 = (int(v) for v in group_boundaries[g])
+            for s, im in enumerate(group_images[g]):
+                keys.append((g, s)); boxes.append((x0, x1, y0, y1)); chunks.append(pack_crop(im, x0, x1, y0, y1))
+        words = np.array([len(c) for c in chunks], dtype=np.int64)
+        offs = np.concatenate([[0], np.cumsum(words)]).astype(np.uint64)
+        imgs = np.concatenate(chunks) if chunks else np.zeros(1, np.uint32)
+        self._group_device = ({k: i for i, k in enumerate(keys)}, _dev(np.array(boxes, dtype=np.int32).reshape(-1, 4), np.int32),
+                              _dev(offs[:-1], np.uint64), _dev(imgs.view(np.int32), np.int32))
+        return self._group_device

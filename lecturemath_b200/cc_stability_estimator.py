@@ -3,15 +3,17 @@ part: __init__, add_frame(img, input_binary=True), finish_processing, get_raw_cc
 and temporal matching all run on the B200 (libaccessmath_b200.so); this class only keeps the Python-visible state
 the reference exposes (unique_cc_objects, unique_cc_frames, cc_idx_per_frame, img_idx, tempo_count ...).
 
-`add_frames(masks)` is the batched fast path (many frames per launch sequence, one read-back per batch)."""
+`add_frames(masks)` is the batched fast path (many frames per launch sequence, one read-back per batch).
+The stage-03 methods (rebuilt_binary_images ... frames_from_groups, :166-681) come from cc_grouping.GroupingMixin."""
 import numpy as np
 import torch
 
 from .cc_engine import CCEngine, Estimator
+from .cc_grouping import GroupingMixin
 from .connected_component import ConnectedComponent
 
 
-class CCStabilityEstimator:
+class CCStabilityEstimator(GroupingMixin):
     def __init__(self, width, height, min_recall, min_precision, max_gap, verbose=False, max_batch=16):
         self.width, self.height = width, height
         self.min_recall, self.min_precision, self.max_gap = min_recall, min_precision, max_gap
@@ -24,6 +26,12 @@ class CCStabilityEstimator:
         self.verbose = verbose
         self._engine = CCEngine(width, height, max_batch)
         self._est = Estimator(width, height, min_recall, min_precision, max_gap)
+
+    def __getstate__(self):
+        """Pickled like the reference object (tempo_stability_*.dat, pre_ST3D_v3.0_02_cc_analaysis.py:43): the Python-visible
+        state only; device handles stay behind and stage 03 re-uploads the packed crops when it runs in another process."""
+        drop = ("_engine", "_est", "_view_cache", "_group_device")
+        return {k: v for k, v in self.__dict__.items() if k not in drop}
 
     def get_raw_cc_count(self):                                          # :33-39
         return sum(len(f) for f in self.cc_idx_per_frame)

@@ -1359,6 +1359,16 @@ extern "C" int am_est_read_unique_crop(am_estimator* e, int u, int words, uint32
     return AM_OK;
 }
 
+extern "C" int am_est_unique_view(am_estimator* e, am_unique_view* out, void* stream) {
+    if (!e || !out) return AM_ERR_ARG;
+    int n = 0;
+    AM_CUDA(cudaMemcpyAsync(&n, e->d_scal, 4, cudaMemcpyDeviceToHost, S(stream)));
+    AM_CUDA(cudaStreamSynchronize(S(stream)));
+    out->min_x = e->u_min_x; out->max_x = e->u_max_x; out->min_y = e->u_min_y; out->max_y = e->u_max_y; out->size = e->u_size;
+    out->crop_off = e->u_crop_off; out->arena = e->arena; out->n = n;
+    return AM_OK;
+}
+
 extern "C" int am_est_export_sizes(am_estimator* e, long long* h_sizes, void* stream) {
     if (!e || !h_sizes) return AM_ERR_ARG;
     k_export_sizes<<<1, 1024, 0, S(stream)>>>(e->act[e->cur], e->d_scal, e->u_min_x, e->u_max_x, e->u_min_y, e->u_max_y, e->d_scal64 + 2);
