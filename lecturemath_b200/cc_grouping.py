@@ -42,6 +42,19 @@ def _crop_words(cc):
 
 
 class GroupingMixin:
+    def _timed(self, name, fn, *args):
+        """Run one C-ABI call; when self.device_ms is a dict (tools/grouping_bench.py) accumulate its CUDA-event time there."""
+        acc = getattr(self, "device_ms", None)
+        if acc is None:
+            return fn(*args)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        e1.synchronize()
+        acc[name] = acc.get(name, 0.0) + e0.elapsed_time(e1)
+        return rc
+
     # ---- device view of the unique CCs ------------------------------------------------------------------------
     def _unique_view(self):
         """(UniqueView, obj_index): obj_index[u] = row of the view that holds unique u's box / crop.  Zero copy while the
@@ -101,7 +114,8 @@ class GroupingMixin:
             args = (len(ccs), d_frame.data_ptr(), d_img.data_ptr(), boxes.data_ptr(), d_off.data_ptr(), imgs.data_ptr())
         else:
             args = (0, None, None, None, None, None)
-        _lib.check(lib.am_paint_frames(*args, 0, n_frames, self.height, self.width, out.data_ptr(), _stream()), "am_paint_frames")
+        _lib.check(self._timed("am_paint_frames", lib.am_paint_frames, *args, 0, n_frames, self.height, self.width, out.data_ptr(), _stream()),
+                   "am_paint_frames")
         host = out[:n_frames * self.height * self.width].cpu().numpy().reshape(n_frames, self.height, self.width)
         return [host[t] for t in range(n_frames)]
 
@@ -148,7 +162,8 @@ class GroupingMixin:
         while True:
             pairs = torch.empty((cap, 3), dtype=torch.int32, device="cuda")
             n = ctypes.c_longlong(0)
-            rc = lib.am_group_overlaps(ctypes.byref(view), d_ids.data_ptr(), len(ids), pairs.data_ptr(), cap, ctypes.byref(n), _stream())
+            rc = self._timed("am_group_overlaps", lib.am_group_overlaps, ctypes.byref(view), d_ids.data_ptr(), len(ids), pairs.data_ptr(), cap,
+                             ctypes.byref(n), _stream())
             if rc == 3:
                 cap = int(n.value)
                 continue
@@ -265,8 +280,8 @@ class GroupingMixin:
         offs = np.concatenate([[0], np.cumsum(words)]).astype(np.uint64)
         d_seg, d_mem, d_off = _dev(seg, np.int32), _dev(np.array(members, dtype=np.int32).reshape(-1, 2), np.int32), _dev(offs[:-1], np.uint64)
         d_out = torch.empty(int(offs[-1]) + 1, dtype=torch.int32, device="cuda")
-        _lib.check(lib.am_group_images(ctypes.byref(view), len(seg), d_seg.data_ptr(), d_mem.data_ptr(), float(segment_threshold),
-                                       d_off.data_ptr(), d_out.data_ptr(), _stream()), "am_group_images")
+        _lib.check(self._timed("am_group_images", lib.am_group_images, ctypes.byref(view), len(seg), d_seg.data_ptr(), d_mem.data_ptr(),
+                               float(segment_threshold), d_off.data_ptr(), d_out.data_ptr(), _stream()), "am_group_images")
         bits = d_out.cpu().numpy().view(np.uint32)
         for i, (g, s) in enumerate(seg_key):
             x0, x1, y0, y1 = (int(v) for v in seg[i, :4])
@@ -307,7 +322,8 @@ class GroupingMixin:
                 args = (len(sel), d_f.data_ptr(), d_i.data_ptr(), d_boxes.data_ptr(), d_off.data_ptr(), d_imgs.data_ptr())
             else:
                 args = (0, None, None, None, None, None)
-            _lib.check(lib.am_paint_frames(*args, f0, nf, self.height, self.width, out.data_ptr(), _stream()), "am_paint_frames")
+            _lib.check(self._timed("am_paint_frames", lib.am_paint_frames, *args, f0, nf, self.height, self.width, out.data_ptr(), _stream()),
+                       "am_paint_frames")
             host = out[:nf * self.height * self.width].cpu().numpy().reshape(nf, self.height, self.width)
             for t in range(nf):
                 clean.append(cv2.imencode(".png", host[t])[1])               # the 03 -> 04 wire format (:677-678)

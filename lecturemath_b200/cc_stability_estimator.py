@@ -30,7 +30,7 @@ class CCStabilityEstimator(GroupingMixin):
     def __getstate__(self):
         """Pickled like the reference object (tempo_stability_*.dat, pre_ST3D_v3.0_02_cc_analaysis.py:43): the Python-visible
         state only; device handles stay behind and stage 03 re-uploads the packed crops when it runs in another process."""
-        drop = ("_engine", "_est", "_view_cache", "_group_device")
+        drop = ("_engine", "_est", "_view_cache", "_group_device", "device_ms")
         return {k: v for k, v in self.__dict__.items() if k not in drop}
 
     def get_raw_cc_count(self):                                          # :33-39

@@ -1,0 +1,74 @@
+"""Stage-03 (CC grouping) timing on dense 1080p masks: the CUDA drop-in's estimator methods next to the CPU oracle
+(= the reference's algorithm) on the same stage-02 state.   python tools/grouping_bench.py [--frames 48] [--no-oracle]
+Prints one JSON line: per-method wall-clock ms (device work is synchronised inside each method by its read-back)."""
+import argparse
+import contextlib
+import io
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def stage03(est, timings):
+    def run(name, fn, *a):
+        t0 = time.perf_counter()
+        with contextlib.redirect_stdout(io.StringIO()), np.errstate(all="ignore"):
+            r = fn(*a)
+        timings[name] = round(1000.0 * (time.perf_counter() - t0), 2)
+        return r
+    run("rebuilt_binary_images", est.rebuilt_binary_images)
+    run("split_stable_cc_by_gaps", est.split_stable_cc_by_gaps, 85, 3)
+    stable = run("get_stable_cc_idxs", est.get_stable_cc_idxs, 3)
+    time_ov, total, all_ov = run("compute_overlapping_stable_cc", est.compute_overlapping_stable_cc, stable, 5)
+    groups, gidx = run("compute_groups", est.compute_groups, stable, time_ov, 0.5, None, None)
+    ages, gpf = run("compute_groups_temporal_information", est.compute_groups_temporal_information, groups)
+    run("compute_conflicting_groups", est.compute_conflicting_groups, stable, all_ov, len(groups), gidx)
+    images, bounds = run("compute_group_images", est.compute_group_images, groups, ages, 0.5)
+    clean = run("frames_from_groups", est.frames_from_groups, groups, bounds, gpf, ages, images, None, 3, True)
+    return {"stable": len(stable), "pairs": sum(len(x) for x in all_ov) // 2, "groups": len(groups),
+            "segments": sum(len(v) for v in images.values()), "frames": len(clean)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--frames", type=int, default=48)
+    ap.add_argument("--no-oracle", action="store_true")
+    args = ap.parse_args()
+    import torch
+    from lecturemath_b200 import synth
+    from lecturemath_b200.cc_stability_estimator import CCStabilityEstimator
+    h, w = 1080, 1920
+    masks = np.stack(list(synth.glyph_masks(args.frames, h, w, seed=0)))
+    est = CCStabilityEstimator(w, h, 0.85, 0.85, 85)
+    est.add_frames(masks)
+    torch.cuda.synchronize()
+    t_gpu = {}
+    stage03(est, {})                                                       # warm-up on a copy of the state would change it: re-run below
+    est = CCStabilityEstimator(w, h, 0.85, 0.85, 85)
+    est.add_frames(masks)
+    torch.cuda.synchronize()
+    est.device_ms = {}
+    info = stage03(est, t_gpu)
+    line = {"workload": "stage 03 on %d dense 1080p glyph-mask frames" % args.frames, **info, "gpu_ms": t_gpu,
+            "gpu_total_ms": round(sum(t_gpu.values()), 1),
+            "device_kernel_ms": {k: round(v, 3) for k, v in est.device_ms.items()}}
+    if not args.no_oracle:
+        from oracle import cc_oracle as CO
+        from oracle.grouping_oracle import GroupingOracle
+        stab = CO.StabilityOracle(w, h, 0.85, 0.85, 85)
+        for m in masks:
+            stab.add_frame(m)
+        t_cpu = {}
+        stage03(GroupingOracle(stab), t_cpu)
+        line["cpu_oracle_ms"] = t_cpu
+        line["cpu_oracle_total_ms"] = round(sum(t_cpu.values()), 1)
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()
