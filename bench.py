@@ -233,19 +233,18 @@ def run_ours(args):
 
     def run_video(n_steps, host_io, timing=None):
         """n_steps batches through the hot path (and the rank ring); returns (d2h bytes, CC rows seen)."""
-        d2h = n_cc = 0
+        n_cc = 0
+        d2h0 = sx.d2h_bytes
         for i in range(n_steps):
             l2_flush.fill_(i & 0xff)                      # L2 flush between timed iterations (activations >> L2 anyway)
             sx.submit(batch_of(pool_h if host_io else pool_d, i), last=(i == n_steps - 1), timing=timing)
             if host_io and i >= 1:
                 rows = sx.collect(i - 1)
-                d2h += sum(r.nbytes for r in rows) + (B + 1) * 4
                 n_cc += sum(len(r) for r in rows)
         if host_io:
             rows = sx.collect(n_steps - 1)
-            d2h += sum(r.nbytes for r in rows) + (B + 1) * 4
             n_cc += sum(len(r) for r in rows)
-        return d2h, n_cc
+        return sx.d2h_bytes - d2h0, n_cc                   # bytes collect() actually copied device -> host
 
     # warm-up (also initialises the NCCL ring)
     run_video(Wm, False)

@@ -8,7 +8,9 @@ methods, same arguments, same result shapes.  All pixel work runs on the B200 ov
 stage 02 left in HBM (csrc/grouping.cu: am_group_overlaps, am_group_images, am_paint_frames); what stays here is the
 order-dependent list / dictionary bookkeeping whose ORDER is part of the reference's result (group numbering, list order).
 There is no CPU path for the pixel work: without the library / a device these methods raise."""
+import bisect
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -92,10 +94,20 @@ class GroupingMixin:
     # ---- :166-179 ---------------------------------------------------------------------------------------------
     def rebuilt_binary_images(self, chunk=64):
         out = []
+        tables = getattr(self, "_frame_tables", None)
+        fast = tables is not None and len(tables) == len(self.cc_idx_per_frame)
         for f0 in range(0, len(self.cc_idx_per_frame), chunk):
             rows = self.cc_idx_per_frame[f0:f0 + chunk]
-            ccs = [(t, cc) for t, row in enumerate(rows) for _, cc in row]
-            out.extend(self._paint(len(rows), [t for t, _ in ccs], [c for _, c in ccs]))
+            if fast:                                                  # the per-frame tables exactly as stage 02 read them back
+                tb = tables[f0:f0 + chunk]
+                base = np.concatenate([[0], np.cumsum([len(t[2]) for t in tb])])
+                out.extend(self._paint_arrays(len(rows), np.repeat(np.arange(len(tb)), [len(t[0]) for t in tb]),
+                                              np.concatenate([t[0] for t in tb]).reshape(-1, 4),
+                                              np.concatenate([t[1] + np.uint64(b) for t, b in zip(tb, base[:-1])]),
+                                              np.concatenate([t[2] for t in tb])))
+            else:
+                ccs = [(t, cc) for t, row in enumerate(rows) for _, cc in row]
+                out.extend(self._paint(len(rows), [t for t, _ in ccs], [c for _, c in ccs]))
         return out
 
     def rebuilt_binary_frame(self, frame_ccs):
@@ -103,15 +115,22 @@ class GroupingMixin:
 
     def _paint(self, n_frames, item_frame, ccs):
         """uint8 frames with `+= 255` at every set pixel of every (frame, crop) item -- am_paint_frames."""
+        if not ccs:
+            return self._paint_arrays(n_frames, np.zeros(0, np.int32), np.zeros((0, 4), np.int32), np.zeros(0, np.uint64), np.zeros(1, np.uint32))
+        words = np.array([_crop_words(c) for c in ccs], dtype=np.int64)
+        offs = np.concatenate([[0], np.cumsum(words)])[:-1].astype(np.uint64)
+        boxes = np.array([(int(c.min_x), int(c.max_x), int(c.min_y), int(c.max_y)) for c in ccs], dtype=np.int32)
+        return self._paint_arrays(n_frames, item_frame, boxes, offs, np.concatenate([_packed(c) for c in ccs]))
+
+    def _paint_arrays(self, n_frames, item_frame, boxes, offs, imgs):
         lib = _lib.lib()
         out = torch.empty(n_frames * self.height * self.width + 8, dtype=torch.uint8, device="cuda")
-        if ccs:
-            words = np.array([_crop_words(c) for c in ccs], dtype=np.int64)
-            offs = np.concatenate([[0], np.cumsum(words)])[:-1].astype(np.uint64)
-            imgs = _dev(np.concatenate([_packed(c) for c in ccs]).view(np.int32), np.int32)
-            boxes = _dev([(int(c.min_x), int(c.max_x), int(c.min_y), int(c.max_y)) for c in ccs], np.int32)
-            d_frame, d_img, d_off = _dev(item_frame, np.int32), _dev(np.arange(len(ccs)), np.int32), _dev(offs, np.uint64)
-            args = (len(ccs), d_frame.data_ptr(), d_img.data_ptr(), boxes.data_ptr(), d_off.data_ptr(), imgs.data_ptr())
+        n = len(boxes)
+        if n:
+            d_imgs = _dev(np.ascontiguousarray(imgs).view(np.int32), np.int32)
+            d_boxes, d_frame = _dev(boxes, np.int32), _dev(item_frame, np.int32)
+            d_img, d_off = _dev(np.arange(n), np.int32), _dev(offs, np.uint64)
+            args = (n, d_frame.data_ptr(), d_img.data_ptr(), d_boxes.data_ptr(), d_off.data_ptr(), d_imgs.data_ptr())
         else:
             args = (0, None, None, None, None, None)
         _lib.check(self._timed("am_paint_frames", lib.am_paint_frames, *args, 0, n_frames, self.height, self.width, out.data_ptr(), _stream()),
@@ -176,19 +195,25 @@ class GroupingMixin:
     def compute_overlapping_stable_cc(self, stable_idxs, temporal_window):
         n = len(self.unique_cc_objects)
         all_ov, time_ov, total = [[] for _ in range(n)], [[] for _ in range(n)], 0
-        first = [f[0][0] for f in self.unique_cc_frames]
-        last = [f[-1][0] for f in self.unique_cc_frames]
-        for u1, u2, match in self.stable_overlaps_device(stable_idxs).tolist():
-            if match == 0:                                                   # recall == precision == 0.0 (:283)
-                continue
-            s1, s2 = self.unique_cc_objects[u1].size, self.unique_cc_objects[u2].size
-            recall, precision = match / float(s1), match / float(s2)        # connected_component.py:239-240 (fp64)
-            matched = int(s1 * recall)                                       # :284
-            all_ov[u1].append((u2, matched, s2, s1))
-            all_ov[u2].append((u1, matched, s1, s2))
-            if last[u1] + temporal_window >= first[u2] and last[u2] >= first[u1] - temporal_window:
-                time_ov[u1].append((u2, recall, precision))
-                time_ov[u2].append((u1, precision, recall))
+        p = self.stable_overlaps_device(stable_idxs)
+        p = p[p[:, 2] > 0]                                                   # recall == precision == 0.0 otherwise (:283)
+        if len(p) == 0:
+            return time_ov, total, all_ov
+        size = np.fromiter((int(c.size) for c in self.unique_cc_objects), dtype=np.int64, count=n)
+        first = np.fromiter((f[0][0] for f in self.unique_cc_frames), dtype=np.int64, count=n)
+        last = np.fromiter((f[-1][0] for f in self.unique_cc_frames), dtype=np.int64, count=n)
+        s1, s2 = size[p[:, 0]], size[p[:, 1]]
+        recall = p[:, 2] / s1.astype(np.float64)                             # connected_component.py:239-240 (IEEE fp64 divide)
+        precision = p[:, 2] / s2.astype(np.float64)
+        matched = (s1 * recall).astype(np.int64)                             # :284  int(cc1.size * recall): fp64 product, truncated
+        in_time = (last[p[:, 0]] + temporal_window >= first[p[:, 1]]) & (last[p[:, 1]] >= first[p[:, 0]] - temporal_window)
+        for u1, u2, m, a, b, r, q, t in zip(p[:, 0].tolist(), p[:, 1].tolist(), matched.tolist(), s1.tolist(), s2.tolist(),
+                                            recall.tolist(), precision.tolist(), in_time.tolist()):
+            all_ov[u1].append((u2, m, b, a))
+            all_ov[u2].append((u1, m, a, b))
+            if t:
+                time_ov[u1].append((u2, r, q))
+                time_ov[u2].append((u1, q, r))
                 total += 1
         return time_ov, total, all_ov
 
@@ -261,12 +286,12 @@ class GroupingMixin:
             ccs = [self.unique_cc_objects[u] for u in grp]
             box = (min(c.min_x for c in ccs), max(c.max_x for c in ccs), min(c.min_y for c in ccs), max(c.max_y for c in ccs))
             bounds[g] = box
-            times = [np.fromiter((t for t, _ in self.unique_cc_frames[u]), dtype=np.int64) for u in grp]
+            times = [[t for t, _ in self.unique_cc_frames[u]] for u in grp]  # ascending frame indices
             marks = group_ages[g]
             for s, (t0, t1) in enumerate(zip(marks[:-1], marks[1:])):
                 begin = len(members)
                 for u, ts in zip(grp, times):
-                    seen = int(np.count_nonzero((ts >= t0) & (ts <= t1)))
+                    seen = bisect.bisect_right(ts, t1) - bisect.bisect_left(ts, t0)      # frames of u inside [t0, t1] (:607)
                     if seen:
                         members.append((int(obj_index[u]), seen))
                 seg_rows.append(tuple(int(v) for v in box) + (begin, len(members)))
@@ -282,10 +307,15 @@ class GroupingMixin:
         d_out = torch.empty(int(offs[-1]) + 1, dtype=torch.int32, device="cuda")
         _lib.check(self._timed("am_group_images", lib.am_group_images, ctypes.byref(view), len(seg), d_seg.data_ptr(), d_mem.data_ptr(),
                                float(segment_threshold), d_off.data_ptr(), d_out.data_ptr(), _stream()), "am_group_images")
-        bits = d_out.cpu().numpy().view(np.uint32)
+        # one unpack for all segments (format conversion only: bit-packed -> the reference's uint8 0/255 arrays)
+        px = np.unpackbits(d_out[:int(offs[-1])].cpu().numpy().view(np.uint8), bitorder="little")
+        px *= np.uint8(255)
+        cws = ((seg[:, 1] >> 5) - (seg[:, 0] >> 5) + 1) * 32
+        lead = seg[:, 0] & 31
         for i, (g, s) in enumerate(seg_key):
-            x0, x1, y0, y1 = (int(v) for v in seg[i, :4])
-            images[g].append(unpack_crop(bits[int(offs[i]):int(offs[i + 1])], x0, x1, y0, y1))
+            a, b = int(offs[i]) * 32, int(offs[i + 1]) * 32
+            x0 = int(lead[i])
+            images[g].append(np.ascontiguousarray(px[a:b].reshape(-1, int(cws[i]))[:, x0:x0 + int(seg[i, 1] - seg[i, 0]) + 1]))
         # kept on the device for frames_from_groups: segment boxes, word offsets, bit-packed images
         self._group_device = ({k: i for i, k in enumerate(seg_key)}, _dev(seg[:, :4], np.int32), d_off, d_out)
         return images, bounds
@@ -313,6 +343,8 @@ class GroupingMixin:
                 items.append((t, seg_index[(g, seg_of[g])]))
         items = np.array(items, dtype=np.int32).reshape(-1, 2)
         clean, n_frames = [], len(groups_per_frame)
+        from concurrent.futures import ThreadPoolExecutor
+        pool = ThreadPoolExecutor(max_workers=max(1, min(16, os.cpu_count() or 1)))
         for f0 in range(0, n_frames, chunk):
             nf = min(chunk, n_frames - f0)
             sel = items[(items[:, 0] >= f0) & (items[:, 0] < f0 + nf)]
@@ -325,8 +357,9 @@ class GroupingMixin:
             _lib.check(self._timed("am_paint_frames", lib.am_paint_frames, *args, f0, nf, self.height, self.width, out.data_ptr(), _stream()),
                        "am_paint_frames")
             host = out[:nf * self.height * self.width].cpu().numpy().reshape(nf, self.height, self.width)
-            for t in range(nf):
-                clean.append(cv2.imencode(".png", host[t])[1])               # the 03 -> 04 wire format (:677-678)
+            # the 03 -> 04 wire format (:677-678) stays cv2's PNG; the encoder releases the GIL, so frames encode in parallel
+            clean.extend(pool.map(lambda fr: cv2.imencode(".png", fr)[1], [host[t] for t in range(nf)]))
+        pool.shutdown()
         return clean
 
     def _upload_group_images(self, group_images, group_boundaries):

@@ -26,11 +26,12 @@ class CCStabilityEstimator(GroupingMixin):
         self.verbose = verbose
         self._engine = CCEngine(width, height, max_batch)
         self._est = Estimator(width, height, min_recall, min_precision, max_gap)
+        self._frame_tables = []          # per frame: (boxes int32 [n][4], crop word offsets, the frame's packed crops) as the GPU returned them
 
     def __getstate__(self):
         """Pickled like the reference object (tempo_stability_*.dat, pre_ST3D_v3.0_02_cc_analaysis.py:43): the Python-visible
         state only; device handles stay behind and stage 03 re-uploads the packed crops when it runs in another process."""
-        drop = ("_engine", "_est", "_view_cache", "_group_device", "device_ms")
+        drop = ("_engine", "_est", "_view_cache", "_group_device", "device_ms", "_frame_tables")
         return {k: v for k, v in self.__dict__.items() if k not in drop}
 
     def get_raw_cc_count(self):                                          # :33-39
@@ -70,6 +71,8 @@ class CCStabilityEstimator(GroupingMixin):
 
     def _absorb(self, rows, crops):
         current = []
+        self._frame_tables.append((np.ascontiguousarray(rows[:, 2:6]), rows[:, 7].astype(np.uint64),
+                                   crops if crops is not None else np.zeros(1, np.uint32)))
         for r in rows:
             u, lab, x0, x1, y0, y1, size, off = (int(v) for v in r)
             words = ((x1 >> 5) - (x0 >> 5) + 1) * (y1 - y0 + 1)

@@ -184,6 +184,11 @@ class StreamingExtractor:
         # the kernels of batch s-1 (the copy engines are free even while the persistent conv kernels own every SM)
         self.inbuf = [self.frames_in, torch.empty_like(self.frames_in)]
         self.copy_stream = torch.cuda.Stream(self.device)
+        # results leave through their own stream into pinned buffers: a read-back enqueued on the compute stream would queue up
+        # BEHIND the next batch's kernels and stall the host for a whole step
+        self.d2h_stream = torch.cuda.Stream(self.device)
+        self.rows_h = [torch.zeros((row_capacity, 8), dtype=torch.int32).pin_memory() for _ in range(depth)]
+        self.offs_h = [torch.zeros((batch + 1,), dtype=torch.int32).pin_memory() for _ in range(depth)]
         self.ev_in_ready = [torch.cuda.Event() for _ in range(2)]
         self.ev_in_free = [None, None]
         self.engines = [CCEngine(width, height, batch, device=self.device) for _ in range(depth)]
@@ -200,6 +205,7 @@ class StreamingExtractor:
             self.buf_recv = torch.zeros(handoff_words, dtype=torch.int32, device=self.device)
         self.step = 0
         self.launches = 0
+        self.d2h_bytes = 0               # bytes collect() has copied device -> host
 
     def submit(self, frames, last=False, timing=None):
         """Enqueue one batch (uint8 (batch,H,W,3) BGR; pinned host or device tensor).  `last`: no further batch follows on
@@ -272,12 +278,21 @@ class StreamingExtractor:
         """Result rows of batch s on the host: list (per frame) of int32 [n_cc][7] = (unique_idx, raw_label, min_x, max_x,
         min_y, max_y, size).  Must be called before batch s + depth is submitted."""
         k = s % self.depth
-        self.ev_matched[k].synchronize()
-        offs = self.offs[k].cpu().numpy()
-        total = int(offs[-1])
-        if total > self.rows[k].shape[0]:
-            raise RuntimeError("result rows exceed row_capacity (%d > %d)" % (total, self.rows[k].shape[0]))
-        rows = self.rows[k][:total].cpu().numpy()
+        first = min(1024, self.rows[k].shape[0])                          # typical batches fit one round trip
+        with torch.cuda.stream(self.d2h_stream):
+            self.d2h_stream.wait_event(self.ev_matched[k])
+            self.offs_h[k].copy_(self.offs[k], non_blocking=True)
+            self.rows_h[k][:first].copy_(self.rows[k][:first], non_blocking=True)
+            self.d2h_stream.synchronize()
+            offs = self.offs_h[k].numpy().copy()
+            total = int(offs[-1])
+            if total > self.rows[k].shape[0]:
+                raise RuntimeError("result rows exceed row_capacity (%d > %d)" % (total, self.rows[k].shape[0]))
+            if total > first:
+                self.rows_h[k][first:total].copy_(self.rows[k][first:total], non_blocking=True)
+                self.d2h_stream.synchronize()
+        rows = self.rows_h[k][:total].numpy().copy()
+        self.d2h_bytes += offs.nbytes + 32 * max(first, total)
         return [rows[offs[f]:offs[f + 1], :7] for f in range(self.batch)]
 
     def finish(self):
