@@ -248,6 +248,14 @@ int am_paint_frames(int n_items, const int* d_item_frame, const int* d_item_img,
                     const unsigned long long* d_img_off, const uint32_t* d_imgs, int frame0, int n_frames, int height, int width,
                     uint8_t* d_out, void* stream);
 
+/* ===== 8. Wire format 01 -> 02 written on the device ========================================
+ * Replaces cv2.imencode(".png", binary) (R/AccessMath/preprocessing/video_worker/FCN_lecturenet_binarizer.py:56); the reader stays
+ * cv2.imdecode(raw, IMREAD_GRAYSCALE) (R/AccessMath/preprocessing/content/helper.py:31).  The file is a 1-bit grayscale PNG
+ * (ink = white), filter 0, zlib stored blocks: it decodes to the same 0 / 255 pixels as the reference's file. */
+long long am_png1_size(int width, int height);          /* bytes per frame (fixed for a frame size); host-only helper */
+/* d_bits [batch][height][am_words_per_row(width)] -> d_out [batch][am_png1_size(width, height)] */
+int am_png1_encode(const uint32_t* d_bits, int batch, int height, int width, uint8_t* d_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,7 +7,11 @@ import numpy as np
 
 
 class FCN_LectureNet_Binarizer:
-    def __init__(self, lecture_net, keep_others=True):
+    def __init__(self, lecture_net, keep_others=True, png="device"):
+        """png: "device" = the PNG bytes of compressed_frames are written on the GPU from the bit-packed mask (csrc/png.cu: 1-bit
+        grayscale, stored deflate; decodes to the same pixels), "cv2" = cv2.imencode on the host as the reference does (:56)."""
+        self.png = png
+        self._png_encoder = None
         self.width = self.height = 0
         self.frame_count = 0
         self.lecture_net = lecture_net
@@ -36,7 +40,13 @@ class FCN_LectureNet_Binarizer:
         # frames above 2.5 MP: binarize_frames halves them (LANCZOS) and resizes the mask back (NEAREST) on the device
         plan = net.binarize_frames(np.ascontiguousarray(frame)[None], want_others=self.keep_others)
         binary, text_mask, rec_img = net.masks_from_plan(plan, 0, self.keep_others)
-        flag, raw_data = cv2.imencode(".png", binary)
+        if self.png == "device":
+            if self._png_encoder is None or (self._png_encoder.width, self._png_encoder.height) != (w, h):
+                from .wire import PngEncoder
+                self._png_encoder = PngEncoder(w, h, 1, plan.bits.device)
+            raw_data = self._png_encoder.encode(plan.bits[:1])[0]
+        else:
+            flag, raw_data = cv2.imencode(".png", binary)
         self.last_binary, self.last_text, self.last_rec = binary, text_mask, rec_img
         self.compressed_frames.append(raw_data)
         self.frame_indices.append(abs_frame_idx)
