@@ -5,7 +5,7 @@
 // cv2.imdecode(raw, IMREAD_GRAYSCALE) (R/AccessMath/preprocessing/content/helper.py:31).  am_png1_encode writes, straight from the
 // bit-packed ink mask the FCN epilogue produced, a PNG every decoder expands to the same 0 / 255 pixels:
 //   1-bit grayscale (ink = 1 = white), filter type 0, one IDAT chunk holding a zlib stream of "stored" deflate blocks.
-// One CTA per frame: scanline bytes are bit-reversed mask bytes (PNG packs the leftmost pixel into the MSB), Adler-32 is a
+// Two launches per batch: scanline bytes are bit-reversed mask bytes (PNG packs the leftmost pixel into the MSB), Adler-32 is a
 // block reduction of two 64-bit sums, CRC-32 is computed per 1024th of the chunk by table lookup and the partial CRCs are
 // merged by a shared-memory tree with precomputed GF(2) shift matrices (the crc32_combine construction).  HBM-bound: reads
 // W*H/8 bytes, writes W*H/8 + H + 77 bytes per frame (260 KB at 1080p, against 40-450 KB for cv2's deflate).
@@ -110,42 +110,43 @@ __device__ __forceinline__ uint32_t gf2_times_dev(const uint32_t* __restrict__ m
     return sum;
 }
 
+constexpr int kSliceBlocks = 16;                 // CTAs per frame in the scanline kernel
+
+// Kernel A, grid (kSliceBlocks, frames): file header, stored-block headers, scanline bytes of this CTA's slice of the raw stream and
+// its Adler-32 partial sums  (A = 1 + sum d_i,  B = n + sum (n - i) d_i  mod 65521)  ->  partial[frame][slice] = (sum d, sum (n - i) d)
 __global__ void __launch_bounds__(kThreads)
-k_png1_encode(const uint32_t* __restrict__ bits, const PngArgs a, const uint32_t* __restrict__ tables, uint8_t* __restrict__ out) {
-    __shared__ uint32_t s_tab[256];
-    __shared__ uint32_t s_mat[kLevels * 32];
+k_png1_scanlines(const uint32_t* __restrict__ bits, const PngArgs a, uint8_t* __restrict__ out, unsigned long long* __restrict__ partial) {
     __shared__ unsigned long long s_red[2][32];
-    __shared__ uint32_t s_crc[kThreads];
-    const int f = blockIdx.x, tid = threadIdx.x;
+    const int f = blockIdx.y, tid = threadIdx.x;
     const uint32_t* fb = bits + (size_t)f * a.H * a.WPR;
     uint8_t* o = out + (size_t)f * a.total;
-    if (tid < 256) s_tab[tid] = tables[tid];
-    if (tid < kLevels * 32) s_mat[tid] = tables[256 + tid];
-    if (tid < 41) o[tid] = a.head[tid];
     uint8_t* z = o + 41;                                              // zlib stream
-    if (tid == 0) { z[0] = 0x78; z[1] = 0x01; }
-    // stored-block headers: BFINAL, LEN, ~LEN (little endian)
-    for (long long b = tid; b < a.n_blocks; b += kThreads) {
-        const long long start = b * 65535, len = min(65535LL, a.raw - start);
-        uint8_t* h = z + 2 + start + 5 * b;
-        h[0] = (b == a.n_blocks - 1) ? 1 : 0;
-        h[1] = (uint8_t)(len & 0xFF); h[2] = (uint8_t)(len >> 8); h[3] = (uint8_t)(~len & 0xFF); h[4] = (uint8_t)((~len >> 8) & 0xFF);
+    if (blockIdx.x == 0) {
+        if (tid < 41) o[tid] = a.head[tid];
+        if (tid == 0) { z[0] = 0x78; z[1] = 0x01; }
+        for (long long b = tid; b < a.n_blocks; b += kThreads) {      // stored-block headers: BFINAL, LEN, ~LEN (little endian)
+            const long long start = b * 65535, len = min(65535LL, a.raw - start);
+            uint8_t* h = z + 2 + start + 5 * b;
+            h[0] = (b == a.n_blocks - 1) ? 1 : 0;
+            h[1] = (uint8_t)(len & 0xFF); h[2] = (uint8_t)(len >> 8); h[3] = (uint8_t)(~len & 0xFF); h[4] = (uint8_t)((~len >> 8) & 0xFF);
+        }
     }
-    // scanlines + Adler-32 partial sums:  A = 1 + sum d_i,  B = n + sum (n - i) d_i   (mod 65521)
     unsigned long long sa = 0, sb = 0;
     const int last_bits = a.W & 7;
-    for (long long r = tid; r < a.raw; r += kThreads) {
-        const int y = (int)(r / a.row_bytes), c = (int)(r - (long long)y * a.row_bytes);
+    const unsigned raw = (unsigned)a.raw, rb = (unsigned)a.row_bytes;  // raw < 2^31 (checked on the host): 32-bit index arithmetic
+    const unsigned per = (raw + gridDim.x - 1) / gridDim.x, r0 = blockIdx.x * per, r1 = min(raw, r0 + per);
+    for (unsigned r = r0 + tid; r < r1; r += kThreads) {
+        const unsigned y = r / rb, c = r - y * rb;
         uint32_t d = 0;
         if (c > 0) {
-            const int k = c - 1;                                      // byte k of the row = pixels 8k .. 8k+7
+            const unsigned k = c - 1;                                 // byte k of the row = pixels 8k .. 8k+7
             d = (fb[(size_t)y * a.WPR + (k >> 2)] >> (8 * (k & 3))) & 0xFFu;
-            if (last_bits && k == a.row_bytes - 2) d &= (1u << last_bits) - 1u;
+            if (last_bits && k == rb - 2) d &= (1u << last_bits) - 1u;
             d = __brev(d) >> 24;                                      // leftmost pixel into the most significant bit
         }
-        z[2 + r + 5 * (r / 65535 + 1)] = (uint8_t)d;
+        z[2 + r + 5 * (r / 65535u + 1)] = (uint8_t)d;
         sa += d;
-        sb += (unsigned long long)(a.raw - r) * d;
+        sb += (unsigned long long)(raw - r) * d;
     }
     for (int off = 16; off; off >>= 1) {                              // 64-bit warp reductions
         sa += __shfl_down_sync(0xffffffffu, sa, off);
@@ -154,14 +155,34 @@ k_png1_encode(const uint32_t* __restrict__ bits, const PngArgs a, const uint32_t
     if ((tid & 31) == 0) { s_red[0][tid >> 5] = sa; s_red[1][tid >> 5] = sb; }
     __syncthreads();
     if (tid == 0) {
+        unsigned long long A = 0, B = 0;
+        for (int w = 0; w < kThreads / 32; ++w) { A += s_red[0][w]; B += s_red[1][w]; }
+        partial[2 * ((size_t)f * gridDim.x + blockIdx.x)] = A;
+        partial[2 * ((size_t)f * gridDim.x + blockIdx.x) + 1] = B;
+    }
+}
+
+// Kernel B, one CTA per frame: Adler-32 from the partial sums, then CRC-32 of "IDAT" + data (thread e, counted from the END of
+// the region, owns bytes [end - (e+1) seg, end - e seg); partial CRCs merged by a tree of zero-shift matrices), then IEND.
+__global__ void __launch_bounds__(kThreads)
+k_png1_checksums(const PngArgs a, const uint32_t* __restrict__ tables, const unsigned long long* __restrict__ partial, int n_slices,
+                 uint8_t* __restrict__ out) {
+    __shared__ uint32_t s_tab[256];
+    __shared__ uint32_t s_mat[kLevels * 32];
+    __shared__ uint32_t s_crc[kThreads];
+    const int f = blockIdx.x, tid = threadIdx.x;
+    uint8_t* o = out + (size_t)f * a.total;
+    uint8_t* z = o + 41;
+    if (tid < 256) s_tab[tid] = tables[tid];
+    if (tid < kLevels * 32) s_mat[tid] = tables[256 + tid];
+    if (tid == 0) {
         unsigned long long A = 1, B = (unsigned long long)(a.raw % 65521);
-        for (int w = 0; w < kThreads / 32; ++w) { A += s_red[0][w]; B = (B + s_red[1][w] % 65521) % 65521; }
+        for (int w = 0; w < n_slices; ++w) { A += partial[2 * ((size_t)f * n_slices + w)]; B = (B + partial[2 * ((size_t)f * n_slices + w) + 1] % 65521) % 65521; }
         const uint32_t adler = (uint32_t)((B % 65521) << 16) | (uint32_t)(A % 65521);
         uint8_t* p = z + a.zlen - 4;
         p[0] = adler >> 24; p[1] = adler >> 16; p[2] = adler >> 8; p[3] = adler;
     }
     __syncthreads();                                                  // the whole chunk is in place (block-scope visibility)
-    // CRC-32 of "IDAT" + data: thread e (counted from the END of the region) owns bytes [end - (e+1) seg, end - e seg)
     const long long crc_len = 4 + a.zlen;
     const uint8_t* reg = o + 37;                                      // "IDAT"
     {
@@ -171,7 +192,15 @@ k_png1_encode(const uint32_t* __restrict__ bits, const PngArgs a, const uint32_t
         if (hi > 0) {
             if (lo < 0) lo = 0;
             c = 0xFFFFFFFFu;
-            for (long long i = lo; i < hi; ++i) c = s_tab[(c ^ reg[i]) & 0xFFu] ^ (c >> 8);
+            long long i = lo;
+            for (; i + 8 <= hi; i += 8) {                             // the eight loads do not depend on the CRC chain
+                uint32_t b[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) b[j] = reg[i + j];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) c = s_tab[(c ^ b[j]) & 0xFFu] ^ (c >> 8);
+            }
+            for (; i < hi; ++i) c = s_tab[(c ^ reg[i]) & 0xFFu] ^ (c >> 8);
             c ^= 0xFFFFFFFFu;
         }
         s_crc[e] = c;
@@ -213,12 +242,30 @@ extern "C" int am_png1_encode(const uint32_t* d_bits, int batch, int height, int
     PngPlan* p = nullptr;
     int rc = png_plan(width, height, &p);
     if (rc) return rc;
-    if (p->zlen > 0x7FFFFFFFLL) return AM_ERR_ARG;                    // chunk length field
+    if (p->zlen > 0x7FFFFFFFLL) return AM_ERR_ARG;                    // chunk length field; also keeps raw < 2^31
     PngArgs a;
     a.W = p->W; a.H = p->H; a.WPR = p->WPR; a.row_bytes = p->row_bytes; a.seg = p->seg;
     a.raw = p->raw; a.n_blocks = p->n_blocks; a.zlen = p->zlen; a.total = p->total;
     memcpy(a.head, p->head, 41);
-    k_png1_encode<<<batch, kThreads, 0, (cudaStream_t)stream>>>(d_bits, a, p->d_tables, d_out);
+    // scratch for the Adler partial sums: cached per device, grown on demand (stream-ordered use only)
+    static std::mutex mu;
+    static std::map<int, std::pair<unsigned long long*, int>> scratch;
+    unsigned long long* d_partial = nullptr;
+    {
+        int dev = 0;
+        AM_CUDA(cudaGetDevice(&dev));
+        std::lock_guard<std::mutex> lk(mu);
+        auto& sc = scratch[dev];
+        if (sc.second < batch) {
+            if (sc.first) cudaFree(sc.first);
+            sc.first = nullptr; sc.second = 0;
+            AM_CUDA(cudaMalloc(&sc.first, (size_t)batch * kSliceBlocks * 2 * sizeof(unsigned long long)));
+            sc.second = batch;
+        }
+        d_partial = sc.first;
+    }
+    k_png1_scanlines<<<dim3(kSliceBlocks, batch), kThreads, 0, (cudaStream_t)stream>>>(d_bits, a, d_out, d_partial);
+    k_png1_checksums<<<batch, kThreads, 0, (cudaStream_t)stream>>>(a, p->d_tables, d_partial, kSliceBlocks, d_out);
     AM_CUDA(cudaGetLastError());
     return AM_OK;
 }

@@ -146,17 +146,28 @@ __device__ __forceinline__ int clip8(int acc) {
 }
 
 // One CTA = one kTH x kTW output tile of one frame.  Shared memory: the input window (rows x row_bytes, loaded as aligned
-// 32-bit words) and the horizontally resampled window (rows x kTW*C uint8).
+// 32-bit words), the horizontally resampled window (rows x kTW*C uint8) and the tile's coefficient rows of both axes.
+// Horizontal pass: thread = (window row, output x), all C channels -- one coefficient load feeds C multiply-adds.
+template <int C>
 __global__ void __launch_bounds__(kThreads)
-k_lanczos_resize(const uint8_t* __restrict__ in, int lead, long long total_bytes, int in_h, int in_w, int C,
+k_lanczos_resize(const uint8_t* __restrict__ in, int lead, long long total_bytes, int in_h, int in_w,
                  const int* __restrict__ bx, const int* __restrict__ kx, int ksx,
                  const int* __restrict__ by, const int* __restrict__ ky, int ksy,
                  int out_h, int out_w, uint8_t* __restrict__ out, int win_words, int win_rows) {
     extern __shared__ uint32_t smem[];
     uint32_t* win = smem;                                              // [win_rows][win_words]
-    uint8_t* hbuf = (uint8_t*)(smem + (size_t)win_rows * win_words);   // [win_rows][kTW * C]
+    int* s_kx = (int*)(smem + (size_t)win_rows * win_words);           // [kTW][ksx]
+    int* s_ky = s_kx + kTW * ksx;                                      // [kTH][ksy]
+    int* s_bx = s_ky + kTH * ksy;                                      // [kTW][2]
+    int* s_by = s_bx + 2 * kTW;                                        // [kTH][2]
+    uint8_t* hbuf = (uint8_t*)(s_by + 2 * kTH);                        // [win_rows][kTW * C]
     const int f = blockIdx.z, oy0 = blockIdx.y * kTH, ox0 = blockIdx.x * kTW;
     const int oy1 = min(oy0 + kTH, out_h), ox1 = min(ox0 + kTW, out_w);
+    const int tw = ox1 - ox0, th = oy1 - oy0;
+    for (int i = threadIdx.x; i < tw * ksx; i += kThreads) s_kx[i] = kx[(size_t)ox0 * ksx + i];
+    for (int i = threadIdx.x; i < th * ksy; i += kThreads) s_ky[i] = ky[(size_t)oy0 * ksy + i];
+    for (int i = threadIdx.x; i < 2 * tw; i += kThreads) s_bx[i] = bx[2 * ox0 + i];
+    for (int i = threadIdx.x; i < 2 * th; i += kThreads) s_by[i] = by[2 * oy0 + i];
     // input window of this tile (bounds are monotone in the output index)
     const int x_lo = bx[2 * ox0], x_hi = bx[2 * (ox1 - 1)] + bx[2 * (ox1 - 1) + 1];
     const int y_lo = by[2 * oy0], y_hi = by[2 * (oy1 - 1)] + by[2 * (oy1 - 1) + 1];
@@ -180,28 +191,146 @@ k_lanczos_resize(const uint8_t* __restrict__ in, int lead, long long total_bytes
     }
     __syncthreads();
     // phase 1: horizontal pass -> hbuf (uint8, as ImagingResampleHorizontal_8bpc)
-    const int tw = ox1 - ox0, twc = tw * C;
-    for (int i = threadIdx.x; i < rows * twc; i += kThreads) {
-        const int r = i / twc, j = i - r * twc, ox = j / C, c = j - ox * C;
-        const int xmin = bx[2 * (ox0 + ox)], n = bx[2 * (ox0 + ox) + 1];
-        const int* k = kx + (size_t)(ox0 + ox) * ksx;
+    for (int i = threadIdx.x; i < rows * tw; i += kThreads) {
+        const int r = i / tw, ox = i - r * tw;
+        const int xmin = s_bx[2 * ox], n = s_bx[2 * ox + 1];
+        const int* k = s_kx + ox * ksx;
         const long long b0 = frame0 + ((long long)(y_lo + r) * in_w + x_lo) * C;
-        const uint8_t* row = (const uint8_t*)(win + (size_t)r * win_words) + (int)(b0 & 3) + (xmin - x_lo) * C + c;
-        int acc = 1 << (kPrecisionBits - 1);
-        for (int t = 0; t < n; ++t) acc += (int)row[t * C] * k[t];
-        hbuf[(size_t)r * (kTW * C) + j] = (uint8_t)clip8(acc);
+        const uint8_t* px = (const uint8_t*)(win + (size_t)r * win_words) + (int)(b0 & 3) + (xmin - x_lo) * C;
+        int acc[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) acc[c] = 1 << (kPrecisionBits - 1);
+#pragma unroll 4
+        for (int t = 0; t < n; ++t) {
+            const int kt = k[t];
+#pragma unroll
+            for (int c = 0; c < C; ++c) acc[c] += (int)px[t * C + c] * kt;
+        }
+        uint8_t* dst = hbuf + (size_t)r * (kTW * C) + ox * C;
+#pragma unroll
+        for (int c = 0; c < C; ++c) dst[c] = (uint8_t)clip8(acc[c]);
     }
     __syncthreads();
     // phase 2: vertical pass (ImagingResampleVertical_8bpc), coalesced row-segment stores
-    const int th = oy1 - oy0;
+    const int twc = tw * C;
     for (int i = threadIdx.x; i < th * twc; i += kThreads) {
         const int oy = i / twc, j = i - oy * twc;
-        const int ymin = by[2 * (oy0 + oy)], n = by[2 * (oy0 + oy) + 1];
-        const int* k = ky + (size_t)(oy0 + oy) * ksy;
+        const int ymin = s_by[2 * oy], n = s_by[2 * oy + 1];
+        const int* k = s_ky + oy * ksy;
         const uint8_t* col = hbuf + (size_t)(ymin - y_lo) * (kTW * C) + j;
         int acc = 1 << (kPrecisionBits - 1);
+#pragma unroll 4
         for (int t = 0; t < n; ++t) acc += (int)col[(size_t)t * (kTW * C)] * k[t];
         out[(((long long)f * out_h + oy0 + oy) * out_w + ox0) * C + j] = (uint8_t)clip8(acc);
+    }
+}
+
+// Fast path for ksize <= kKMax on both axes (scale factors up to 2.33x: every halving of the 2.5 MP guard).  Same tiles and shared
+// memory layout as k_lanczos_resize; the passes are re-mapped so that shared-memory LOAD count -- the bound of the generic kernel --
+// drops ~5x: horizontal: thread = one output x for every 4th window row, coefficients in registers, pixels read as aligned 32-bit
+// words + funnel shift; vertical: thread = one output row and C words (4 bytes each) of it, coefficients in registers.
+constexpr int kKMax = 16;
+template <int C>
+__global__ void __launch_bounds__(kThreads)
+k_lanczos_fast(const uint8_t* __restrict__ in, int lead, long long total_bytes, int in_h, int in_w,
+               const int* __restrict__ bx, const int* __restrict__ kx, int ksx,
+               const int* __restrict__ by, const int* __restrict__ ky, int ksy,
+               int out_h, int out_w, uint8_t* __restrict__ out, int win_words, int win_rows) {
+    extern __shared__ uint32_t smem[];
+    uint32_t* win = smem;                                              // [win_rows][win_words]
+    uint32_t* hbuf = smem + (size_t)win_rows * win_words;              // [win_rows][kTW * C / 4]
+    constexpr int kRowWords = kTW * C / 4;
+    const int f = blockIdx.z, oy0 = blockIdx.y * kTH, ox0 = blockIdx.x * kTW;
+    const int oy1 = min(oy0 + kTH, out_h), ox1 = min(ox0 + kTW, out_w);
+    const int tw = ox1 - ox0, th = oy1 - oy0;
+    const int x_lo = bx[2 * ox0], x_hi = bx[2 * (ox1 - 1)] + bx[2 * (ox1 - 1) + 1];
+    const int y_lo = by[2 * oy0], y_hi = by[2 * (oy1 - 1)] + by[2 * (oy1 - 1) + 1];
+    const int rows = y_hi - y_lo;
+    const long long frame0 = lead + (long long)f * in_h * in_w * C;
+    // phase 0: window rows through aligned word loads (one spare word per row is cleared for the funnel shift)
+    for (int r = threadIdx.x / 32; r < rows; r += kThreads / 32) {
+        const long long b0 = frame0 + ((long long)(y_lo + r) * in_w + x_lo) * C, b1 = b0 + (long long)(x_hi - x_lo) * C;
+        const long long a0 = b0 & ~3LL;
+        const int nw = (int)((b1 - a0 + 3) >> 2);
+        for (int w = threadIdx.x & 31; w < win_words; w += 32) {
+            uint32_t v = 0;
+            const long long a = a0 + 4LL * w;
+            if (w < nw) {
+                if (a + 4 <= total_bytes) v = *(const uint32_t*)(in + a);
+                else
+                    for (int j = 0; j < 4; ++j) if (a + j < total_bytes) v |= (uint32_t)in[a + j] << (8 * j);
+            }
+            win[(size_t)r * win_words + w] = v;
+        }
+    }
+    __syncthreads();
+    // phase 1: horizontal pass
+    {
+        const int ox = threadIdx.x % kTW, rl = threadIdx.x / kTW;     // 4 row lanes
+        if (ox < tw) {
+            const int xmin = bx[2 * (ox0 + ox)], n = bx[2 * (ox0 + ox) + 1];
+            int kreg[kKMax];
+#pragma unroll
+            for (int t = 0; t < kKMax; ++t) kreg[t] = t < n ? kx[(size_t)(ox0 + ox) * ksx + t] : 0;
+            constexpr int kNW = (kKMax * C + 3) / 4 + 1;                // words that can hold the taps at any byte phase
+            for (int r = rl; r < rows; r += kThreads / kTW) {
+                const long long b0 = frame0 + ((long long)(y_lo + r) * in_w + x_lo) * C;
+                const int s = (int)(b0 & 3) + (xmin - x_lo) * C, sh = 8 * (s & 3);
+                const uint32_t* src = win + (size_t)r * win_words + (s >> 2);
+                const int lim = win_words - (s >> 2);                 // words left in this row of the window
+                uint32_t w[kNW];
+#pragma unroll
+                for (int j = 0; j < kNW; ++j) w[j] = j < lim ? src[j] : 0u;
+                int acc[C];
+#pragma unroll
+                for (int c = 0; c < C; ++c) acc[c] = 1 << (kPrecisionBits - 1);
+#pragma unroll
+                for (int t = 0; t < kKMax; ++t) {
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        const int i = t * C + c;                       // byte i of the tap stream (compile-time)
+                        const uint32_t al = __funnelshift_r(w[i >> 2], w[(i >> 2) + 1], sh);
+                        acc[c] += (int)((al >> (8 * (i & 3))) & 0xFFu) * kreg[t];
+                    }
+                }
+                uint8_t* dst = (uint8_t*)(hbuf + (size_t)r * kRowWords) + ox * C;
+#pragma unroll
+                for (int c = 0; c < C; ++c) dst[c] = (uint8_t)clip8(acc[c]);
+            }
+        }
+    }
+    __syncthreads();
+    // phase 2: vertical pass: thread = (output row, C words of it)
+    {
+        const int oy = threadIdx.x / 16, wl = threadIdx.x % 16;
+        if (oy < th) {
+            const int ymin = by[2 * (oy0 + oy)], n = by[2 * (oy0 + oy) + 1];
+            int kreg[kKMax];
+#pragma unroll
+            for (int t = 0; t < kKMax; ++t) kreg[t] = t < n ? ky[(size_t)(oy0 + oy) * ksy + t] : 0;
+            const int twc = tw * C;
+            uint8_t* orow = out + (((long long)f * out_h + oy0 + oy) * out_w + ox0) * C;
+            const bool aligned = (((uintptr_t)orow) & 3) == 0;
+#pragma unroll
+            for (int q = 0; q < C; ++q) {
+                const int wi = wl + 16 * q;
+                if (4 * wi >= twc) continue;
+                const uint32_t* col = hbuf + (size_t)(ymin - y_lo) * kRowWords + wi;
+                int a0 = 1 << (kPrecisionBits - 1), a1 = a0, a2 = a0, a3 = a0;
+#pragma unroll
+                for (int t = 0; t < kKMax; ++t) {
+                    if (t < n) {
+                        const uint32_t v = col[(size_t)t * kRowWords];
+                        a0 += (int)(v & 0xFFu) * kreg[t]; a1 += (int)((v >> 8) & 0xFFu) * kreg[t];
+                        a2 += (int)((v >> 16) & 0xFFu) * kreg[t]; a3 += (int)(v >> 24) * kreg[t];
+                    }
+                }
+                const uint32_t pk = (uint32_t)clip8(a0) | ((uint32_t)clip8(a1) << 8) | ((uint32_t)clip8(a2) << 16) | ((uint32_t)clip8(a3) << 24);
+                if (aligned && 4 * wi + 4 <= twc) *(uint32_t*)(orow + 4 * wi) = pk;
+                else
+                    for (int j = 0; j < 4; ++j) if (4 * wi + j < twc) orow[4 * wi + j] = (uint8_t)(pk >> (8 * j));
+            }
+        }
     }
 }
 
@@ -263,18 +392,41 @@ extern "C" int am_lanczos_resize_u8(const uint8_t* d_in, int batch, int in_h, in
     if (rc) return rc;
     rc = axis_table(in_h, out_h, kTH, &ty);
     if (rc) return rc;
-    const int win_words = (tx->max_span * channels + 3 + 3) / 4 + 1, win_rows = ty->max_span;
-    const size_t smem = (size_t)win_rows * win_words * 4 + (size_t)win_rows * kTW * channels;
+    const int win_words = (tx->max_span * channels + 3 + 3) / 4 + 2, win_rows = ty->max_span;    // + spare words (funnel shift)
+    const size_t smem = (size_t)win_rows * win_words * 4 + ((size_t)kTW * tx->ksize + (size_t)kTH * ty->ksize + 2 * kTW + 2 * kTH) * 4 +
+                        (size_t)win_rows * kTW * channels;
     if (smem > 200 * 1024) {
         fprintf(stderr, "[accessmath_b200] am_lanczos_resize_u8: scale too large for one tile (%zu B of shared memory)\n", smem);
         return AM_ERR_ARG;
     }
-    if (smem > 48 * 1024) AM_CUDA(cudaFuncSetAttribute(k_lanczos_resize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(am_div_up(out_w, kTW), am_div_up(out_h, kTH), batch);
     const int lead = (int)((uintptr_t)d_in & 3);
-    k_lanczos_resize<<<grid, kThreads, smem, (cudaStream_t)stream>>>(d_in - lead, lead, lead + (long long)batch * in_h * in_w * channels, in_h, in_w,
-                                                                    channels, tx->d_bounds, tx->d_coef, tx->ksize, ty->d_bounds, ty->d_coef,
-                                                                    ty->ksize, out_h, out_w, d_out, win_words, win_rows);
+    const long long total = lead + (long long)batch * in_h * in_w * channels;
+    const bool fast = tx->ksize <= kKMax && ty->ksize <= kKMax;
+    const size_t smem_fast = (size_t)win_rows * win_words * 4 + (size_t)win_rows * kTW * channels;
+#define AM_LANCZOS_LAUNCH(CH)                                                                                                       \
+    do {                                                                                                                            \
+        if (fast) {                                                                                                                 \
+            if (smem_fast > 48 * 1024)                                                                                              \
+                AM_CUDA(cudaFuncSetAttribute(k_lanczos_fast<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fast));     \
+            k_lanczos_fast<CH><<<grid, kThreads, smem_fast, (cudaStream_t)stream>>>(d_in - lead, lead, total, in_h, in_w, tx->d_bounds,     \
+                                                                                   tx->d_coef, tx->ksize, ty->d_bounds, ty->d_coef,         \
+                                                                                   ty->ksize, out_h, out_w, d_out, win_words, win_rows);    \
+        } else {                                                                                                                    \
+            if (smem > 48 * 1024)                                                                                                   \
+                AM_CUDA(cudaFuncSetAttribute(k_lanczos_resize<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
+            k_lanczos_resize<CH><<<grid, kThreads, smem, (cudaStream_t)stream>>>(d_in - lead, lead, total, in_h, in_w, tx->d_bounds,        \
+                                                                               tx->d_coef, tx->ksize, ty->d_bounds, ty->d_coef, ty->ksize,  \
+                                                                               out_h, out_w, d_out, win_words, win_rows);                   \
+        }                                                                                                                           \
+    } while (0)
+    switch (channels) {
+        case 1: AM_LANCZOS_LAUNCH(1); break;
+        case 2: AM_LANCZOS_LAUNCH(2); break;
+        case 3: AM_LANCZOS_LAUNCH(3); break;
+        default: AM_LANCZOS_LAUNCH(4); break;
+    }
+#undef AM_LANCZOS_LAUNCH
     AM_CUDA(cudaGetLastError());
     return AM_OK;
 }
