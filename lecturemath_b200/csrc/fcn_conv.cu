@@ -181,7 +181,7 @@ __device__ __forceinline__ void tmem_wait16(uint32_t* v) {
 // z = x (a + b s + c s^2), s = min(x^2, 36) (minimax fit, tools/fit_gelu.py: |error| <= 2.6e-5 absolute for every fp32
 // x; beyond |x| = 6 the clamp keeps z monotone and the tanh saturated).  tanh is ONE MUFU op (tanh.approx.f32, relative
 // error 2^-11 => |error| <= 2.5e-4 |x| on top of the fit, an order of magnitude below the bf16 rounding of the stored
-// activation); measured end to end (tools/fcn_accuracy.py, 1080p, fp32 oracle): max probability error 5.4e-4 and mask
+// activation); measured end to end (oracle/check_fcn_accuracy.py, 1080p, fp32 oracle): max probability error 5.4e-4 and mask
 // disagreement 2.4e-5 - 4.4e-5, identical to the Abramowitz-Stegun 7.1.28 erf (13 FP32 ops + 1 MUFU) used before.
 // The epilogue warps are issue bound on the K <= 96 layers, so the arithmetic runs on PACKED fp32 pairs
 // (fma/mul/add.rn.f32x2: two elements per issue slot on sm_100): 3.5 FMA-pipe + 1 ALU (min) + 1 MUFU per element.

@@ -172,9 +172,11 @@ class StreamingExtractor:
     memory, so side-stream kernels would only start at conv-kernel boundaries.)"""
 
     def __init__(self, net, width, height, min_recall=0.85, min_precision=0.85, max_gap=85, batch=8, rank=0, world=1,
-                 device=None, handoff_words=1 << 20, row_capacity=1 << 16, depth=2, handoff=None):
+                 device=None, handoff_words=1 << 20, row_capacity=0, depth=2, handoff=None):
         self.net, self.width, self.height, self.batch = net, width, height, batch
         self.rank, self.world, self.depth = rank, world, depth
+        if row_capacity <= 0:                                            # result rows per batch: dense handwriting has ~450 px per CC
+            row_capacity = max(1 << 16, batch * width * height // 128)
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
         net.cuda(self.device.index)
         self.large = net.large_adapter(batch, height, width)             # > 2.5 MP frames: FCN at the halved size, CC at full size

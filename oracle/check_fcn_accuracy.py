@@ -1,6 +1,6 @@
 """Accuracy of the FCN binarizer against the fp32 oracle on the same GPU (cuDNN fp32, TF32 off): max probability error and
 mask disagreement on synthetic whiteboard frames with the reference's seed-0 random init.  Test infrastructure (imports
-oracle/); used to compare kernel variants (AM_B200_LIB=...).   python tools/fcn_accuracy.py [--hw 1080x1920] [--frames 2]"""
+oracle/); used to compare kernel variants (AM_B200_LIB=...).   python oracle/check_fcn_accuracy.py [--hw 1080x1920] [--frames 2]"""
 import argparse
 import json
 import os

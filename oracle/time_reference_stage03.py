@@ -1,5 +1,5 @@
 """Container-only (needs /root/reference): wall-clock of the UNMODIFIED reference's stage 02 + stage 03 estimator methods on the
-dense 1080p glyph-mask workload of tools/grouping_bench.py, for the record in DESIGN.md.   python tools/reference_stage03_timing.py 32"""
+dense 1080p glyph-mask workload of tools/grouping_bench.py, for the record in DESIGN.md.   python oracle/time_reference_stage03.py 32"""
 import json
 import os
 import sys
