@@ -66,6 +66,7 @@ struct alignas(64) ConvParams {
     long long out_sn, out_sy; int out_sx, out_padx, out_coff;
     int Cout, Sy, Sx, Ntot, act;
     unsigned cout_magic;  // floor(2^32 / Cout) + 1 (Cout >= 2)
+    unsigned nrt_magic, nyt_magic, nnb_magic;   // floor(2^32 / d) + 1 for d = nRT, nYT, nNB (0 when d == 1): exact for n * d < 2^32
     const float* bias;
     int* work_counter;    // [0] next work item (dynamic tile scheduler), [1] CTAs finished (the last one resets both)
 };
@@ -90,8 +91,20 @@ __device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
         : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     return done;
 }
+// try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes (wake-up is immediate) or the hint
+// expires, instead of re-issuing the poll loop every few hundred cycles -- on the epilogue-bound layers the waiting producer /
+// issuer warps were spending 12 % of the SM's issue slots in that loop (profile r01_n, op 0)
+__device__ __forceinline__ uint32_t mbar_try_sleep(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity), "r"(20000u) : "memory");
+    return done;
+}
 __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
-    for (uint32_t it = 0; !mbar_try(bar, parity); ++it)
+    for (uint32_t it = 0; !mbar_try_sleep(bar, parity); ++it)
         if (it > (1u << 26)) { printf("[accessmath_b200] mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
@@ -230,14 +243,16 @@ __device__ __forceinline__ uint64_t gelu_erf2(uint64_t x) {
     return f2_fma(hx, f2_pack(tanh_approx(z0), tanh_approx(z1)), hx);
 }
 
+// n / d through the precomputed reciprocal (magic = 0 encodes d == 1); exact for n * d < 2^32 (work-item counts are < 2^20)
+__device__ __forceinline__ int fast_div(int n, unsigned magic) { return magic ? (int)__umulhi((unsigned)n, magic) : n; }
 struct TileCoord { int frame, y0, r0; bool valid; };
 __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int t) {
     TileCoord c;
     c.valid = t < p.n_mtiles;
     if (!c.valid) t = p.n_mtiles - 1;                // duplicate the last tile: loads stay in bounds, stores are skipped
-    const int rt = t % p.nRT; t /= p.nRT;
-    const int yt = t % p.nYT;
-    c.frame = t / p.nYT; c.y0 = yt * p.YT; c.r0 = rt * p.RT;
+    const int t1 = fast_div(t, p.nrt_magic), rt = t - t1 * p.nRT;      // t / nRT, t % nRT without the integer-division sequence
+    const int fr = fast_div(t1, p.nyt_magic), yt = t1 - fr * p.nYT;
+    c.frame = fr; c.y0 = yt * p.YT; c.r0 = rt * p.RT;
     return c;
 }
 
@@ -433,7 +448,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv_gemm(const __grid_cons
             if (++slot == SCHED_DEPTH) { slot = 0; ps ^= 1; }
             if (w < 0) break;
             w_next = sched_fetch(p.work_counter, lane);                  // latency hidden behind this item's loads
-            const int st = w / p.nNB, nb = w - st * p.nNB;
+            const int st = fast_div(w, p.nnb_magic), nb = w - st * p.nNB;
             const int n0 = nb * p.NT;
             TileCoord tcs[kMT];
 #pragma unroll
@@ -546,7 +561,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv_gemm(const __grid_cons
         while (true) {
             const int w = sched_next(schedFull, schedEmpty, sched_w, slot, ps, lane);
             if (w < 0) break;
-            const int st = w / p.nNB, nb = w - st * p.nNB;
+            const int st = fast_div(w, p.nnb_magic), nb = w - st * p.nNB;
             const int n0 = nb * p.NT;
             if (nb != bias_nb) {
                 asm volatile("bar.sync 1, %0;" ::"r"(kEpiWarps * 32));     // everyone finished reading the previous bias
@@ -710,7 +725,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) k_c
         int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
         const uint32_t fullA_l = mapa_rank(fullA, 0), fullB_l = mapa_rank(fullB, 0);
         for (int w = w_first; w < n_work; w += w_step) {
-            const int st = w / p.nNB, nb = w - st * p.nNB;
+            const int st = fast_div(w, p.nnb_magic), nb = w - st * p.nNB;
             const int n0 = nb * p.NT + (int)rank * (p.NT >> 1);
             TileCoord tcs[kMT];
 #pragma unroll
@@ -814,7 +829,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) k_c
         const bool f32fast = p.out_f32 && p.out_sx == p.Cout && (p.Sy == 1 || ((p.Sx * p.Cout) & 15) == 0) && p.out_coff == 0 &&
                              ((p.Ntot | (int)p.out_sy | (int)p.out_sn) & 3) == 0;
         for (int w = w_first; w < n_work; w += w_step) {
-            const int st = w / p.nNB, nb = w - st * p.nNB;
+            const int st = fast_div(w, p.nnb_magic), nb = w - st * p.nNB;
             const int n0 = nb * p.NT;
             if (nb != bias_nb) {
                 asm volatile("bar.sync 1, %0;" ::"r"(kEpiWarps * 32));
@@ -985,6 +1000,12 @@ static int conv_prepare(const am_conv_desc* d, am_conv_plan* plan) {
     p.out_sn = d->out_sn; p.out_sy = d->out_sy; p.out_sx = d->out_sx; p.out_padx = d->out_padx; p.out_coff = d->out_coff;
     p.Cout = d->Cout; p.Sy = d->Sy; p.Sx = d->Sx; p.Ntot = d->Ntot; p.act = d->act; p.bias = d->bias;
     p.cout_magic = d->Cout >= 2 ? (unsigned)((1ull << 32) / (unsigned long long)d->Cout) + 1u : 0u;
+    auto magic = [](int dv) -> unsigned { return dv >= 2 ? (unsigned)((1ull << 32) / (unsigned long long)dv) + 1u : 0u; };
+    p.nrt_magic = magic(p.nRT); p.nyt_magic = magic(p.nYT); p.nnb_magic = magic(p.nNB);
+    if ((unsigned long long)(p.n_mtiles + 8) * (unsigned long long)std::max(p.nRT, std::max(p.nYT, p.nNB)) * (unsigned long long)std::max(1, p.nNB) >= (1ull << 32)) {
+        fprintf(stderr, "[accessmath_b200] am_conv: tile count too large for the reciprocal division\n");
+        return AM_ERR_ARG;
+    }
     if (d->Sy < 1 || d->Sy > 2 || d->Sx < 1) return AM_ERR_ARG;
 
     // ---- shared-memory / TMEM budget -------------------------------------------------------------------
