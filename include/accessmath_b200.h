@@ -173,6 +173,8 @@ typedef struct am_conv_desc {
 #define AM_CONV_NO_MT2 2           /* one M-tile per work item even when two would share the weight tiles */
 #define AM_CONV_FORCE_MT2 4        /* two M-tiles per work item (two MMA issuer warps) whenever TMEM and smem allow */
 #define AM_CONV_CTA_PAIR 16        /* cta_group::2: clusters of two CTAs run M = 256 MMAs, each CTA holds half of every weight tile */
+#define AM_CONV_EPI8 32            /* 8 epilogue warps take part (tensor-bound layers); default: chosen from K */
+#define AM_CONV_EPI16 64           /* all 16 epilogue warps (epilogue-bound layers: K <= 640) */
 #define AM_CONV_FORCE_MT4 8        /* four M-tiles per work item (four MMA issuer warps, 12 epilogue warps): narrow N <= 128 layers */
 
 /* one launch: encodes the tensor maps, picks the tiling and runs the persistent tcgen05 kernel */

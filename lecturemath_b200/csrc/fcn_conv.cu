@@ -66,6 +66,7 @@ struct alignas(64) ConvParams {
     long long out_sn, out_sy; int out_sx, out_padx, out_coff;
     int Cout, Sy, Sx, Ntot, act;
     unsigned cout_magic;  // floor(2^32 / Cout) + 1 (Cout >= 2)
+    int epi_per_q;        // epilogue warps per TMEM lane quarter that take part in this launch (<= compiled EPI_WARPS / 4)
     unsigned nrt_magic, nyt_magic, nnb_magic;   // floor(2^32 / d) + 1 for d = nRT, nYT, nNB (0 when d == 1): exact for n * d < 2^32
     const float* bias;
     int* work_counter;    // [0] next work item (dynamic tile scheduler), [1] CTAs finished (the last one resets both)
@@ -105,7 +106,8 @@ __device__ __forceinline__ uint32_t mbar_try_sleep(uint32_t bar, uint32_t parity
 }
 __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
     for (uint32_t it = 0; !mbar_try_sleep(bar, parity); ++it)
-        if (it > (1u << 26)) { printf("[accessmath_b200] mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+        if (it > (1u << 20)) {                       // >= 0.2 s of polling, ~20 s when every poll sleeps its 20 us hint
+            printf("[accessmath_b200] mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (!mbar_try(bar, parity)) mbar_wait_slow(bar, parity);
@@ -123,7 +125,8 @@ __device__ __forceinline__ void mbar_wait_old(uint32_t bar, uint32_t parity) {
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.b32 %0, 1, 0, p;\n\t}"
             : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        if (it > (1u << 26)) { printf("[accessmath_b200] mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+        if (it > (1u << 20)) {                       // >= 0.2 s of polling, ~20 s when every poll sleeps its 20 us hint
+            printf("[accessmath_b200] mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
     }
 }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
@@ -408,8 +411,10 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv_gemm(const __grid_cons
         // every MMA issuer (one per M-tile) commits to the empty / accumulator-full barriers
         for (int i = 0; i < p.stagesA; ++i) { mbar_init(fullA + 8 * i, 1); mbar_init(emptyA + 8 * i, kMT); }
         for (int i = 0; i < p.stagesB; ++i) { mbar_init(fullB + 8 * i, 1); mbar_init(emptyB + 8 * i, kMT); }
-        for (int i = 0; i < 2; ++i) { mbar_init(accFull + 8 * i, kMT); mbar_init(accEmpty + 8 * i, kEpiWarps); }
-        for (int i = 0; i < SCHED_DEPTH; ++i) { mbar_init(schedFull + 8 * i, 1); mbar_init(schedEmpty + 8 * i, kMT + kEpiWarps); }
+        // only the first p.epi_per_q epilogue warps of every lane quarter work in this launch (the others idle at the final barrier)
+        const int n_epi = min(4 * p.epi_per_q, kEpiWarps);
+        for (int i = 0; i < 2; ++i) { mbar_init(accFull + 8 * i, kMT); mbar_init(accEmpty + 8 * i, n_epi); }
+        for (int i = 0; i < SCHED_DEPTH; ++i) { mbar_init(schedFull + 8 * i, 1); mbar_init(schedEmpty + 8 * i, kMT + n_epi); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         tma_prefetch_desc(&p.tmA[0]);
         if (p.nseg > 1) tma_prefetch_desc(&p.tmA[1]);
@@ -538,12 +543,13 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv_gemm(const __grid_cons
             __syncwarp();
             if (++as == acc_stages) { as = 0; pacc ^= 1; }
         }
-    } else if (warp < kEpiFirst) {
-        // idle warps
+    } else if (warp < kEpiFirst || ((warp - kEpiFirst) >> 2) >= p.epi_per_q) {
+        // idle warps (incl. the epilogue warps this launch does not use: tensor-bound layers run faster with 8 than with 16)
     } else {
         // ===================== epilogue (warps 4..) =====================
         const int q = warp & 3;                          // TMEM lane quarter this warp may access
-        const int h = (warp - kEpiFirst) >> 2;           // which share of the 16-column groups (0 .. kEpiPerQ-1)
+        const int h = (warp - kEpiFirst) >> 2;           // which share of the 16-column groups (0 .. epi_per_q-1)
+        const int epiPerQ = min(p.epi_per_q, kEpiPerQ), epiThreads = epiPerQ * 128;
         const int m = q * 32 + lane;
         const int yy = m >> p.logRT, rr = m & (p.RT - 1);
         // bias of this CTA's N block -> smem (reloaded per work item only when there are several N blocks)
@@ -564,9 +570,9 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv_gemm(const __grid_cons
             const int st = fast_div(w, p.nnb_magic), nb = w - st * p.nNB;
             const int n0 = nb * p.NT;
             if (nb != bias_nb) {
-                asm volatile("bar.sync 1, %0;" ::"r"(kEpiWarps * 32));     // everyone finished reading the previous bias
-                for (int i = threadIdx.x - kEpiFirst * 32; i < p.NT; i += kEpiWarps * 32) sbias[i] = __ldg(p.bias + n0 + i);
-                asm volatile("bar.sync 1, %0;" ::"r"(kEpiWarps * 32));
+                asm volatile("bar.sync 1, %0;" ::"r"(epiThreads));     // everyone finished reading the previous bias
+                for (int i = threadIdx.x - kEpiFirst * 32; i < p.NT; i += epiThreads) sbias[i] = __ldg(p.bias + n0 + i);
+                asm volatile("bar.sync 1, %0;" ::"r"(epiThreads));
                 bias_nb = nb;
             }
             mbar_wait(accFull + 8 * as, pacc);
@@ -604,13 +610,13 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv_gemm(const __grid_cons
             if (g < units) tmem_ld16_async(unit_addr(g), va);
             while (g < units) {
                 tmem_wait16(va);
-                int g2 = g + kEpiPerQ;
+                int g2 = g + epiPerQ;
                 if (g2 < units) tmem_ld16_async(unit_addr(g2), vb);
                 { const int j0 = enter(g); if (row_ok) epi_unit(p, va, sbias, n0, j0, base, vec16, vec8, f32fast, sy1_ok); }
                 g = g2;
                 if (g >= units) break;
                 tmem_wait16(vb);
-                g2 = g + kEpiPerQ;
+                g2 = g + epiPerQ;
                 if (g2 < units) tmem_ld16_async(unit_addr(g2), va);
                 { const int j0 = enter(g); if (row_ok) epi_unit(p, vb, sbias, n0, j0, base, vec16, vec8, f32fast, sy1_ok); }
                 g = g2;
@@ -703,7 +709,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) k_c
     if (threadIdx.x == 0) {
         for (int i = 0; i < p.stagesA; ++i) { mbar_init(fullA + 8 * i, 1); mbar_init(emptyA + 8 * i, kMT); }
         for (int i = 0; i < p.stagesB; ++i) { mbar_init(fullB + 8 * i, 1); mbar_init(emptyB + 8 * i, kMT); }
-        for (int i = 0; i < 2; ++i) { mbar_init(accFull + 8 * i, kMT); mbar_init(accEmpty + 8 * i, 2 * kEpiWarps); }
+        const int n_epi = min(4 * p.epi_per_q, kEpiWarps);          // working epilogue warps per CTA of the pair
+        for (int i = 0; i < 2; ++i) { mbar_init(accFull + 8 * i, kMT); mbar_init(accEmpty + 8 * i, 2 * n_epi); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         tma_prefetch_desc(&p.tmA[0]);
         if (p.nseg > 1) tma_prefetch_desc(&p.tmA[1]);
@@ -810,12 +817,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) k_c
                 if (++as == acc_stages) { as = 0; pacc ^= 1; }
             }
         }
-    } else if (warp < kEpiFirst) {
+    } else if (warp < kEpiFirst || ((warp - kEpiFirst) >> 2) >= p.epi_per_q) {
         // idle
     } else {
         // ===================== epilogue: this CTA's two M-tiles =====================
         const int q = warp & 3;
         const int h = (warp - kEpiFirst) >> 2;
+        const int epiPerQ = min(p.epi_per_q, kEpiPerQ), epiThreads = epiPerQ * 128;
         const int m = q * 32 + lane;
         const int yy = m >> p.logRT, rr = m & (p.RT - 1);
         float* sbias = (float*)(smem_raw + (sBias - smem_u32(smem_raw)));
@@ -832,9 +840,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) k_c
             const int st = fast_div(w, p.nnb_magic), nb = w - st * p.nNB;
             const int n0 = nb * p.NT;
             if (nb != bias_nb) {
-                asm volatile("bar.sync 1, %0;" ::"r"(kEpiWarps * 32));
-                for (int i = threadIdx.x - kEpiFirst * 32; i < p.NT; i += kEpiWarps * 32) sbias[i] = __ldg(p.bias + n0 + i);
-                asm volatile("bar.sync 1, %0;" ::"r"(kEpiWarps * 32));
+                asm volatile("bar.sync 1, %0;" ::"r"(epiThreads));
+                for (int i = threadIdx.x - kEpiFirst * 32; i < p.NT; i += epiThreads) sbias[i] = __ldg(p.bias + n0 + i);
+                asm volatile("bar.sync 1, %0;" ::"r"(epiThreads));
                 bias_nb = nb;
             }
             mbar_wait(accFull + 8 * as, pacc);
@@ -865,13 +873,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) k_c
             if (g < units) tmem_ld16_async(unit_addr(g), va);
             while (g < units) {
                 tmem_wait16(va);
-                int g2 = g + kEpiPerQ;
+                int g2 = g + epiPerQ;
                 if (g2 < units) tmem_ld16_async(unit_addr(g2), vb);
                 { const int j0 = enter(g); if (row_ok) epi_unit(p, va, sbias, n0, j0, base, vec16, vec8, f32fast, sy1_ok); }
                 g = g2;
                 if (g >= units) break;
                 tmem_wait16(vb);
-                g2 = g + kEpiPerQ;
+                g2 = g + epiPerQ;
                 if (g2 < units) tmem_ld16_async(unit_addr(g2), va);
                 { const int j0 = enter(g); if (row_ok) epi_unit(p, vb, sbias, n0, j0, base, vec16, vec8, f32fast, sy1_ok); }
                 g = g2;
@@ -1002,6 +1010,10 @@ static int conv_prepare(const am_conv_desc* d, am_conv_plan* plan) {
     p.cout_magic = d->Cout >= 2 ? (unsigned)((1ull << 32) / (unsigned long long)d->Cout) + 1u : 0u;
     auto magic = [](int dv) -> unsigned { return dv >= 2 ? (unsigned)((1ull << 32) / (unsigned long long)dv) + 1u : 0u; };
     p.nrt_magic = magic(p.nRT); p.nyt_magic = magic(p.nYT); p.nnb_magic = magic(p.nNB);
+    // epilogue warps per TMEM lane quarter: layers whose main loop is short (K <= 640 incl. padding) are bound by the epilogue's
+    // issue rate and want all 16 warps; the tensor-bound layers run 2-5 % faster with 8 (fewer warps competing with the MMA
+    // issuers / TMA producer for issue slots and power) -- measured per layer, profiles/README.md (r01_v)
+    p.epi_per_q = (d->flags & AM_CONV_EPI16) ? 4 : (d->flags & AM_CONV_EPI8) ? 2 : ((long long)total_chunks * d->KH * 64 <= 640 ? 4 : 2);
     if ((unsigned long long)(p.n_mtiles + 8) * (unsigned long long)std::max(p.nRT, std::max(p.nYT, p.nNB)) * (unsigned long long)std::max(1, p.nNB) >= (1ull << 32)) {
         fprintf(stderr, "[accessmath_b200] am_conv: tile count too large for the reciprocal division\n");
         return AM_ERR_ARG;
