@@ -3,6 +3,7 @@
 One CCEngine owns the scratch for a batch of frames of a fixed size; `label()` runs labeling + stats + crops,
 `match()` runs temporal matching for the frames of the batch, the `read_*` calls bring tables to the host."""
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -12,6 +13,12 @@ from . import _lib
 MIN_CC_PIXELS = 20        # R/AccessMath/preprocessing/content/labeler.py:22
 LABEL_LAUNCHES = 3            # am_cc_label_batch: k_strip_label, k_resolve, k_crop_fill (+1 with a label image)
 MATCH_LAUNCHES_PER_FRAME = 6  # am_est_add_frames: k_match_pairs, _overlap, _select, _refresh, _update, _copy
+
+
+def match_launches(n_frames):
+    """Kernel launches of one am_est_add_frames call: ONE cooperative k_match_fused for the whole batch (default), or the six
+    per-frame kernels with AM_B200_MATCH=multi."""
+    return MATCH_LAUNCHES_PER_FRAME * n_frames if os.environ.get("AM_B200_MATCH") == "multi" else 1
 
 
 def _stream():

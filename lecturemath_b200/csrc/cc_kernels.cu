@@ -23,6 +23,9 @@
 //            bits at their ABSOLUTE x position, so two crops AND together without shifting.
 #include "am_common.cuh"
 #include "../../include/accessmath_b200.h"
+#include <cooperative_groups.h>
+#include <cstdlib>
+#include <cstring>
 
 #define NONE_U32 0xFFFFFFFFu
 
@@ -546,7 +549,9 @@ struct am_estimator {
     void* slab;
     int* h_scal; unsigned long long* h_scal64;   // pinned
 };
-#define MATCH_CHUNK 2048
+#ifndef MATCH_CHUNK
+#define MATCH_CHUNK 512          // words of one overlap work item (one warp): a board-sized pair (64k words) spreads over 128 warps
+#endif
 #define MATCH_NONE 0x7fffffff
 
 // Temporal matching is pair-parallel.  The reference tests a CC's candidates in ascending unique index and stops
@@ -577,10 +582,11 @@ __device__ __forceinline__ void append_pair(int c, int u, int cx0, int cx1, int 
             if (ii < MI) items[ii] = make_int2(pi, k);
     }
 }
-__global__ void __launch_bounds__(MP_THREADS, 4)
-k_match_pairs(const CcFrame* __restrict__ frames, const int* __restrict__ counts, int f, const int* __restrict__ act,
-              const uint2* __restrict__ box, int* __restrict__ scal, int2* __restrict__ pair_cu, int* __restrict__ pair_m,
-              int2* __restrict__ items, int MP, int MI, unsigned long long* __restrict__ tested_total) {
+// (bodies take a virtual block index / block count so that the per-frame kernels and the fused cooperative kernel share them;
+//  nothing that another phase of the same frame writes is read through const __restrict__ -- no ld.global.nc inside the fused kernel)
+__device__ __forceinline__ void match_pairs_body(int bid, int nblk, const CcFrame* frames, const int* __restrict__ counts, int f, const int* act,
+              const uint2* box, int* scal, int2* pair_cu, int* pair_m,
+              int2* items, int MP, int MI, unsigned long long* tested_total) {
     __shared__ __align__(16) uint2 s_box[MP_TILE];
     __shared__ int4 s_cc[MP_THREADS];                    // boxes of the tile's current CCs
     __shared__ unsigned s_queue[MP_QUEUE];               // (thread << 16) | j
@@ -592,7 +598,7 @@ k_match_pairs(const CcFrame* __restrict__ frames, const int* __restrict__ counts
     const int tiles_c = (n_kept + MP_THREADS - 1) / MP_THREADS, tiles_a = max(1, (n_act + MP_TILE - 1) / MP_TILE);
     const int tid = threadIdx.x;
     unsigned hits = 0;
-    for (int t = blockIdx.x; t < tiles_c * tiles_a; t += gridDim.x) {
+    for (int t = bid; t < tiles_c * tiles_a; t += nblk) {
         const int ci = t % tiles_c, ai = t / tiles_c;
         const int a0 = ai * MP_TILE, jn = min(MP_TILE, n_act - a0);
         __syncthreads();
@@ -662,17 +668,21 @@ k_match_pairs(const CcFrame* __restrict__ frames, const int* __restrict__ counts
     hits = __reduce_add_sync(0xffffffffu, hits);
     if ((tid & 31) == 0 && hits) atomicAdd(tested_total, (unsigned long long)hits);
 }
+__global__ void __launch_bounds__(MP_THREADS, 4)
+k_match_pairs(const CcFrame* frames, const int* __restrict__ counts, int f, const int* act, const uint2* box, int* scal, int2* pair_cu,
+              int* pair_m, int2* items, int MP, int MI, unsigned long long* tested_total) {
+    match_pairs_body(blockIdx.x, gridDim.x, frames, counts, f, act, box, scal, pair_cu, pair_m, items, MP, MI, tested_total);
+}
 
 // M1b: persistent warps over the work items: popcount(cc.mask & unique.mask) on the bit-packed crops, which sit at
 // their ABSOLUTE x position so the AND needs no shifting (connected_component.py:211-228)
-__global__ void k_match_overlap(const CcFrame* __restrict__ frames, int f, int* __restrict__ scal,
-                                const int* __restrict__ u_min_x, const int* __restrict__ u_max_x, const int* __restrict__ u_min_y,
-                                const int* __restrict__ u_max_y, const unsigned long long* __restrict__ u_crop_off,
-                                const uint32_t* __restrict__ arena, const int2* __restrict__ pair_cu, int* __restrict__ pair_m,
-                                const int2* __restrict__ items, int MP, int MI) {
+__device__ __forceinline__ void match_overlap_body(int bid, int nblk, const CcFrame* frames, int f, int* scal,
+                                const int* u_min_x, const int* u_max_x, const int* u_min_y, const int* u_max_y,
+                                const unsigned long long* u_crop_off, const uint32_t* arena, const int2* pair_cu, int* pair_m,
+                                const int2* items, int MP, int MI) {
     const CcFrame fr = frames[f];
     const int lane = threadIdx.x & 31;
-    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int wid = (bid * blockDim.x + threadIdx.x) >> 5, nwarps = (nblk * blockDim.x) >> 5;
     const int n_items = min(scal[5], MI);
     for (int it = wid; it < n_items; it += nwarps) {
         const int2 item = items[it];
@@ -701,14 +711,18 @@ __global__ void k_match_overlap(const CcFrame* __restrict__ frames, int f, int* 
         if (lane == 0 && m) atomicAdd(&pair_m[item.x], m);
     }
 }
+__global__ void k_match_overlap(const CcFrame* frames, int f, int* scal, const int* u_min_x, const int* u_max_x, const int* u_min_y,
+                                const int* u_max_y, const unsigned long long* u_crop_off, const uint32_t* arena, const int2* pair_cu,
+                                int* pair_m, const int2* items, int MP, int MI) {
+    match_overlap_body(blockIdx.x, gridDim.x, frames, f, scal, u_min_x, u_max_x, u_min_y, u_max_y, u_crop_off, arena, pair_cu, pair_m, items, MP, MI);
+}
 
 // M1c: per pair: recall / precision in IEEE fp64 (connected_component.py:239-240), lowest passing unique index wins
-__global__ void k_match_select(const CcFrame* __restrict__ frames, int f, const int* __restrict__ scal, const int* __restrict__ u_size,
-                               const int2* __restrict__ pair_cu, const int* __restrict__ pair_m, int MP,
-                               double min_recall, double min_precision) {
+__device__ __forceinline__ void match_select_body(int bid, int nblk, const CcFrame* frames, int f, const int* scal, const int* u_size,
+                               const int2* pair_cu, const int* pair_m, int MP, double min_recall, double min_precision) {
     const CcFrame fr = frames[f];
     const int n_pairs = min(scal[4], MP);
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pairs; i += gridDim.x * blockDim.x) {
+    for (int i = bid * blockDim.x + threadIdx.x; i < n_pairs; i += nblk * blockDim.x) {
         const int2 cu = pair_cu[i];
         const int m = pair_m[i];
         const int csz = fr.t_count[fr.kept_label[cu.x] - 1];
@@ -717,16 +731,23 @@ __global__ void k_match_select(const CcFrame* __restrict__ frames, int f, const 
         if (recall >= min_recall && precision >= min_precision) atomicMin(&fr.match_unique[cu.x], cu.y);
     }
 }
+__global__ void k_match_select(const CcFrame* frames, int f, const int* scal, const int* u_size, const int2* pair_cu, const int* pair_m, int MP,
+                               double min_recall, double min_precision) {
+    match_select_body(blockIdx.x, gridDim.x, frames, f, scal, u_size, pair_cu, pair_m, MP, min_recall, min_precision);
+}
 
 // M2a: matched CCs refresh their unique's last-seen frame (:104) -- must be complete before the expiry pass reads it
-__global__ void k_match_refresh(const CcFrame* __restrict__ frames, const int* __restrict__ counts, int f, const int* __restrict__ scal,
-                                int* __restrict__ u_last) {
+__device__ __forceinline__ void match_refresh_body(int bid, int nblk, const CcFrame* frames, const int* __restrict__ counts, int f, const int* scal,
+                                int* u_last) {
     const CcFrame fr = frames[f];
     const int n_kept = counts[f * 4 + 2], img_idx = scal[2];
-    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n_kept; c += gridDim.x * blockDim.x) {
+    for (int c = bid * blockDim.x + threadIdx.x; c < n_kept; c += nblk * blockDim.x) {
         const int u = fr.match_unique[c];
         if (u != MATCH_NONE) u_last[u] = img_idx;
     }
+}
+__global__ void k_match_refresh(const CcFrame* frames, const int* __restrict__ counts, int f, const int* scal, int* u_last) {
+    match_refresh_body(blockIdx.x, gridDim.x, frames, counts, f, scal, u_last);
 }
 
 __device__ __forceinline__ uint2 pack_box(int x0, int x1, int y0, int y1) {
@@ -738,12 +759,12 @@ __device__ __forceinline__ uint2 pack_box(int x0, int x1, int y0, int y1) {
 // as an unordered compaction of the active list.  The last block out publishes the scalars of the next frame.
 #define MU_THREADS 1024
 #define MU_ITEMS 8
-__global__ void __launch_bounds__(MU_THREADS)
-k_match_update(const CcFrame* __restrict__ frames, const int* __restrict__ counts, int f,
-               const int* __restrict__ act_in, const uint2* __restrict__ box_in, int* __restrict__ act_out, uint2* __restrict__ box_out,
-               int* __restrict__ scal, unsigned long long* __restrict__ scal64,
+template <int THREADS>
+__device__ __forceinline__ void match_update_body(int bid, int nblk, const CcFrame* frames, const int* __restrict__ counts, int f,
+               const int* act_in, const uint2* box_in, int* act_out, uint2* box_out,
+               int* scal, unsigned long long* scal64,
                int* u_min_x, int* u_max_x, int* u_min_y, int* u_max_y, int* u_size, int* u_last,
-               int* u_first_frame, int* u_first_label, unsigned long long* u_crop_off, int* __restrict__ newlist,
+               int* u_first_frame, int* u_first_label, unsigned long long* u_crop_off, int* newlist,
                int MU, int MA, unsigned long long AW, int max_gap, int MP, int MI) {
     __shared__ int sm[33];
     const CcFrame fr = frames[f];
@@ -751,11 +772,11 @@ k_match_update(const CcFrame* __restrict__ frames, const int* __restrict__ count
     const int img_idx = scal[2], n_uniq0 = scal[0], n_act0 = scal[1];
     const int tid = threadIdx.x;
     bool over = false;
-    if (blockIdx.x == 0) {
+    if (bid == 0) {
         // every thread owns MU_ITEMS consecutive current CCs per round: all their loads are in flight together and
         // one block scan per round ranks the new ones in ascending order
         int n_new = 0;
-        for (int c0 = 0; c0 < n_kept; c0 += MU_THREADS * MU_ITEMS) {
+        for (int c0 = 0; c0 < n_kept; c0 += THREADS * MU_ITEMS) {
             const int cb = c0 + tid * MU_ITEMS;
             unsigned newmask = 0;
 #pragma unroll
@@ -790,7 +811,7 @@ k_match_update(const CcFrame* __restrict__ frames, const int* __restrict__ count
         }
     } else {
         const int lane = tid & 31;
-        for (int i0 = (blockIdx.x - 1) * MU_THREADS; i0 < n_act0; i0 += (gridDim.x - 1) * MU_THREADS) {
+        for (int i0 = (bid - 1) * THREADS; i0 < n_act0; i0 += (nblk - 1) * THREADS) {
             const int i = i0 + tid;
             const int u = (i < n_act0) ? act_in[i] : -1;
             const bool keep = (u >= 0) && (img_idx == 0 || img_idx - u_last[u] < max_gap);
@@ -808,7 +829,7 @@ k_match_update(const CcFrame* __restrict__ frames, const int* __restrict__ count
     if (__syncthreads_or(over) && tid == 0) atomicOr(&scal[3], 8);
     if (tid == 0) {
         __threadfence();
-        if (atomicAdd(&scal[6], 1) == (int)gridDim.x - 1) {              // last block out
+        if (atomicAdd(&scal[6], 1) == (int)nblk - 1) {              // last block out
             __threadfence();
             const int n_new = ((volatile int*)scal)[8], n_act = ((volatile int*)scal)[7];
             scal[0] = min(n_uniq0 + n_new, MU);
@@ -818,13 +839,21 @@ k_match_update(const CcFrame* __restrict__ frames, const int* __restrict__ count
         }
     }
 }
+__global__ void __launch_bounds__(MU_THREADS)
+k_match_update(const CcFrame* frames, const int* __restrict__ counts, int f, const int* act_in, const uint2* box_in, int* act_out, uint2* box_out,
+               int* scal, unsigned long long* scal64, int* u_min_x, int* u_max_x, int* u_min_y, int* u_max_y, int* u_size, int* u_last,
+               int* u_first_frame, int* u_first_label, unsigned long long* u_crop_off, int* newlist, int MU, int MA, unsigned long long AW,
+               int max_gap, int MP, int MI) {
+    match_update_body<MU_THREADS>(blockIdx.x, gridDim.x, frames, counts, f, act_in, box_in, act_out, box_out, scal, scal64, u_min_x, u_max_x, u_min_y,
+                                  u_max_y, u_size, u_last, u_first_frame, u_first_label, u_crop_off, newlist, MU, MA, AW, max_gap, MP, MI);
+}
 
 // M2c: the crops of the new uniques go into the arena (first-seen instance, never updated): warp per new unique
-__global__ void k_match_copy(const CcFrame* __restrict__ frames, int f, const int* __restrict__ scal, const int* __restrict__ newlist,
-                             const unsigned long long* __restrict__ u_crop_off, uint32_t* __restrict__ arena) {
+__device__ __forceinline__ void match_copy_body(int bid, int nblk, const CcFrame* frames, int f, const int* scal, const int* newlist,
+                             const unsigned long long* u_crop_off, uint32_t* arena) {
     const CcFrame fr = frames[f];
     const int n = scal[9], lane = threadIdx.x & 31;
-    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += (gridDim.x * blockDim.x) >> 5) {
+    for (int i = (bid * blockDim.x + threadIdx.x) >> 5; i < n; i += (nblk * blockDim.x) >> 5) {
         const int c = newlist[i];
         if (c < 0) continue;
         const int l = fr.kept_label[c] - 1;
@@ -832,6 +861,45 @@ __global__ void k_match_copy(const CcFrame* __restrict__ frames, int f, const in
         const uint32_t* src = fr.crops + fr.kept_crop_off[c];
         uint32_t* dst = arena + u_crop_off[fr.match_unique[c]];
         for (int k = lane; k < words; k += 32) dst[k] = src[k];
+    }
+}
+__global__ void k_match_copy(const CcFrame* frames, int f, const int* scal, const int* newlist, const unsigned long long* u_crop_off,
+                             uint32_t* arena) {
+    match_copy_body(blockIdx.x, gridDim.x, frames, f, scal, newlist, u_crop_off, arena);
+}
+
+// All six phases of `n` consecutive frames in ONE cooperative launch: grid-wide barriers replace the kernel boundaries (6 launches
+// and their ~5 us dependency gaps per frame -> 5 grid syncs).  On the headline workload (a handful of CCs per frame) the matching
+// of an 8-frame batch drops from 48 launches to one; dense frames keep the same parallelism (the bodies are grid-strided).
+struct MatchArgs {
+    const CcFrame* frames; const int* counts; int first, n, cur;
+    int* act[2]; uint2* box[2];
+    int* scal; unsigned long long* scal64;
+    int *u_min_x, *u_max_x, *u_min_y, *u_max_y, *u_size, *u_last, *u_first_frame, *u_first_label;
+    unsigned long long* u_crop_off; uint32_t* arena; int* newlist;
+    int2* pair_cu; int* pair_m; int2* items;
+    int MU, MA, MP, MI, max_gap; unsigned long long AW; double min_recall, min_precision;
+};
+__global__ void __launch_bounds__(MP_THREADS, 4) k_match_fused(const MatchArgs a) {
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    const int bid = blockIdx.x, nblk = gridDim.x;
+    int cur = a.cur;
+    for (int f = a.first; f < a.first + a.n; ++f, cur ^= 1) {
+        match_pairs_body(bid, nblk, a.frames, a.counts, f, a.act[cur], a.box[cur], a.scal, a.pair_cu, a.pair_m, a.items, a.MP, a.MI, a.scal64);
+        grid.sync();
+        match_overlap_body(bid, nblk, a.frames, f, a.scal, a.u_min_x, a.u_max_x, a.u_min_y, a.u_max_y, a.u_crop_off, a.arena, a.pair_cu, a.pair_m,
+                           a.items, a.MP, a.MI);
+        grid.sync();
+        match_select_body(bid, nblk, a.frames, f, a.scal, a.u_size, a.pair_cu, a.pair_m, a.MP, a.min_recall, a.min_precision);
+        grid.sync();
+        match_refresh_body(bid, nblk, a.frames, a.counts, f, a.scal, a.u_last);
+        grid.sync();
+        match_update_body<MP_THREADS>(bid, nblk, a.frames, a.counts, f, a.act[cur], a.box[cur], a.act[cur ^ 1], a.box[cur ^ 1], a.scal, a.scal64,
+                                      a.u_min_x, a.u_max_x, a.u_min_y, a.u_max_y, a.u_size, a.u_last, a.u_first_frame, a.u_first_label, a.u_crop_off,
+                                      a.newlist, a.MU, a.MA, a.AW, a.max_gap, a.MP, a.MI);
+        grid.sync();
+        // the crop copies only have to land before the NEXT frame's overlap phase (one grid sync away)
+        match_copy_body(bid, nblk, a.frames, f, a.scal, a.newlist, a.u_crop_off, a.arena);
     }
 }
 
@@ -1297,6 +1365,37 @@ static inline unsigned long long* est_tmp(am_estimator* e) { return e->tmp_off; 
 extern "C" int am_est_add_frames(am_estimator* e, am_cc_ctx* c, int first, int n, void* stream) {
     if (!e || !c || first < 0 || n <= 0 || first + n > c->B) return AM_ERR_ARG;
     cudaStream_t st = S(stream);
+    // default: ONE cooperative launch for the whole batch (k_match_fused); AM_B200_MATCH=multi keeps the six launches per frame
+    static int fused_mode = -1, fused_grid = 0;
+    if (fused_mode < 0) {
+        const char* env = getenv("AM_B200_MATCH");
+        int dev = 0, coop = 0, sms = 0, occ = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_match_fused, MP_THREADS, 0);
+        const char* genv = getenv("AM_B200_MATCH_CTAS_PER_SM");     // tuning knob (default 2): grid syncs get dearer with more CTAs
+        int per_sm = genv ? atoi(genv) : 2;
+        if (per_sm < 1) per_sm = 1;
+        if (per_sm > occ) per_sm = occ;
+        fused_grid = sms * per_sm;
+        fused_mode = (coop && fused_grid >= 2 && !(env && strcmp(env, "multi") == 0)) ? 1 : 0;
+    }
+    if (fused_mode == 1) {
+        MatchArgs a;
+        a.frames = c->d_frames; a.counts = c->d_counts; a.first = first; a.n = n; a.cur = e->cur;
+        a.act[0] = e->act[0]; a.act[1] = e->act[1]; a.box[0] = e->box[0]; a.box[1] = e->box[1];
+        a.scal = e->d_scal; a.scal64 = e->d_scal64;
+        a.u_min_x = e->u_min_x; a.u_max_x = e->u_max_x; a.u_min_y = e->u_min_y; a.u_max_y = e->u_max_y; a.u_size = e->u_size;
+        a.u_last = e->u_last; a.u_first_frame = e->u_first_frame; a.u_first_label = e->u_first_label; a.u_crop_off = e->u_crop_off;
+        a.arena = e->arena; a.newlist = e->newlist; a.pair_cu = e->pair_cu; a.pair_m = e->pair_m; a.items = e->items;
+        a.MU = e->MU; a.MA = e->MA; a.MP = e->MP; a.MI = e->MI; a.max_gap = e->max_gap; a.AW = e->AW;
+        a.min_recall = e->min_recall; a.min_precision = e->min_precision;
+        void* args[] = {&a};
+        AM_CUDA(cudaLaunchCooperativeKernel((const void*)k_match_fused, dim3(fused_grid), dim3(MP_THREADS), args, 0, st));
+        e->cur ^= (n & 1);
+        return AM_OK;
+    }
     for (int f = first; f < first + n; ++f) {
         int* a_in = e->act[e->cur]; int* a_out = e->act[e->cur ^ 1];
         uint2* b_in = e->box[e->cur]; uint2* b_out = e->box[e->cur ^ 1];

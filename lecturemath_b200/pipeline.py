@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .cc_engine import CCEngine, Estimator, LABEL_LAUNCHES, MATCH_LAUNCHES_PER_FRAME
+from .cc_engine import CCEngine, Estimator, LABEL_LAUNCHES, match_launches
 
 
 class ContentExtractor:
@@ -54,7 +54,7 @@ class ContentExtractor:
         if not match:
             return None
         self.est.add_frames(eng, 0, self.batch)
-        self.launches += MATCH_LAUNCHES_PER_FRAME * self.batch
+        self.launches += match_launches(self.batch)
         return None
 
     def read_rows(self):
@@ -254,7 +254,7 @@ class StreamingExtractor:
             self.launches += 3
         self.est.add_frames(eng, 0, self.batch)
         eng.pack_rows_into(self.rows[k], self.offs[k], self.batch)
-        self.launches += MATCH_LAUNCHES_PER_FRAME * self.batch + 2
+        self.launches += match_launches(self.batch) + 2
         if need_send and self.handoff == "p2p":
             m = self.mail
             m.n_send += 1
