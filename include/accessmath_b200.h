@@ -168,6 +168,13 @@ typedef struct am_conv_desc {
     int flags;                     /* AM_CONV_* tuning overrides (0 = let the library choose) */
     int in_ystep;                  /* input rows per GEMM row step: 1, or 2 = "2-D packing": a GEMM row produces Sy = 2 output rows,
                                       KH is then the Toeplitz-extended tap count KH_conv + 1 and RT must be 8 (0 means 1) */
+    /* optional fused MaxPool2d(2) (floor) of the activated output (FCN_lecturenet.py:264-276): the epilogue also writes the pooled
+     * NHWC bf16 tensor, saving the separate pass over the un-pooled one.  NULL = off.  Needs Sx = Sy = 1, RT <= 16, bf16 output,
+     * Cout % 16 == 0 (the 2x2 block of a pixel then lives in four lanes of one epilogue warp). */
+    void* pool_out;
+    int pool_H, pool_W;            /* out_H / 2, out_W / 2 */
+    long long pool_sn, pool_sy;    /* element strides: frame, row */
+    int pool_sx, pool_padx;        /* pixel stride (channels), left pad (pixels) */
 } am_conv_desc;
 #define AM_CONV_NO_RESIDENT 1      /* always stream the weights through the B ring */
 #define AM_CONV_NO_MT2 2           /* one M-tile per work item even when two would share the weight tiles */

@@ -66,6 +66,7 @@ struct alignas(64) ConvParams {
     long long out_sn, out_sy; int out_sx, out_padx, out_coff;
     int Cout, Sy, Sx, Ntot, act;
     unsigned cout_magic;  // floor(2^32 / Cout) + 1 (Cout >= 2)
+    void* pool_out; int pool_H, pool_W, pool_sx, pool_padx; long long pool_sn, pool_sy;   // fused MaxPool2d(2) destination (NULL = off)
     int epi_per_q;        // epilogue warps per TMEM lane quarter that take part in this launch (<= compiled EPI_WARPS / 4)
     unsigned nrt_magic, nyt_magic, nnb_magic;   // floor(2^32 / d) + 1 for d = nRT, nYT, nNB (0 when d == 1): exact for n * d < 2^32
     const float* bias;
@@ -260,8 +261,11 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int t) {
 }
 
 // Epilogue of one 16-column unit of one accumulator row: bias + activation + NHWC store.
+// With a fused max-pool (p.pool_out) EVERY lane of the warp calls this (row_ok only predicates the stores): the 2x2 block of an
+// output pixel sits in lanes l, l^1 (x) and l^RT (y), so the pooled value is two shuffle + max rounds on the packed bf16 pairs.
 __device__ __forceinline__ void epi_unit(const ConvParams& p, const uint32_t (&v)[16], const float* __restrict__ sbias, int n0, int j0,
-                                         long long base, bool vec16, bool vec8, bool f32fast, bool sy1_ok) {
+                                         long long base, bool vec16, bool vec8, bool f32fast, bool sy1_ok, bool row_ok = true,
+                                         long long pbase = 0, bool pool_ok = false) {
     if (vec16) {
         // Cout % 16 == 0: the unit's 16 columns are 16 consecutive channels of ONE output pixel -> one address
         // computation and one 32-byte store per unit (every GELU layer of the network takes this path)
@@ -290,12 +294,35 @@ __device__ __forceinline__ void epi_unit(const ConvParams& p, const uint32_t (&v
             pk[i] = *(const uint32_t*)&h;
         }
         __nv_bfloat16* o = (__nv_bfloat16*)p.out + off;
-        if ((off & 15) == 0) {
-            asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(o), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]),
-                         "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
-        } else {
-            *(uint4*)o = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            *(uint4*)(o + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        if (row_ok) {
+            if ((off & 15) == 0) {
+                asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(o), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]),
+                             "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
+            } else {
+                *(uint4*)o = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                *(uint4*)(o + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            }
+        }
+        if (p.pool_out != nullptr) {                       // warp-uniform
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                uint32_t t = __shfl_xor_sync(0xffffffffu, pk[i], 1);
+                __nv_bfloat162 m = __hmax2(*(const __nv_bfloat162*)&pk[i], *(const __nv_bfloat162*)&t);
+                uint32_t mu = *(const uint32_t*)&m;
+                t = __shfl_xor_sync(0xffffffffu, mu, p.RT);
+                m = __hmax2(m, *(const __nv_bfloat162*)&t);
+                pk[i] = *(const uint32_t*)&m;
+            }
+            if (pool_ok) {
+                __nv_bfloat16* po = (__nv_bfloat16*)p.pool_out + pbase + co;
+                if ((((uintptr_t)po) & 31) == 0) {
+                    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(po), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]),
+                                 "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
+                } else {
+                    *(uint4*)po = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    *(uint4*)(po + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                }
+            }
         }
     } else if (vec8) {
         // two 8-channel groups; a group never straddles a pixel because Cout % 8 == 0
@@ -582,8 +609,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv_gemm(const __grid_cons
             // current one is processed; two register sets ping-pong (no copies)
             uint32_t va[16], vb[16];
             int cur_mt = -1;
-            bool row_ok = false, sy1_ok = true;
-            long long base = 0;
+            bool row_ok = false, sy1_ok = true, pool_ok = false;
+            long long base = 0, pbase = 0;
             auto tile_of = [&](int g) -> int {               // M-tile of unit g (units are laid out tile after tile)
                 if (kMT == 1) return 0;
                 if (kMT == 2) return g >= units_per_tile ? 1 : 0;
@@ -600,6 +627,10 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv_gemm(const __grid_cons
                     const TileCoord tc = decode_tile(p, st * kMT + mt);
                     const int y = tc.y0 + yy, r = tc.r0 + rr;
                     row_ok = tc.valid && (y < p.Hin) && (r < p.nR);
+                    if (p.pool_out != nullptr) {             // Sx = Sy = 1: (y, r) is the output pixel; even lanes of even rows write the pooled pixel
+                        pool_ok = tc.valid && !((y | r) & 1) && (y >> 1) < p.pool_H && (r >> 1) < p.pool_W;
+                        pbase = (long long)tc.frame * p.pool_sn + (long long)(y >> 1) * p.pool_sy + (long long)((r >> 1) + p.pool_padx) * p.pool_sx;
+                    }
                     base = (long long)tc.frame * p.out_sn + (long long)(p.Sy * y) * p.out_sy + (long long)(p.Sx * r + p.out_padx) * p.out_sx + p.out_coff;
                     if (p.Sy * y >= p.out_H || p.Sx * r + p.Sx > p.out_W) row_ok = false;
                     sy1_ok = p.Sy * y + 1 < p.out_H;                               // odd image height: the last row pair has no second row
@@ -612,13 +643,13 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv_gemm(const __grid_cons
                 tmem_wait16(va);
                 int g2 = g + epiPerQ;
                 if (g2 < units) tmem_ld16_async(unit_addr(g2), vb);
-                { const int j0 = enter(g); if (row_ok) epi_unit(p, va, sbias, n0, j0, base, vec16, vec8, f32fast, sy1_ok); }
+                { const int j0 = enter(g); if (row_ok || p.pool_out != nullptr) epi_unit(p, va, sbias, n0, j0, base, vec16, vec8, f32fast, sy1_ok, row_ok, pbase, pool_ok); }
                 g = g2;
                 if (g >= units) break;
                 tmem_wait16(vb);
                 g2 = g + epiPerQ;
                 if (g2 < units) tmem_ld16_async(unit_addr(g2), va);
-                { const int j0 = enter(g); if (row_ok) epi_unit(p, vb, sbias, n0, j0, base, vec16, vec8, f32fast, sy1_ok); }
+                { const int j0 = enter(g); if (row_ok || p.pool_out != nullptr) epi_unit(p, vb, sbias, n0, j0, base, vec16, vec8, f32fast, sy1_ok, row_ok, pbase, pool_ok); }
                 g = g2;
             }
             // all tcgen05.ld of this stage have completed (tmem_wait16 in the last iteration): hand the stage back
@@ -850,8 +881,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) k_c
             const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * kMT * p.NTc);
             uint32_t va[16], vb[16];
             int cur_mt = -1;
-            bool row_ok = false, sy1_ok = true;
-            long long base = 0;
+            bool row_ok = false, sy1_ok = true, pool_ok = false;
+            long long base = 0, pbase = 0;
             auto unit_addr = [&](int g) -> uint32_t {
                 const int mt = g >= units_per_tile ? 1 : 0;
                 return tacc + (uint32_t)(mt * p.NTc + (g - mt * units_per_tile) * 16);
@@ -863,6 +894,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) k_c
                     const TileCoord tc = decode_tile(p, st * 2 * kMT + (int)rank * kMT + mt);
                     const int y = tc.y0 + yy, r = tc.r0 + rr;
                     row_ok = tc.valid && (y < p.Hin) && (r < p.nR);
+                    if (p.pool_out != nullptr) {             // Sx = Sy = 1: (y, r) is the output pixel; even lanes of even rows write the pooled pixel
+                        pool_ok = tc.valid && !((y | r) & 1) && (y >> 1) < p.pool_H && (r >> 1) < p.pool_W;
+                        pbase = (long long)tc.frame * p.pool_sn + (long long)(y >> 1) * p.pool_sy + (long long)((r >> 1) + p.pool_padx) * p.pool_sx;
+                    }
                     base = (long long)tc.frame * p.out_sn + (long long)(p.Sy * y) * p.out_sy + (long long)(p.Sx * r + p.out_padx) * p.out_sx + p.out_coff;
                     if (p.Sy * y >= p.out_H || p.Sx * r + p.Sx > p.out_W) row_ok = false;
                     sy1_ok = p.Sy * y + 1 < p.out_H;
@@ -875,13 +910,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) k_c
                 tmem_wait16(va);
                 int g2 = g + epiPerQ;
                 if (g2 < units) tmem_ld16_async(unit_addr(g2), vb);
-                { const int j0 = enter(g); if (row_ok) epi_unit(p, va, sbias, n0, j0, base, vec16, vec8, f32fast, sy1_ok); }
+                { const int j0 = enter(g); if (row_ok || p.pool_out != nullptr) epi_unit(p, va, sbias, n0, j0, base, vec16, vec8, f32fast, sy1_ok, row_ok, pbase, pool_ok); }
                 g = g2;
                 if (g >= units) break;
                 tmem_wait16(vb);
                 g2 = g + epiPerQ;
                 if (g2 < units) tmem_ld16_async(unit_addr(g2), va);
-                { const int j0 = enter(g); if (row_ok) epi_unit(p, vb, sbias, n0, j0, base, vec16, vec8, f32fast, sy1_ok); }
+                { const int j0 = enter(g); if (row_ok || p.pool_out != nullptr) epi_unit(p, vb, sbias, n0, j0, base, vec16, vec8, f32fast, sy1_ok, row_ok, pbase, pool_ok); }
                 g = g2;
             }
             tc_fence_before();
@@ -1007,6 +1042,16 @@ static int conv_prepare(const am_conv_desc* d, am_conv_plan* plan) {
     p.out = d->out; p.out_f32 = d->out_f32; p.out_H = d->out_H; p.out_W = d->out_W;
     p.out_sn = d->out_sn; p.out_sy = d->out_sy; p.out_sx = d->out_sx; p.out_padx = d->out_padx; p.out_coff = d->out_coff;
     p.Cout = d->Cout; p.Sy = d->Sy; p.Sx = d->Sx; p.Ntot = d->Ntot; p.act = d->act; p.bias = d->bias;
+    p.pool_out = d->pool_out; p.pool_H = d->pool_H; p.pool_W = d->pool_W; p.pool_sn = d->pool_sn; p.pool_sy = d->pool_sy;
+    p.pool_sx = d->pool_sx; p.pool_padx = d->pool_padx;
+    if (d->pool_out) {            // the fused pool rides on the single-address 16-channel epilogue path
+        const bool vec16 = (d->Cout & 15) == 0 && !d->out_f32 && ((d->out_coff | d->out_sx | (int)(d->out_sy & 7) | (int)(d->out_sn & 7)) & 7) == 0;
+        if (d->Sx != 1 || d->Sy != 1 || d->RT > 16 || !vec16 || d->Ntot != d->Cout || (d->pool_sx & 15) || (d->pool_sy & 15) || (d->pool_sn & 15) ||
+            d->pool_H != d->out_H / 2 || d->pool_W != d->out_W / 2) {
+            fprintf(stderr, "[accessmath_b200] am_conv: fused max-pool needs Sx = Sy = 1, RT <= 16, bf16 output with Cout %% 16 == 0\n");
+            return AM_ERR_ARG;
+        }
+    }
     p.cout_magic = d->Cout >= 2 ? (unsigned)((1ull << 32) / (unsigned long long)d->Cout) + 1u : 0u;
     auto magic = [](int dv) -> unsigned { return dv >= 2 ? (unsigned)((1ull << 32) / (unsigned long long)dv) + 1u : 0u; };
     p.nrt_magic = magic(p.nRT); p.nyt_magic = magic(p.nYT); p.nnb_magic = magic(p.nNB);

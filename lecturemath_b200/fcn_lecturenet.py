@@ -76,7 +76,9 @@ class ConvDesc(ctypes.Structure):
                 ("out", ctypes.c_void_p), ("out_f32", ctypes.c_int), ("out_H", ctypes.c_int), ("out_W", ctypes.c_int),
                 ("out_sn", ctypes.c_longlong), ("out_sy", ctypes.c_longlong),
                 ("out_sx", ctypes.c_int), ("out_padx", ctypes.c_int), ("out_coff", ctypes.c_int),
-                ("Cout", ctypes.c_int), ("Sy", ctypes.c_int), ("Sx", ctypes.c_int), ("act", ctypes.c_int), ("flags", ctypes.c_int), ("in_ystep", ctypes.c_int)]
+                ("Cout", ctypes.c_int), ("Sy", ctypes.c_int), ("Sx", ctypes.c_int), ("act", ctypes.c_int), ("flags", ctypes.c_int), ("in_ystep", ctypes.c_int),
+                ("pool_out", ctypes.c_void_p), ("pool_H", ctypes.c_int), ("pool_W", ctypes.c_int),
+                ("pool_sn", ctypes.c_longlong), ("pool_sy", ctypes.c_longlong), ("pool_sx", ctypes.c_int), ("pool_padx", ctypes.c_int)]
 
 
 def fold_bn(w, b, bn_w, bn_b, mean, var, out_dim=0):
@@ -322,8 +324,8 @@ class FCNPlan:
         for i in range(5):
             w, b = cbn("conv_down_block_%d" % (i + 1))
             cmap = [0, 1, 2] + [-1] * 5 if i == 0 else ident(src.C)
-            self._conv("conv_down_block_%d" % (i + 1), w, b, [(src, cmap)], self.d[i], act=1)
-            self.ops.append(("pool", (self.d[i], self.p[i])))
+            if not self._conv("conv_down_block_%d" % (i + 1), w, b, [(src, cmap)], self.d[i], act=1, pool_dst=self.p[i]):
+                self.ops.append(("pool", (self.d[i], self.p[i])))      # not fusable in this configuration (S / Sy packing, RT = 32)
             src = self.p[i]
         w, b = cbn("mid_block")
         self._conv("mid_block", w, b, [(src, ident(src.C))], self.mid, act=1)
@@ -417,18 +419,22 @@ class FCNPlan:
                 best = c
         return best[1], best[2], best[3], best[4]
 
-    def _conv(self, name, w, b, srcs, dst, act, cap=None, f32_out=None):
+    def _conv(self, name, w, b, srcs, dst, act, cap=None, f32_out=None, pool_dst=None):
+        """pool_dst: buffer for MaxPool2d(2) of the output; returns True when the pool was fused into this conv's epilogue."""
         nrows, cin_total, KH, KW = w.shape
         first = srcs[0][0]
         cfg = self._pick_config(name, first.W, first.H, nrows, [buf.C for buf, _ in srcs], KW, KH, cap)
-        self.specs[name] = dict(kind="conv", w=w, b=b, srcs=srcs, dst=dst, act=act, cap=cap, f32_out=f32_out, op=len(self.ops), cfg=cfg)
-        d, keep = self._conv_desc(w, b, srcs, dst, act, f32_out, cfg)
+        self.specs[name] = dict(kind="conv", w=w, b=b, srcs=srcs, dst=dst, act=act, cap=cap, f32_out=f32_out, op=len(self.ops), cfg=cfg,
+                                pool_dst=pool_dst)
+        d, keep = self._conv_desc(w, b, srcs, dst, act, f32_out, cfg, pool_dst)
         self.keep += keep
         self.ops.append(("conv", d))
+        fused = bool(d.pool_out)
         self.op_flops[len(self.ops) - 1] = 2 * first.H * first.W * nrows * cin_total * KH * KW
         self.flops += 2 * first.H * first.W * nrows * cin_total * KH * KW
+        return fused
 
-    def _conv_desc(self, w, b, srcs, dst, act, f32_out, cfg):
+    def _conv_desc(self, w, b, srcs, dst, act, f32_out, cfg, pool_dst=None):
         """Kernel descriptor (+ the packed tensors it points to) of one convolution for configuration cfg = (S, Sy, NT, MT)."""
         nrows, cin_total, KH, KW = w.shape
         first = srcs[0][0]
@@ -465,6 +471,14 @@ class FCNPlan:
             d.out_padx, d.out_coff = dst.pad, 0
         d.Cout, d.Sy, d.Sx, d.act = nrows, Sy, S, act
         d.flags = 0 if MT is None else MT_FLAGS[MT]
+        # MaxPool2d(2) fused into the epilogue where the 2x2 block of a pixel sits in four lanes of one warp (csrc/fcn_conv.cu epi_unit)
+        # ... and where the main loop is long enough to hide the extra epilogue work (K > 640: on the epilogue-bound conv_down_block_2
+        # the fused pool cost as much as the separate pass saved)
+        if (pool_dst is not None and f32_out is None and S == 1 and Sy == 1 and d.RT <= 16 and nrows % 16 == 0 and self.rowrun
+                and (cin_total * KHc * KW > 640 or self.ov.get("fused_pool") == "all") and not self.ov.get("no_fused_pool")):
+            d.pool_out, d.pool_H, d.pool_W = pool_dst.ptr, pool_dst.H, pool_dst.W
+            d.pool_sx, d.pool_sy, d.pool_sn = pool_dst.C, pool_dst.Wp * pool_dst.C, pool_dst.H * pool_dst.Wp * pool_dst.C
+            d.pool_padx = pool_dst.pad
         return d, [packed, bias]
 
     def conv_candidates(self, name):
@@ -487,7 +501,7 @@ class FCNPlan:
         sp = self.specs[name]
         if sp["kind"] == "tconv":
             return self._tconv_desc(sp["wt"], sp["bt"], sp["src"], sp["dst"], cfg[2], cfg[3])[:2]
-        return self._conv_desc(sp["w"], sp["b"], sp["srcs"], sp["dst"], sp["act"], sp["f32_out"], tuple(cfg))
+        return self._conv_desc(sp["w"], sp["b"], sp["srcs"], sp["dst"], sp["act"], sp["f32_out"], tuple(cfg), sp.get("pool_dst"))
 
     def _tconv(self, name, wt, bt, src, dst):
         """ConvTranspose2d(k=2,s=2) + BN + GELU as a 1x1 GEMM with N = (sy,sx,co); odd output sizes get the
