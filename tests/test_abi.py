@@ -42,3 +42,22 @@ def test_words_per_row():
     lib = _lib.load()
     assert lib.am_words_per_row(1920) == 60 and lib.am_words_per_row(1280) == 40
     assert lib.am_words_per_row(121) == 4 and lib.am_words_per_row(1) == 4 and lib.am_words_per_row(129) == 8
+
+
+def test_header_is_plain_c_and_struct_sizes_match_the_ctypes_mirrors(tmp_path):
+    """include/accessmath_b200.h must compile as C99 (the boundary is a C ABI), and the structs passed by pointer must have the
+    layout the Python side assumes."""
+    import ctypes
+    import shutil
+    import subprocess
+    from lecturemath_b200.cc_grouping import UniqueView
+    from lecturemath_b200.fcn_lecturenet import ConvDesc
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "t.c"
+    src.write_text('#include <stdio.h>\n#include "accessmath_b200.h"\n'
+                   'int main(void){ printf("%zu %zu\\n", sizeof(am_conv_desc), sizeof(am_unique_view)); return 0; }\n')
+    exe = tmp_path / "t"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(REPO, "include"), str(src), "-o", str(exe)])
+    sizes = [int(v) for v in subprocess.check_output([str(exe)]).split()]
+    assert sizes == [ctypes.sizeof(ConvDesc), ctypes.sizeof(UniqueView)]
