@@ -19,11 +19,17 @@ extern "C" {
 
 /* ===== 1. Legacy entry point (host pointers, same signature as the reference) ================
  * Replaces CC_AgeBoundaries, R/accessmath_lib.c:357-359 (argtypes R/AccessMath/preprocessing/content/
- * labeler.py:159-165).  Stages H2D/D2H internally.  Precondition kept from the reference's callers:
- * ages >= 0 (frame times); labels outside 1..count_labels are ignored instead of written out of bounds. */
+ * labeler.py:159-165).  Stages H2D/D2H internally.  The age rule `if (age < 0 || a < age) age = a` in raster order
+ * (accessmath_lib.c:405-407) is reproduced for every input, negative ages included (it is the plain minimum for ages >= 0,
+ * frame times); labels outside 1..count_labels are ignored instead of written out of bounds. */
 int CC_AgeBoundaries(int* labels, float* ages, int width, int height, int count_labels,
                      int* out_mins_y, int* out_maxs_y, int* out_mins_x, int* out_maxs_x,
                      int* out_counts, float* output_age);
+/* The same operator on DEVICE pointers, asynchronous on `stream` (no PCIe round trip of the 8*P label / age bytes):
+ * d_out6[6][count_labels] = min_y, max_y, min_x, max_x, count (int32), age (fp32 bits); d_ages may be NULL (all zero);
+ * d_scratch >= 10 * count_labels + 4 ints. */
+int am_cc_age_boundaries_dev(const int* d_labels, const float* d_ages, int width, int height, int count_labels, int* d_out6,
+                             int* d_scratch, void* stream);
 
 /* ===== 1b. The other four exports of the reference's accessmath_lib (legacy 2013-15 binarizer / speaker detection).
  * Same names and signatures as R/accessmath_lib.c so that ctypes.CDLL callers resolve them unchanged;

@@ -12,6 +12,7 @@ c_int, c_void_p, c_double, c_ll, c_ull = ctypes.c_int, ctypes.c_void_p, ctypes.c
 # name -> (restype, argtypes): one entry per symbol declared in include/accessmath_b200.h
 SIGNATURES = {
     "CC_AgeBoundaries": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int] + [c_void_p] * 6),
+    "am_cc_age_boundaries_dev": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "adapthisteq": (c_int, [c_void_p, c_int, c_int, c_double, c_int, c_int, c_void_p]),
     "regionCumulativeDistribution": (None, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_double, c_void_p]),
     "combine_results": (c_int, [c_void_p, c_void_p, c_int, c_int, ctypes.c_ubyte, c_void_p]),

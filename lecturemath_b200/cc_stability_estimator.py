@@ -62,12 +62,14 @@ class CCStabilityEstimator(GroupingMixin):
         eng.read_counts()
         rows, offs = eng.packed_rows(n)
         rows_h, offs_h = rows.cpu().numpy(), offs.cpu().numpy()
+        st = est.state()                                                 # raises on a capacity / hand-off flag BEFORE rows are absorbed
         crops = [eng.crops(f) if eng.counts[f, 2] else None for f in range(n)]
         for f in range(n):
             self._absorb(rows_h[offs_h[f]:offs_h[f + 1]], crops[f])
-        st = est.state()
         self.tempo_count = st["tempo_count"]
-        assert st["img_idx"] == self.img_idx and st["n_unique"] == len(self.unique_cc_objects)
+        if st["img_idx"] != self.img_idx or st["n_unique"] != len(self.unique_cc_objects):
+            raise RuntimeError("device estimator state (img_idx %d, %d uniques) does not match the host view (%d, %d)"
+                               % (st["img_idx"], st["n_unique"], self.img_idx, len(self.unique_cc_objects)))
 
     def _absorb(self, rows, crops):
         current = []

@@ -38,6 +38,16 @@ class ConnectedComponent:
         self.next_cc = None
         self.prev_cc = None
 
+    def __setstate__(self, state):
+        """Also accepts the attribute dictionary of a reference ConnectedComponent (plain `img` attribute), so that files
+        written by the reference's stage 02 load into this class (lecturemath_b200/compat.py)."""
+        state = dict(state)
+        if "img" in state:
+            state["_img"] = state.pop("img")
+        state.setdefault("_img", None)
+        state.setdefault("_packed", None)
+        self.__dict__.update(state)
+
     @property
     def img(self):
         if self._img is None and self._packed is not None:

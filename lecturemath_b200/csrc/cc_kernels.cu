@@ -488,44 +488,91 @@ __device__ __forceinline__ unsigned f32_key(float v) {     // order-preserving f
 __device__ __forceinline__ float key_f32(unsigned k) {
     return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
-__global__ void k_ageb_init(int n, int W, int H, int* mny, int* mxy, int* mnx, int* mxx, int* cnt, unsigned* agek) {
+// CC_AgeBoundaries' age rule (accessmath_lib.c:405-407) is `if (age < 0 || a < age) age = a` over the pixels of a component in
+// raster order.  With L = the raster index of the component's LAST pixel whose age is negative (none: no L) that sequence
+// ends as  min(a_i : i > L)  or, when L is the component's last pixel, a_L itself -- so two order-free reductions reproduce
+// it exactly: pass 1 (k_ageb_scan) reduces bounds / count / plain minimum and atomicMax-es L, pass 2 (k_ageb_neg, a no-op
+// unless some age was negative) redoes the minimum over the pixels behind L.
+__global__ void k_ageb_init(int n, int W, int H, int* mny, int* mxy, int* mnx, int* mxx, int* cnt, unsigned* agek, long long* lastneg,
+                            int* any_neg) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) *any_neg = 0;
     if (i >= n) return;
-    mny[i] = H; mxy[i] = 0; mnx[i] = W; mxx[i] = 0; cnt[i] = 0; agek[i] = 0xFFFFFFFFu;
+    mny[i] = H; mxy[i] = 0; mnx[i] = W; mxx[i] = 0; cnt[i] = 0; agek[i] = 0xFFFFFFFFu; lastneg[i] = 0;
 }
 __global__ void k_ageb_scan(const int32_t* __restrict__ labels, const float* __restrict__ ages, int W, int H, int n,
-                            int* mny, int* mxy, int* mnx, int* mxx, int* cnt, unsigned* agek) {
+                            int* mny, int* mxy, int* mnx, int* mxx, int* cnt, unsigned* agek, long long* lastneg, int* any_neg) {
     const int y = blockIdx.y;
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    int lab = 0; unsigned ak = 0xFFFFFFFFu;
+    int lab = 0; unsigned ak = 0xFFFFFFFFu; long long neg = -1;
     if (x < W) {
         size_t idx = (size_t)y * W + x;
         lab = labels[idx];
         if (lab < 0 || lab > n) lab = 0;                 // the reference would write out of bounds here
-        if (lab > 0 && ages) ak = f32_key(ages[idx]);
+        if (lab > 0 && ages) { const float a = ages[idx]; ak = f32_key(a); if (a < 0.0f) neg = (long long)idx; }
         else if (lab > 0) ak = f32_key(0.0f);
     }
     unsigned peers = __match_any_sync(0xffffffffu, lab);
     int mn_x = __reduce_min_sync(peers, x), mx_x = __reduce_max_sync(peers, x);
     int c = __popc(peers);
     unsigned amin = __reduce_min_sync(peers, ak);
+    int negx = __reduce_max_sync(peers, neg >= 0 ? x : -1);
     if (lab > 0 && (int)(threadIdx.x & 31) == __ffs(peers) - 1) {
         int l = lab - 1;
         atomicMin(&mnx[l], mn_x); atomicMax(&mxx[l], mx_x);
         atomicMin(&mny[l], y); atomicMax(&mxy[l], y);
         atomicAdd(&cnt[l], c);
         atomicMin(&agek[l], amin);
+        if (negx >= 0) { atomicMax((unsigned long long*)&lastneg[l], (unsigned long long)((long long)y * W + negx + 1)); *any_neg = 1; }
     }
 }
-__global__ void k_ageb_finish(int n, const int* cnt, const unsigned* agek, float* out_age) {
+// lastneg holds (raster index + 1) of the last negative-age pixel through the unsigned atomicMax above (0 / -1 = none)
+__global__ void k_ageb_neg_reset(int n, const long long* lastneg, unsigned* agek, const int* any_neg) {
+    if (!*any_neg) return;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && lastneg[i] > 0) agek[i] = 0xFFFFFFFFu;
+}
+__global__ void k_ageb_neg(const int32_t* __restrict__ labels, const float* __restrict__ ages, int W, int H, int n,
+                           const long long* lastneg, unsigned* agek, const int* any_neg) {
+    if (!*any_neg) return;
+    const int y = blockIdx.y;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= W) return;
+    const long long idx = (long long)y * W + x;
+    const int lab = labels[idx];
+    if (lab <= 0 || lab > n) return;
+    const long long L = lastneg[lab - 1];
+    if (L > 0 && idx + 1 > L) atomicMin(&agek[lab - 1], f32_key(ages[idx]));
+}
+__global__ void k_ageb_finish(int n, const int* cnt, const unsigned* agek, const long long* lastneg, const float* __restrict__ ages,
+                              float* out_age) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    out_age[i] = (cnt[i] > 0) ? key_f32(agek[i]) : -1.0f;    // accessmath_lib.c:373 "-1 = unset"
+    float a = -1.0f;                                          // accessmath_lib.c:373 "-1 = unset"
+    if (cnt[i] > 0) a = (agek[i] == 0xFFFFFFFFu && lastneg[i] > 0) ? ages[lastneg[i] - 1] : key_f32(agek[i]);
+    out_age[i] = a;
+}
+// labels / ages / outputs in DEVICE memory; d_tab = scratch of 10 * n ints.  Asynchronous on `st`.
+static int ageb_run(const int32_t* d_lab, const float* d_age, int width, int height, int n, int* d_tab, cudaStream_t st) {
+    int *mny = d_tab, *mxy = d_tab + n, *mnx = d_tab + 2 * n, *mxx = d_tab + 3 * n, *cnt = d_tab + 4 * n;
+    unsigned* agek = (unsigned*)(d_tab + 5 * n); float* oage = (float*)(d_tab + 6 * n);
+    long long* lastneg = (long long*)(d_tab + 7 * n + (n & 1));              // 8-byte aligned (d_tab is)
+    int* any_neg = d_tab + 10 * n + 1;
+    k_ageb_init<<<am_div_up(n, 256), 256, 0, st>>>(n, width, height, mny, mxy, mnx, mxx, cnt, agek, lastneg, any_neg);
+    k_ageb_scan<<<dim3(am_div_up(width, 256), height), 256, 0, st>>>(d_lab, d_age, width, height, n, mny, mxy, mnx, mxx, cnt, agek, lastneg, any_neg);
+    if (d_age) {
+        k_ageb_neg_reset<<<am_div_up(n, 256), 256, 0, st>>>(n, lastneg, agek, any_neg);
+        k_ageb_neg<<<dim3(am_div_up(width, 256), height), 256, 0, st>>>(d_lab, d_age, width, height, n, lastneg, agek, any_neg);
+    }
+    k_ageb_finish<<<am_div_up(n, 256), 256, 0, st>>>(n, cnt, agek, lastneg, d_age, oage);
+    AM_CUDA(cudaGetLastError());
+    return AM_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
 // Temporal matching (CCStabilityEstimator.add_frame, cc_stability_estimator.py:41-155)
 struct am_estimator {
+    int fused_mode = -1, fused_grid = 0;     // k_match_fused launch configuration of the device this estimator lives on
     int W, H, max_gap, MU, MA;
     unsigned long long AW;       // arena capacity in words
     unsigned long long* tmp_off; // [MA] scratch for export/import
@@ -1165,7 +1212,7 @@ extern "C" am_cc_ctx* am_cc_create(int width, int height, int max_batch, int max
     c->strip_smem = (2 * R * c->WPR + c->CAP + 5 * STRIP_CAPS) * 4;
     if (c->strip_smem > 200 * 1024) { fprintf(stderr, "[accessmath_b200] am_cc_create: width %d too large\n", width); delete c; return nullptr; }
     c->ML = max_labels > 0 ? max_labels : (int)(P / 2 + 64);
-    c->MK = max_kept > 0 ? max_kept : (int)(P / 20 + 64);      // a kept CC has >= min_pixels (20) pixels
+    c->MK = max_kept > 0 ? max_kept : (int)(P / (min_pixels > 1 ? min_pixels : 1) + 64);      // a kept CC has >= min_pixels pixels
     if (c->MK > c->ML) c->MK = c->ML;
     c->CW = crop_words > 0 ? crop_words : (int)(4 * (long long)c->WPR * height + 1024);
     c->min_pixels = min_pixels;
@@ -1296,25 +1343,38 @@ extern "C" int CC_AgeBoundaries(int* labels, float* ages, int width, int height,
     if (!labels || width <= 0 || height <= 0) return AM_ERR_ARG;
     size_t P = (size_t)width * height, n = (size_t)count_labels;
     int32_t* d_lab = nullptr; float* d_age = nullptr; int* d_tab = nullptr;
-    AM_CUDA(cudaMalloc(&d_lab, P * 4));
-    if (ages) AM_CUDA(cudaMalloc(&d_age, P * 4));
-    AM_CUDA(cudaMalloc(&d_tab, n * 4 * 7));
-    int *mny = d_tab, *mxy = d_tab + n, *mnx = d_tab + 2 * n, *mxx = d_tab + 3 * n, *cnt = d_tab + 4 * n;
-    unsigned* agek = (unsigned*)(d_tab + 5 * n); float* oage = (float*)(d_tab + 6 * n);
-    AM_CUDA(cudaMemcpy(d_lab, labels, P * 4, cudaMemcpyHostToDevice));
-    if (ages) AM_CUDA(cudaMemcpy(d_age, ages, P * 4, cudaMemcpyHostToDevice));
-    k_ageb_init<<<am_div_up(count_labels, 256), 256>>>(count_labels, width, height, mny, mxy, mnx, mxx, cnt, agek);
-    k_ageb_scan<<<dim3(am_div_up(width, 256), height), 256>>>(d_lab, d_age, width, height, count_labels, mny, mxy, mnx, mxx, cnt, agek);
-    k_ageb_finish<<<am_div_up(count_labels, 256), 256>>>(count_labels, cnt, agek, oage);
-    AM_CUDA(cudaGetLastError());
-    AM_CUDA(cudaMemcpy(out_mins_y, mny, n * 4, cudaMemcpyDeviceToHost));
-    AM_CUDA(cudaMemcpy(out_maxs_y, mxy, n * 4, cudaMemcpyDeviceToHost));
-    AM_CUDA(cudaMemcpy(out_mins_x, mnx, n * 4, cudaMemcpyDeviceToHost));
-    AM_CUDA(cudaMemcpy(out_maxs_x, mxx, n * 4, cudaMemcpyDeviceToHost));
-    AM_CUDA(cudaMemcpy(out_counts, cnt, n * 4, cudaMemcpyDeviceToHost));
-    AM_CUDA(cudaMemcpy(output_age, oage, n * 4, cudaMemcpyDeviceToHost));
+    int* outs[6] = {out_mins_y, out_maxs_y, out_mins_x, out_maxs_x, out_counts, (int*)output_age};
+    const int src[6] = {0, 1, 2, 3, 4, 6};
+    int rc = AM_ERR_CUDA;
+    do {                                                   // single exit: the temporaries are freed on every path
+        if (cudaMalloc(&d_lab, P * 4) != cudaSuccess) break;
+        if (ages && cudaMalloc(&d_age, P * 4) != cudaSuccess) break;
+        if (cudaMalloc(&d_tab, (n * 10 + 4) * 4) != cudaSuccess) break;
+        if (cudaMemcpy(d_lab, labels, P * 4, cudaMemcpyHostToDevice) != cudaSuccess) break;
+        if (ages && cudaMemcpy(d_age, ages, P * 4, cudaMemcpyHostToDevice) != cudaSuccess) break;
+        if (ageb_run(d_lab, d_age, width, height, count_labels, d_tab, 0) != AM_OK) break;
+        bool ok = true;
+        for (int i = 0; i < 6 && ok; ++i)
+            ok = cudaMemcpy(outs[i], d_tab + (size_t)src[i] * n, n * 4, cudaMemcpyDeviceToHost) == cudaSuccess;
+        if (ok) rc = 0;
+    } while (0);
+    if (rc) { cudaError_t e = cudaGetLastError(); fprintf(stderr, "[accessmath_b200] CC_AgeBoundaries: CUDA error %d (%s)\n", (int)e, cudaGetErrorString(e)); }
     cudaFree(d_lab); cudaFree(d_age); cudaFree(d_tab);
-    return 0;
+    return rc;
+}
+// The same operator on DEVICE pointers (labels int32 [H][W], ages fp32 [H][W] or NULL = all zero; outputs 6 x n, d_scratch >= 10 n + 4
+// ints), asynchronous on `stream`: what Labeler uses when the label image is already resident (no PCIe round trip of 8 P bytes).
+extern "C" int am_cc_age_boundaries_dev(const int* d_labels, const float* d_ages, int width, int height, int count_labels, int* d_out6,
+                                        int* d_scratch, void* stream) {
+    if (count_labels <= 0) return AM_OK;
+    if (!d_labels || !d_out6 || !d_scratch || width <= 0 || height <= 0) return AM_ERR_ARG;
+    const size_t n = (size_t)count_labels;
+    int rc = ageb_run(d_labels, d_ages, width, height, count_labels, d_scratch, S(stream));
+    if (rc) return rc;
+    const int src[6] = {0, 1, 2, 3, 4, 6};
+    for (int i = 0; i < 6; ++i)
+        AM_CUDA(cudaMemcpyAsync(d_out6 + (size_t)i * n, d_scratch + (size_t)src[i] * n, n * 4, cudaMemcpyDeviceToDevice, S(stream)));
+    return AM_OK;
 }
 
 // ---- estimator ------------------------------------------------------------------------------
@@ -1366,8 +1426,8 @@ extern "C" int am_est_add_frames(am_estimator* e, am_cc_ctx* c, int first, int n
     if (!e || !c || first < 0 || n <= 0 || first + n > c->B) return AM_ERR_ARG;
     cudaStream_t st = S(stream);
     // default: ONE cooperative launch for the whole batch (k_match_fused); AM_B200_MATCH=multi keeps the six launches per frame
-    static int fused_mode = -1, fused_grid = 0;
-    if (fused_mode < 0) {
+    // the cooperative-launch configuration belongs to the estimator (= to the device it was created on), not to the process
+    if (e->fused_mode < 0) {
         const char* env = getenv("AM_B200_MATCH");
         int dev = 0, coop = 0, sms = 0, occ = 0;
         cudaGetDevice(&dev);
@@ -1378,9 +1438,10 @@ extern "C" int am_est_add_frames(am_estimator* e, am_cc_ctx* c, int first, int n
         int per_sm = genv ? atoi(genv) : 2;
         if (per_sm < 1) per_sm = 1;
         if (per_sm > occ) per_sm = occ;
-        fused_grid = sms * per_sm;
-        fused_mode = (coop && fused_grid >= 2 && !(env && strcmp(env, "multi") == 0)) ? 1 : 0;
+        e->fused_grid = sms * per_sm;
+        e->fused_mode = (coop && e->fused_grid >= 2 && !(env && strcmp(env, "multi") == 0)) ? 1 : 0;
     }
+    const int fused_mode = e->fused_mode, fused_grid = e->fused_grid;
     if (fused_mode == 1) {
         MatchArgs a;
         a.frames = c->d_frames; a.counts = c->d_counts; a.first = first; a.n = n; a.cur = e->cur;

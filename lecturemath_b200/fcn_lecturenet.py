@@ -585,14 +585,18 @@ class FCNPlan:
     def launches_per_run(self):
         return 1 + len(self.ops)
 
-    def run(self, stream, want_others=False, threshold=128, timing=None):
-        """frames (self.frames, uint8 BGR) -> self.logits / self.bits (and text_logit / rec when asked).
+    def run(self, stream, want_others=False, threshold=128, timing=None, frames=None):
+        """frames (uint8 BGR [B][H][W][3] device tensor; default self.frames) -> self.logits / self.bits (and text_logit /
+        rec when asked).  The plan is shared by every extractor of one (net, batch, size): callers that own their input
+        buffers pass them here instead of rebinding self.frames.
         timing: optional list; gets (op_index, start_event, end_event) per conv GEMM launch (CUDA events on the
         launching stream, which must be torch's current stream)."""
         lib, B, H, W = _lib.lib(), self.B, self.H, self.W
         st = ctypes.c_void_p(stream)
         chk = _lib.check
-        chk(lib.am_fcn_prep_input(self.frames.data_ptr(), B, H, W, self.x0.ptr, self.x0.C, self.x0.pad, st), "am_fcn_prep_input")
+        frames = self.frames if frames is None else frames
+        assert frames.is_cuda and frames.dtype == torch.uint8 and tuple(frames.shape) == (B, H, W, 3) and frames.is_contiguous()
+        chk(lib.am_fcn_prep_input(frames.data_ptr(), B, H, W, self.x0.ptr, self.x0.C, self.x0.pad, st), "am_fcn_prep_input")
         for i, (kind, a) in enumerate(self.ops):
             if kind == "conv":
                 if timing is not None:
@@ -609,7 +613,7 @@ class FCNPlan:
                 dst, yf, xf, vals = a
                 chk(lib.am_fcn_fill_border(dst.ptr, B, dst.H, dst.W, dst.C, dst.pad, yf, xf, vals.data_ptr(), st), "am_fcn_fill_border")
             elif kind == "heads_post":
-                chk(lib.am_fcn_heads_post(self.heads.data_ptr(), self.frames.data_ptr(), B, H, W, self.diff.ptr, self.diff.C, self.diff.pad,
+                chk(lib.am_fcn_heads_post(self.heads.data_ptr(), frames.data_ptr(), B, H, W, self.diff.ptr, self.diff.C, self.diff.pad,
                                           self.text_logit.data_ptr() if want_others else None,
                                           self.rec.data_ptr() if want_others else None, st), "am_fcn_heads_post")
             elif kind == "threshold":
@@ -751,7 +755,11 @@ class FCN_LectureNet:
     def forward(self, x0):
         """x0: (N,3,H,W) fp32 normalised as prepare_image does -> (output_logit, text_mask_logit, rec_img) CUDA fp32.
         The kernels start from the uint8 frame, so x0 is mapped back to its uint8 pixels (exact for prepare_image output)."""
-        u8 = torch.round((x0.detach().float().cpu() * 0.5 + 0.5) * 255.0).clamp(0, 255).to(torch.uint8)
+        x = x0.detach().float().cpu()
+        u8 = torch.round((x * 0.5 + 0.5) * 255.0).clamp(0, 255).to(torch.uint8)
+        if (((u8.float() / 255.0) - 0.5) / 0.5 - x).abs().max().item() > 1e-6:
+            raise ValueError("FCN_LectureNet.forward: the device path starts from uint8 pixels, so x0 must be prepare_image() output "
+                             "(values (v/255 - 0.5)/0.5 with integer v); got a tensor that is not representable that way")
         bgr = u8.permute(0, 2, 3, 1).flip(-1).contiguous()
         plan = self.binarize_frames(bgr, want_others=True)
         return (plan.logits.unsqueeze(1).clone(), plan.text_logit.unsqueeze(1).clone(), plan.rec.permute(0, 3, 1, 2).contiguous())

@@ -46,14 +46,15 @@ class Labeler:
             return []                                                   # labeler.py:133-135
         rows, crops = eng.kept_rows(0), eng.crops(0)
         min_age = None
-        if need_ages:                                                   # real ages: the legacy operator, on device
-            lab_h = labels[0].cpu().numpy()
-            outs = [np.zeros(n_labels, dtype=np.int32) for _ in range(5)] + [np.zeros(n_labels, dtype=np.float32)]
-            a = np.ascontiguousarray(ages, dtype=np.float32)
-            _lib.check(eng.lib.CC_AgeBoundaries(lab_h.ctypes.data_as(ctypes.c_void_p), a.ctypes.data_as(ctypes.c_void_p), width,
-                                                height, n_labels, *[o.ctypes.data_as(ctypes.c_void_p) for o in outs]),
-                       "CC_AgeBoundaries")
-            min_age = outs[5]
+        if need_ages:                                                   # real ages: CC_AgeBoundaries on the resident label image
+            n = n_labels
+            d_ages = torch.from_numpy(np.ascontiguousarray(ages, dtype=np.float32)).cuda(non_blocking=True)
+            d_out = torch.empty((6, n), dtype=torch.int32, device=labels.device)
+            d_tmp = torch.empty(10 * n + 4, dtype=torch.int32, device=labels.device)
+            _lib.check(eng.lib.am_cc_age_boundaries_dev(labels[0].data_ptr(), d_ages.data_ptr(), width, height, n, d_out.data_ptr(),
+                                                        d_tmp.data_ptr(), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                       "am_cc_age_boundaries_dev")
+            min_age = d_out[5].cpu().numpy().view(np.float32)
         comps = []
         for i in range(n_kept):
             _, lab, x0, x1, y0, y1, size, off = (int(v) for v in rows[i])

@@ -184,7 +184,8 @@ class StreamingExtractor:
         self.frames_in = self.large.frames if self.large.active else self.plan.frames
         # host frames arrive through a copy stream into two alternating device buffers, so the H2D copy of batch s overlaps
         # the kernels of batch s-1 (the copy engines are free even while the persistent conv kernels own every SM)
-        self.inbuf = [self.frames_in, torch.empty_like(self.frames_in)]
+        self.inbuf = [torch.empty_like(self.frames_in), torch.empty_like(self.frames_in)]     # this extractor's own buffers
+        self.fcn_in = torch.empty_like(self.plan.frames) if self.large.active else None          # LANCZOS-halved frames
         self.copy_stream = torch.cuda.Stream(self.device)
         # results leave through their own stream into pinned buffers: a read-back enqueued on the compute stream would queue up
         # BEHIND the next batch's kernels and stall the host for a whole step
@@ -208,16 +209,25 @@ class StreamingExtractor:
         self.step = 0
         self.launches = 0
         self.d2h_bytes = 0               # bytes collect() has copied device -> host
+        # ring ranks match chunk s-1 behind the FCN of chunk s (see submit); AM_B200_RING_LAG=1 restores the in-order form
+        self.lag = 2 if (world > 1 and os.environ.get("AM_B200_RING_LAG", "2") != "1") else 1
+        self._pending = None
+        self._matched_step = [-1] * depth
+        self.handoff_timeout_s = float(os.environ.get("AM_B200_HANDOFF_TIMEOUT", "120"))
 
-    def submit(self, frames, last=False, timing=None):
+    def submit(self, frames, last=False, timing=None, inject_bits=None):
         """Enqueue one batch (uint8 (batch,H,W,3) BGR; pinned host or device tensor).  `last`: no further batch follows on
-        ANY rank after this round (the final rank then keeps the state instead of sending it on)."""
-        import torch.distributed as dist
+        ANY rank after this round (the final rank then keeps the state instead of sending it on).
+        inject_bits: bit-packed CUDA masks (batch, H, WPR) that REPLACE the FCN's output for the CC stage (the FCN still runs):
+        measurement / test hook for dense-handwriting masks, which random-init weights never produce (BASELINE configs[3]).
+
+        Ring ranks (world > 1) are software-pipelined by one chunk: submit(s) enqueues FCN + labeling of chunk s FIRST and only
+        then the hand-off wait / import / matching / export of chunk s-1, so a predecessor that is late by up to one whole FCN
+        step costs this rank nothing (the stream never sleeps in front of work it could do).  Results of chunk s are therefore
+        complete `lag` submits later (lag = 2 on a ring, 1 alone); flush() enqueues the outstanding matching."""
         s, k = self.step, self.step % self.depth
         plan, eng = self.plan, self.engines[k]
         main = torch.cuda.current_stream(self.device)
-        need_recv = self.world > 1 and not (self.rank == 0 and s == 0)
-        need_send = self.world > 1 and not (last and self.rank == self.world - 1)
         kin = s & 1
         src = self.inbuf[kin]
         if frames.is_cuda:
@@ -230,16 +240,42 @@ class StreamingExtractor:
                 self.ev_in_ready[kin].record(self.copy_stream)
             main.wait_event(self.ev_in_ready[kin])
         if self.large.active:                                            # FCN_lecturenet.py:434-437 on the device
-            self.large.downscale(plan.frames, main.cuda_stream, src=src)
-        else:
-            plan.frames = src
-        plan.run(main.cuda_stream, False, 128, timing)
+            self.large.downscale(self.fcn_in, main.cuda_stream, src=src)
+            plan.run(main.cuda_stream, False, 128, timing, frames=self.fcn_in)
+        else:                                                            # the plan is shared (net.plan caches it): never rebind plan.frames
+            plan.run(main.cuda_stream, False, 128, timing, frames=src)
         if self.ev_in_free[kin] is None:
             self.ev_in_free[kin] = torch.cuda.Event()
         self.ev_in_free[kin].record(main)
         self.bits = self.large.upscale_bits(plan.bits, main.cuda_stream) if self.large.active else plan.bits   # :481-486
+        if inject_bits is not None:
+            self.bits = inject_bits
         eng.label(self.bits, want_labels=False, sync=False)
         self.launches += plan.launches_per_run + self.large.launches_per_run + LABEL_LAUNCHES
+        if self._pending is not None:                                    # ring: chunk s-1 is matched behind this chunk's FCN
+            self._match(*self._pending)
+            self._pending = None
+        if self.lag == 1:
+            self._match(s, last)
+        else:
+            self._pending = (s, last)
+        self.step += 1
+        return s
+
+    def flush(self):
+        """Enqueue whatever submit() deferred (the matching of the last chunk on a ring rank)."""
+        if self._pending is not None:
+            self._match(*self._pending)
+            self._pending = None
+
+    def _match(self, s, last):
+        """[await + import the predecessor's active set] -> temporal matching of chunk s -> pack rows -> [export to the successor]."""
+        import torch.distributed as dist
+        k = s % self.depth
+        eng = self.engines[k]
+        main = torch.cuda.current_stream(self.device)
+        need_recv = self.world > 1 and not (self.rank == 0 and s == 0)
+        need_send = self.world > 1 and not (last and self.rank == self.world - 1)
         st = ctypes.c_void_p(main.cuda_stream)
         if need_recv and self.handoff == "p2p":
             m = self.mail
@@ -267,20 +303,26 @@ class StreamingExtractor:
             dist.send(self.buf_send, dst=(self.rank + 1) % self.world)
             self.launches += 2
         self.ev_matched[k].record(main)
-        self.step += 1
-        return s
+        self._matched_step[k] = s
 
     def reset(self):
         """Start a new video: fresh temporal state, step counter back to 0 (all ranks must call it between videos)."""
+        self.flush()
         torch.cuda.current_stream(self.device).synchronize()
         self.est = Estimator(self.width, self.height, self.est_params[0], self.est_params[1], self.est_params[2], device=self.device)
         self.step = 0
+        self._matched_step = [-1] * self.depth
 
     def collect(self, s):
         """Result rows of batch s on the host: list (per frame) of int32 [n_cc][7] = (unique_idx, raw_label, min_x, max_x,
         min_y, max_y, size).  Must be called before batch s + depth is submitted."""
         k = s % self.depth
+        if self._matched_step[k] != s:
+            raise RuntimeError("collect(%d): the matching of that batch is not enqueued yet (results lag submit() by %d; call flush() "
+                               "after the last submit) or its slot was reused" % (s, self.lag))
         first = min(1024, self.rows[k].shape[0])                          # typical batches fit one round trip
+        if self.world > 1:
+            self._await(self.ev_matched[k], s)
         with torch.cuda.stream(self.d2h_stream):
             self.d2h_stream.wait_event(self.ev_matched[k])
             self.offs_h[k].copy_(self.offs[k], non_blocking=True)
@@ -297,8 +339,25 @@ class StreamingExtractor:
         self.d2h_bytes += offs.nbytes + 32 * max(first, total)
         return [rows[offs[f]:offs[f + 1], :7] for f in range(self.batch)]
 
+    def _await(self, event, s):
+        """Bounded wait of a ring rank: the stream sleeps in cuStreamWaitValue32 until the predecessor's chunk arrives, which
+        has no timeout of its own -- a dead peer must fail loudly here instead of hanging the ring."""
+        import time
+        t0 = time.monotonic()
+        while not event.query():
+            if time.monotonic() - t0 > self.handoff_timeout_s:
+                raise _lib.AccessMathB200Error(
+                    "ring hand-off stalled: batch %d of rank %d/%d was not matched within %.0f s (predecessor rank %d did not "
+                    "deliver its active set, or the successor never acknowledged)" % (s, self.rank, self.world, self.handoff_timeout_s,
+                                                                                    (self.rank - 1) % self.world))
+            time.sleep(0.0002)
+
     def finish(self):
         """Drain both streams and surface any capacity / hand-off failure recorded on the device."""
+        self.flush()
+        if self.world > 1 and self.step > 0:
+            last = (self.step - 1) % self.depth
+            self._await(self.ev_matched[last], self.step - 1)
         torch.cuda.current_stream(self.device).synchronize()
         for eng in self.engines:
             eng.batch = self.batch

@@ -186,3 +186,50 @@ def test_estimator_state_export_import_roundtrip(golden):
         got = np.array([(t,) + tuple(int(v) for v in row[:7]) for t in range(n) for row in rows[offs[t]:offs[t + 1]]], dtype=np.int64).reshape(-1, 8)
         np.testing.assert_array_equal(got, ref)
         assert b.state()["tempo_count"] == int(z["blobs_gap6_tempo"])
+
+
+def _chalk_masks_4k(n):
+    """Sparse 3840x2160 masks: the ink of the synthetic chalkboard video (strokes 230 on a 40 background, BASELINE configs[4])."""
+    from lecturemath_b200 import synth
+    return np.stack([(fr.max(axis=2) > 128).astype(np.uint8) * 255
+                     for fr in synth.whiteboard_frames(n, 2160, 3840, seed=21, chalk=True, strokes_per_frame=40)])
+
+
+@pytest.mark.parametrize("kind", ["chalk", "dense"])
+def test_4k_label_rows_crops_and_match_vs_oracle(kind):
+    """BASELINE configs[4]: the CC stage at 3840x2160 (am_cc_create picks R = 8 rows per strip there, a configuration the
+    1080p cases never reach).  Labels, the label table, kept rows, crops and an 8-frame temporal match: bit-exact vs the oracle."""
+    from lecturemath_b200 import synth
+    from lecturemath_b200.cc_engine import CCEngine, Estimator
+    from lecturemath_b200.connected_component import unpack_crop
+    n, h, w = 8, 2160, 3840
+    masks = _chalk_masks_4k(n) if kind == "chalk" else np.stack(list(synth.glyph_masks(n, h, w, seed=2)))
+    eng = CCEngine(w, h, n)
+    bits = eng.pack(torch.from_numpy(masks).cuda())
+    labels = eng.label(bits, want_labels=True)
+    est_o = O.StabilityOracle(w, h, 0.85, 0.85, 85)
+    est = Estimator(w, h, 0.85, 0.85, 85)
+    est.add_frames(eng, 0, n)
+    rows_d, offs_d = eng.packed_rows(n)
+    rows_d, offs_d = rows_d.cpu().numpy(), offs_d.cpu().numpy()
+    for f in range(n):
+        lab_o, n_lab = O.label4(masks[f])
+        assert int(eng.counts[f, 1]) == n_lab
+        if f < 2:                                                       # the 33 MB label image: two frames are enough
+            np.testing.assert_array_equal(labels[f].cpu().numpy(), lab_o)
+            ref_t = O.age_boundaries(lab_o, np.zeros(lab_o.shape, np.float32), n_lab)
+            for a, b in zip(eng.label_table(f), ref_t[:5]):
+                np.testing.assert_array_equal(a, b)
+        est_o.add_frame(masks[f])
+        ref = np.array(est_o.frame_table(f), dtype=np.int64).reshape(-1, 7)
+        np.testing.assert_array_equal(rows_d[offs_d[f]:offs_d[f + 1], :7].astype(np.int64), ref)
+        if f in (0, n - 1):                                             # crops of every kept CC against the oracle's images
+            rows, crops = eng.kept_rows(f), eng.crops(f)
+            comps, _, _ = O.extract_components(masks[f])
+            assert len(rows) == len(comps)
+            for r, c in zip(rows, comps):
+                got = unpack_crop(crops[r[7]:r[7] + ((r[3] >> 5) - (r[2] >> 5) + 1) * (r[5] - r[4] + 1)], r[2], r[3], r[4], r[5])
+                np.testing.assert_array_equal(got, c.img)
+    st = est.state()
+    assert st["tempo_count"] == est_o.tempo_count and st["n_unique"] == len(est_o.unique_cc_objects)
+    assert (len(est_o.unique_cc_objects) > 15000) if kind == "dense" else (len(est_o.unique_cc_objects) > 50)

@@ -19,6 +19,16 @@ def _sig(a):
     return 1.0 / (1.0 + np.exp(-a))
 
 
+def _check_mask(ink, ink_ref, p_ref):
+    """north_star bar: mask disagreement <= 0.1 % of pixels AND confined to near-threshold pixels, i.e. every pixel that
+    differs has a reference probability within PROB_TOL of the 128/255 decision point (ink = p*255 truncated < 128)."""
+    bad = ink != ink_ref
+    assert bad.mean() <= MASK_TOL, "mask disagreement %.4f %% (%d of %d pixels)" % (100 * bad.mean(), bad.sum(), bad.size)
+    if bad.any():
+        far = np.abs(p_ref[bad] - 128.0 / 255.0).max()
+        assert far < PROB_TOL, "a disagreeing pixel sits %.4f from the threshold in the reference" % far
+
+
 @pytest.mark.parametrize("tag", ["tiny", "full"])
 @pytest.mark.parametrize("mode", ["rowrun", "kx", "sy2", "mt1", "mt2", "mt4", "mt22", "poolall", "nopool"])
 def test_forward_vs_reference_golden(golden, tag, mode):
@@ -52,7 +62,7 @@ def test_forward_vs_reference_golden(golden, tag, mode):
     assert np.abs(_sig(plan.text_logit[0].cpu().numpy()) - _sig(z[tag + "_text_logit"])).max() < PROB_TOL
     assert np.abs(plan.rec[0].permute(2, 0, 1).cpu().numpy() - z[tag + "_rec_raw"]).max() < 2e-2
     ink, text_m, rec = net.masks_from_plan(plan, 0)
-    assert (ink != z[tag + "_binary"]).mean() <= 2 * MASK_TOL          # 10k-pixel image: 0.1 % = 10 pixels
+    _check_mask(ink, z[tag + "_binary"], _sig(z[tag + "_logit"]))
     assert np.abs(rec.astype(int) - z[tag + "_rec"].astype(int)).max() <= 3
 
 
@@ -65,7 +75,7 @@ def test_binarize_and_worker_api_vs_oracle(golden):
     frame = z["frame_bgr"]
     pil = Image.fromarray(cv2.cvtColor(frame, cv2.COLOR_RGB2BGR))
     binary, text_m, rec = net.binarize(pil, return_others=True, force_binary=True)
-    assert ((255 - binary) != z["tiny_binary"]).mean() <= 2 * MASK_TOL
+    _check_mask(255 - binary, z["tiny_binary"], _sig(z["tiny_logit"]))
     soft = net.binarize(pil)
     sd = {k: v for k, v in net.state_dict().items()}
     ref_soft, _, _ = FO.binarize(sd, frame[:, :, ::-1], force_binary=False)
@@ -76,7 +86,7 @@ def test_binarize_and_worker_api_vs_oracle(golden):
     assert worker.frame_indices == [7] and worker.frame_times == [40.0] and worker.getWorkName()
     decoded = cv2.imdecode(worker.compressed_frames[0], cv2.IMREAD_GRAYSCALE)
     np.testing.assert_array_equal(decoded, worker.last_binary)
-    assert (decoded != z["tiny_binary"]).mean() <= 2 * MASK_TOL
+    _check_mask(decoded, z["tiny_binary"], _sig(z["tiny_logit"]))
     lg, tx, rc = net.forward(net.prepare_image(pil))
     assert lg.shape == (1, 1) + frame.shape[:2] and rc.shape == (1, 3) + frame.shape[:2]
     assert np.abs(_sig(lg[0, 0].cpu().numpy()) - _sig(z["tiny_logit"])).max() < PROB_TOL
