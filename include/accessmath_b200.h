@@ -181,13 +181,29 @@ typedef struct am_conv_desc {
     int pool_H, pool_W;            /* out_H / 2, out_W / 2 */
     long long pool_sn, pool_sy;    /* element strides: frame, row */
     int pool_sx, pool_padx;        /* pixel stride (channels), left pad (pixels) */
+    /* optional fused epilogues of the two fp32 layers (`out` may then be NULL: the fp32 intermediate never reaches HBM):
+     * AM_EPI_HEADS (Cout = 4: text logit, reconstruction pre-tanh x3):  diff = (x0 - tanh(rec)) * sigmoid(text)
+     *   (FCN_lecturenet.py:370-377) as bf16 into diff_out[B][H][W+2*diff_pad][diff_C] (diff_C = 4 or 8, channels >= 3 zero), x0 read
+     *   from the uint8 BGR `frames` [B][H][W][3]; optional text_out fp32 [B][H][W], rec_out fp32 [B][H][W][3] (RGB, tanh applied).
+     * AM_EPI_THRESHOLD (Cout = 1, Sx % 16 == 0): ink <=> (uint8)(sigmoid(z) * 255) < threshold (FCN_lecturenet.py:452-467 and
+     *   `255 - binary`, FCN_lecturenet_binarizer.py:54) bit-packed into bits_out[B][H][bits_wpr] (bit b of word w = pixel 32w+b),
+     *   16 pixels per thread and store; `out` (fp32 logits [B][H][W]) is written as well when it is not NULL. */
+    int epi_mode;
+    const uint8_t* frames;
+    void* diff_out; int diff_C, diff_pad;
+    float* text_out; float* rec_out;
+    uint32_t* bits_out; int bits_wpr, threshold;
 } am_conv_desc;
+#define AM_EPI_PLAIN 0
+#define AM_EPI_HEADS 1
+#define AM_EPI_THRESHOLD 2
 #define AM_CONV_NO_RESIDENT 1      /* always stream the weights through the B ring */
 #define AM_CONV_NO_MT2 2           /* one M-tile per work item even when two would share the weight tiles */
 #define AM_CONV_FORCE_MT2 4        /* two M-tiles per work item (two MMA issuer warps) whenever TMEM and smem allow */
 #define AM_CONV_CTA_PAIR 16        /* cta_group::2: clusters of two CTAs run M = 256 MMAs, each CTA holds half of every weight tile */
 #define AM_CONV_EPI8 32            /* 8 epilogue warps take part (tensor-bound layers); default: chosen from K */
 #define AM_CONV_EPI16 64           /* all 16 epilogue warps (epilogue-bound layers: K <= 640) */
+#define AM_CONV_NO_EDGE_HALF 128    /* CTA pairs with 2-D packing: issue the two edge taps in y as full-N MMAs (tuning / debugging) */
 #define AM_CONV_FORCE_MT4 8        /* four M-tiles per work item (four MMA issuer warps, 12 epilogue warps): narrow N <= 128 layers */
 
 /* one launch: encodes the tensor maps, picks the tiling and runs the persistent tcgen05 kernel */
@@ -197,6 +213,14 @@ typedef struct am_conv_plan am_conv_plan;
 am_conv_plan* am_conv_plan_create(const am_conv_desc* desc);
 void am_conv_plan_destroy(am_conv_plan* plan);
 int am_conv_plan_launch(const am_conv_plan* plan, void* stream);
+/* re-bind the per-call pointers of a prepared launch (they are kernel arguments, not baked into the tensor maps): the frame batch
+ * AM_EPI_HEADS reads, and the optional fp32 outputs (NULL = do not write).  which = AM_BIND_*; takes effect at the next launch. */
+#define AM_BIND_FRAMES 0
+#define AM_BIND_TEXT_OUT 1
+#define AM_BIND_REC_OUT 2
+#define AM_BIND_OUT 3
+#define AM_BIND_THRESHOLD 4        /* ptr carries the integer threshold */
+int am_conv_plan_bind(am_conv_plan* plan, int which, void* ptr);
 /* info[8] = M-tiles per work item, resident weights (0/1), accumulator stages, A stages, B stages, grid, smem bytes, work items */
 int am_conv_plan_info(const am_conv_plan* plan, int* info);
 

@@ -57,6 +57,7 @@ SIGNATURES = {
     "am_conv_plan_destroy": (None, [c_void_p]),
     "am_conv_plan_launch": (c_int, [c_void_p, c_void_p]),
     "am_conv_plan_info": (c_int, [c_void_p, c_void_p]),
+    "am_conv_plan_bind": (c_int, [c_void_p, c_int, c_void_p]),
     "am_fcn_prep_input": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
     "am_fcn_maxpool2": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "am_fcn_fill_border": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),

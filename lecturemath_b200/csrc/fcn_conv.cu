@@ -44,6 +44,8 @@
 struct alignas(64) ConvParams {
     CUtensorMap tmA[2];
     CUtensorMap tmB;
+    CUtensorMap tmBq;    // CTA pairs with 2-D packing: box of NT/4 weight rows (one CTA's share of an edge tap, see edge_half)
+    int edge_half;       // 1: the first / last Toeplitz tap in y only feeds the sy = 0 / sy = 1 half of the columns -> N/2 MMAs
     int nseg;
     int seg_nkx[2];      // horizontal taps enumerated by separate loads (1 in row-run mode)
     int seg_nck[2];      // 64-element K chunks per (segment, kx)
@@ -71,6 +73,12 @@ struct alignas(64) ConvParams {
     unsigned nrt_magic, nyt_magic, nnb_magic;   // floor(2^32 / d) + 1 for d = nRT, nYT, nNB (0 when d == 1): exact for n * d < 2^32
     const float* bias;
     int* work_counter;    // [0] next work item (dynamic tile scheduler), [1] CTAs finished (the last one resets both)
+    // fused epilogues of the fp32 layers (am_conv_desc.epi_mode)
+    int epi_mode;
+    const uint8_t* frames; int img_H, img_W;
+    __nv_bfloat16* diff_out; int diff_C, diff_pad;
+    float* text_out; float* rec_out;
+    uint16_t* bits_out; int bits_hpr, threshold;      // halfwords per mask row
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -260,12 +268,80 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int t) {
     return c;
 }
 
+// Fused epilogues of the two fp32 layers.  They live in their own kernel instantiations (template parameter kFUSED): compiled into the
+// common kernels their registers (expf / tanhf, 16 live logits) spilled the GELU path of k_conv_gemm<1, true>, which is issue bound on
+// the K <= 640 layers (conv_down_block_1 and the transposed convs ran 20 % slower, profile r02_b).
+__device__ __forceinline__ void epi_heads(const ConvParams& p, const uint32_t (&v)[16], const float* __restrict__ sbias, int n0, int j0,
+                                          long long base, long long pbase, bool sy1_ok) {
+    // Cout = 4 columns per pixel: (text logit, reconstruction pre-tanh R, G, B).  diff = (x0 - tanh(rec)) * sigmoid(text)
+    // (FCN_lecturenet.py:370-377) goes straight to the bf16 `diff` buffer; the fp32 heads never reach HBM.
+    // `base` = pixel index (frame*H + Sy*y) * W + Sx*r of the unit's row (out_sx = 1 in this mode), `pbase` = frame*H + Sy*y.
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int n = n0 + j0 + 4 * i;
+        if (n >= p.Ntot) break;
+        const int grp = n >> 2;
+        const int sy = (p.Sy == 2 && grp >= p.Sx) ? 1 : 0, sx = grp - sy * p.Sx;
+        if (sy != 0 && !sy1_ok) continue;
+        const long long row = pbase + sy;                                          // frame*H + y
+        const int x = (int)(base - pbase * p.img_W) + sx;
+        const long long pix = row * p.img_W + x;
+        const float t = __uint_as_float(v[4 * i]) + sbias[j0 + 4 * i];
+        const float r0 = tanhf(__uint_as_float(v[4 * i + 1]) + sbias[j0 + 4 * i + 1]);
+        const float r1 = tanhf(__uint_as_float(v[4 * i + 2]) + sbias[j0 + 4 * i + 2]);
+        const float r2 = tanhf(__uint_as_float(v[4 * i + 3]) + sbias[j0 + 4 * i + 3]);
+        const float sg = 1.0f / (1.0f + expf(-t));                                   // torch.sigmoid(text_mask), :372
+        const uint8_t* px = p.frames + pix * 3;
+        const float x0r = ((float)px[2] / 255.0f - 0.5f) / 0.5f, x0g = ((float)px[1] / 255.0f - 0.5f) / 0.5f,
+                    x0b = ((float)px[0] / 255.0f - 0.5f) / 0.5f;                    // BGR -> RGB, prepare_image :607-618
+        const __nv_bfloat162 h0 = __floats2bfloat162_rn((x0r - r0) * sg, (x0g - r1) * sg);
+        const __nv_bfloat162 h1 = __floats2bfloat162_rn((x0b - r2) * sg, 0.0f);
+        __nv_bfloat16* o = p.diff_out + (row * (p.img_W + 2 * p.diff_pad) + x + p.diff_pad) * p.diff_C;
+        if (p.diff_C == 4) *(uint2*)o = make_uint2(*(const uint32_t*)&h0, *(const uint32_t*)&h1);
+        else *(uint4*)o = make_uint4(*(const uint32_t*)&h0, *(const uint32_t*)&h1, 0u, 0u);
+        if (p.text_out) p.text_out[pix] = t;
+        if (p.rec_out) { p.rec_out[pix * 3] = r0; p.rec_out[pix * 3 + 1] = r1; p.rec_out[pix * 3 + 2] = r2; }
+    }
+}
+__device__ __forceinline__ void epi_threshold(const ConvParams& p, const uint32_t (&v)[16], const float* __restrict__ sbias, int n0, int j0,
+                                              long long base, long long pbase, bool sy1_ok) {
+    // Cout = 1, Sx % 16 == 0: the unit's 16 columns are 16 consecutive pixels of one image row -> one 16-bit store of the
+    // bit-packed ink mask: ink <=> (uint8)(sigmoid(z) * 255) < threshold (FCN_lecturenet.py:461-467 + `255 - binary`)
+    const int n = n0 + j0;
+    if (n >= p.Ntot) return;
+    const int sy = (p.Sy == 2 && n >= p.Sx) ? 1 : 0, sx = n - sy * p.Sx;
+    if (sy != 0 && !sy1_ok) return;
+    const long long row = pbase + sy;                                              // frame*H + y; base = pixel index of (frame, Sy*y, Sx*r)
+    const int x = (int)(base - pbase * p.img_W) + sx;
+    const long long pix = row * p.img_W + x;
+    unsigned m = 0;
+    float* o = p.out != nullptr ? (float*)p.out + pix : nullptr;
+#pragma unroll
+    for (int i = 0; i < 16; i += 4) {
+        float z[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            z[k] = __uint_as_float(v[i + k]) + sbias[j0 + i + k];
+            const float sg = 1.0f / (1.0f + expf(-z[k]));
+            m |= ((int)(sg * 255.0f) < p.threshold ? 1u : 0u) << (i + k);
+        }
+        if (o) *(float4*)(o + i) = make_float4(z[0], z[1], z[2], z[3]);
+    }
+    p.bits_out[row * p.bits_hpr + (x >> 4)] = (uint16_t)m;
+}
+
 // Epilogue of one 16-column unit of one accumulator row: bias + activation + NHWC store.
 // With a fused max-pool (p.pool_out) EVERY lane of the warp calls this (row_ok only predicates the stores): the 2x2 block of an
 // output pixel sits in lanes l, l^1 (x) and l^RT (y), so the pooled value is two shuffle + max rounds on the packed bf16 pairs.
+template <bool kFUSED>
 __device__ __forceinline__ void epi_unit(const ConvParams& p, const uint32_t (&v)[16], const float* __restrict__ sbias, int n0, int j0,
                                          long long base, bool vec16, bool vec8, bool f32fast, bool sy1_ok, bool row_ok = true,
                                          long long pbase = 0, bool pool_ok = false) {
+    if (kFUSED) {                                          // the instantiations the two fp32 layers are launched with
+        if (p.epi_mode == AM_EPI_HEADS) epi_heads(p, v, sbias, n0, j0, base, pbase, sy1_ok);
+        else epi_threshold(p, v, sbias, n0, j0, base, pbase, sy1_ok);
+        return;
+    }
     if (vec16) {
         // Cout % 16 == 0: the unit's 16 columns are 16 consecutive channels of ONE output pixel -> one address
         // computation and one 32-byte store per unit (every GELU layer of the network takes this path)
@@ -409,7 +485,7 @@ __device__ __forceinline__ int sched_next(uint32_t schedFull, uint32_t schedEmpt
 // kMT = M-tiles per work item, kRES = weights resident in shared memory (compile-time so the single-warp issue loops stay short)
 // kMT = 4 (four issuer warps, warps 1..4) takes the epilogue down to 12 warps (8..19) so that the CTA stays at 640 threads
 // (96 registers each: 20 warps is what the register file holds).
-template <int kMT, bool kRES>
+template <int kMT, bool kRES, bool kFUSED>
 __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv_gemm(const __grid_constant__ ConvParams p) {
     constexpr int kEpiFirst = (kMT == 4) ? 8 : 4;                      // first epilogue warp (multiple of 4: TMEM lane quarters)
     constexpr int kEpiWarps = (CONV_THREADS / 32) - kEpiFirst;
@@ -632,6 +708,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv_gemm(const __grid_cons
                         pbase = (long long)tc.frame * p.pool_sn + (long long)(y >> 1) * p.pool_sy + (long long)((r >> 1) + p.pool_padx) * p.pool_sx;
                     }
                     base = (long long)tc.frame * p.out_sn + (long long)(p.Sy * y) * p.out_sy + (long long)(p.Sx * r + p.out_padx) * p.out_sx + p.out_coff;
+                    if (p.epi_mode != AM_EPI_PLAIN) pbase = (long long)tc.frame * p.out_H + (long long)(p.Sy * y);
                     if (p.Sy * y >= p.out_H || p.Sx * r + p.Sx > p.out_W) row_ok = false;
                     sy1_ok = p.Sy * y + 1 < p.out_H;                               // odd image height: the last row pair has no second row
                 }
@@ -643,13 +720,13 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv_gemm(const __grid_cons
                 tmem_wait16(va);
                 int g2 = g + epiPerQ;
                 if (g2 < units) tmem_ld16_async(unit_addr(g2), vb);
-                { const int j0 = enter(g); if (row_ok || p.pool_out != nullptr) epi_unit(p, va, sbias, n0, j0, base, vec16, vec8, f32fast, sy1_ok, row_ok, pbase, pool_ok); }
+                { const int j0 = enter(g); if (row_ok || p.pool_out != nullptr) epi_unit<kFUSED>(p, va, sbias, n0, j0, base, vec16, vec8, f32fast, sy1_ok, row_ok, pbase, pool_ok); }
                 g = g2;
                 if (g >= units) break;
                 tmem_wait16(vb);
                 g2 = g + epiPerQ;
                 if (g2 < units) tmem_ld16_async(unit_addr(g2), va);
-                { const int j0 = enter(g); if (row_ok || p.pool_out != nullptr) epi_unit(p, vb, sbias, n0, j0, base, vec16, vec8, f32fast, sy1_ok, row_ok, pbase, pool_ok); }
+                { const int j0 = enter(g); if (row_ok || p.pool_out != nullptr) epi_unit<kFUSED>(p, vb, sbias, n0, j0, base, vec16, vec8, f32fast, sy1_ok, row_ok, pbase, pool_ok); }
                 g = g2;
             }
             // all tcgen05.ld of this stage have completed (tmem_wait16 in the last iteration): hand the stage back
@@ -716,6 +793,7 @@ __device__ __forceinline__ void tc2_mma_bf16(uint32_t tmem_d, uint64_t adesc, ui
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
+template <bool kFUSED>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) k_conv_gemm_pair(const __grid_constant__ ConvParams p) {
     constexpr int kMT = 2;                               // M-tiles per CTA (4 per work item)
     constexpr int kEpiFirst = 4, kEpiWarps = (CONV_THREADS / 32) - kEpiFirst, kEpiPerQ = kEpiWarps / 4;
@@ -746,6 +824,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) k_c
         tma_prefetch_desc(&p.tmA[0]);
         if (p.nseg > 1) tma_prefetch_desc(&p.tmA[1]);
         tma_prefetch_desc(&p.tmB);
+        if (p.edge_half) tma_prefetch_desc(&p.tmBq);
     }
     if (warp == 1) {                                     // the same warp of both CTAs allocates the pair's tensor memory
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)p.tmem_cols) : "memory");
@@ -784,11 +863,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) k_c
                         }
                         __syncwarp();
                         if (++sa == p.stagesA) { sa = 0; pa ^= 1; }
-                        for (int dy = 0; dy < p.KH; ++dy) {
+                        for (int t = 0; t < p.KH; ++t) {
+                            // edge_half: taps in the order 1 .. KH-2, 0, KH-1 (the item's first MMA must cover all columns); the two
+                            // edge taps only carry the sy = 0 resp. sy = 1 half of the weight rows, a quarter per CTA
+                            const int dy = !p.edge_half ? t : (t < p.KH - 2 ? t + 1 : (t == p.KH - 2 ? 0 : p.KH - 1));
+                            const bool edge = p.edge_half && t >= p.KH - 2;
                             mbar_wait_uniform(emptyB + 8 * sb, pb ^ 1);
                             if (elect_one()) {
-                                if (rank == 0) mbar_expect_tx(fullB + 8 * sb, 2 * bytesBh);
-                                tma2_load_2d(sB0 + bytesBh * sb, &p.tmB, fullB_l + 8 * sb, 0, (chunk * p.KH + dy) * p.Ntot_pad + n0);
+                                if (!edge) {
+                                    if (rank == 0) mbar_expect_tx(fullB + 8 * sb, 2 * bytesBh);
+                                    tma2_load_2d(sB0 + bytesBh * sb, &p.tmB, fullB_l + 8 * sb, 0, (chunk * p.KH + dy) * p.Ntot_pad + n0);
+                                } else {
+                                    if (rank == 0) mbar_expect_tx(fullB + 8 * sb, bytesBh);
+                                    tma2_load_2d(sB0 + bytesBh * sb, &p.tmBq, fullB_l + 8 * sb, 0,
+                                                 (chunk * p.KH + dy) * p.Ntot_pad + (dy == 0 ? 0 : (p.NT >> 1)) + (int)rank * (p.NT >> 2));
+                                }
                             }
                             __syncwarp();
                             if (++sb == p.stagesB) { sb = 0; pb ^= 1; }
@@ -802,8 +891,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) k_c
             // ===================== MMA issuer of M-tile pair `mt` (leader CTA only) =====================
             const int mt = warp - 1;
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NT >> 3) << 17) | ((256u >> 4) << 24);
+            const uint32_t idesc_half = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NT >> 4) << 17) | ((256u >> 4) << 24);
             const int KH = p.KH, stagesA = p.stagesA, stagesB = p.stagesB, acc_stages = p.acc_stages, nseg = p.nseg;
-            const uint32_t NTc = (uint32_t)p.NTc;
+            const int edge_half = p.edge_half;
+            const uint32_t NTc = (uint32_t)p.NTc, NT = (uint32_t)p.NT;
             const uint32_t dy_step = ((uint32_t)p.RT * 128u) >> 4, b_step = bytesBh >> 4, a_step = bytesA >> 4;
             const uint32_t a_lo0 = desc_lo(sA0 + bytesA1 * (uint32_t)mt), b_lo0 = desc_lo(sB0);
             const uint64_t hiA = desc_hi_sw128(1024u * (uint32_t)p.ystep), hiB = desc_hi_sw128(1024u);
@@ -821,21 +912,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) k_c
                         if (++ck == nck) ck = 0;
                         mbar_wait_uniform(fullA + 8 * sa, pa);
                         tc_fence_after();
-                        uint32_t alo = a_lo0 + a_step * (uint32_t)sa;
-                        for (int dy = 0; dy < KH; ++dy) {
+                        const uint32_t alo0 = a_lo0 + a_step * (uint32_t)sa;
+                        for (int t = 0; t < KH; ++t) {
+                            const int dy = !edge_half ? t : (t < KH - 2 ? t + 1 : (t == KH - 2 ? 0 : KH - 1));      // see the producer
+                            const bool edge = edge_half && t >= KH - 2;
+                            const uint32_t alo = alo0 + dy_step * (uint32_t)dy;
+                            const uint32_t idx = edge ? idesc_half : idesc;
+                            const uint32_t tdd = (edge && dy != 0) ? td + (NT >> 1) : td;        // sy = 1 columns
                             mbar_wait_uniform(fullB + 8 * sb, pb);
                             tc_fence_after();
                             const uint32_t blo = b_lo0 + b_step * (uint32_t)sb;
                             if (elect_one()) {
-                                tc2_mma_bf16(td, hiA | alo, hiB | blo, idesc, acc);
-                                if (ksteps > 1) tc2_mma_bf16(td, hiA | (alo + 2), hiB | (blo + 2), idesc, 1);
-                                if (ksteps > 2) tc2_mma_bf16(td, hiA | (alo + 4), hiB | (blo + 4), idesc, 1);
-                                if (ksteps > 3) tc2_mma_bf16(td, hiA | (alo + 6), hiB | (blo + 6), idesc, 1);
+                                tc2_mma_bf16(tdd, hiA | alo, hiB | blo, idx, acc);
+                                if (ksteps > 1) tc2_mma_bf16(tdd, hiA | (alo + 2), hiB | (blo + 2), idx, 1);
+                                if (ksteps > 2) tc2_mma_bf16(tdd, hiA | (alo + 4), hiB | (blo + 4), idx, 1);
+                                if (ksteps > 3) tc2_mma_bf16(tdd, hiA | (alo + 6), hiB | (blo + 6), idx, 1);
                                 tc2_commit(emptyB + 8 * sb);
                             }
                             __syncwarp();
                             acc = 1;
-                            alo += dy_step;
                             if (++sb == stagesB) { sb = 0; pb ^= 1; }
                         }
                         if (elect_one()) tc2_commit(emptyA + 8 * sa);
@@ -899,6 +994,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) k_c
                         pbase = (long long)tc.frame * p.pool_sn + (long long)(y >> 1) * p.pool_sy + (long long)((r >> 1) + p.pool_padx) * p.pool_sx;
                     }
                     base = (long long)tc.frame * p.out_sn + (long long)(p.Sy * y) * p.out_sy + (long long)(p.Sx * r + p.out_padx) * p.out_sx + p.out_coff;
+                    if (p.epi_mode != AM_EPI_PLAIN) pbase = (long long)tc.frame * p.out_H + (long long)(p.Sy * y);
                     if (p.Sy * y >= p.out_H || p.Sx * r + p.Sx > p.out_W) row_ok = false;
                     sy1_ok = p.Sy * y + 1 < p.out_H;
                 }
@@ -910,13 +1006,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) k_c
                 tmem_wait16(va);
                 int g2 = g + epiPerQ;
                 if (g2 < units) tmem_ld16_async(unit_addr(g2), vb);
-                { const int j0 = enter(g); if (row_ok || p.pool_out != nullptr) epi_unit(p, va, sbias, n0, j0, base, vec16, vec8, f32fast, sy1_ok, row_ok, pbase, pool_ok); }
+                { const int j0 = enter(g); if (row_ok || p.pool_out != nullptr) epi_unit<kFUSED>(p, va, sbias, n0, j0, base, vec16, vec8, f32fast, sy1_ok, row_ok, pbase, pool_ok); }
                 g = g2;
                 if (g >= units) break;
                 tmem_wait16(vb);
                 g2 = g + epiPerQ;
                 if (g2 < units) tmem_ld16_async(unit_addr(g2), va);
-                { const int j0 = enter(g); if (row_ok || p.pool_out != nullptr) epi_unit(p, vb, sbias, n0, j0, base, vec16, vec8, f32fast, sy1_ok, row_ok, pbase, pool_ok); }
+                { const int j0 = enter(g); if (row_ok || p.pool_out != nullptr) epi_unit<kFUSED>(p, vb, sbias, n0, j0, base, vec16, vec8, f32fast, sy1_ok, row_ok, pbase, pool_ok); }
                 g = g2;
             }
             tc_fence_before();
@@ -1032,6 +1128,19 @@ static int conv_prepare(const am_conv_desc* d, am_conv_plan* plan) {
         int rc = encode_map(&p.tmB, (void*)d->weights, 2, dims, strides, box);
         if (rc) return rc;
     }
+    // 2-D packing (Sy = 2): the Toeplitz extension in y leaves the first vertical tap with weights for the sy = 0 columns only and the
+    // last one for the sy = 1 columns only.  A CTA pair issues those two taps as N/2 MMAs (half the tensor and weight-read time of
+    // 2 of the KH taps) when the whole layer is one N block whose halves are exactly the two sy groups.  N >= 128 only: below that
+    // an MMA is bound by the shared-memory read of A, and the narrower edge MMAs only add issue slots (conv_out + 11 %, r02_d).
+    p.edge_half = (pair && ystep == 2 && d->Sy == 2 && d->KH >= 4 && d->Ntot_pad == d->NT && d->Ntot == d->NT && d->NT % 32 == 0 && d->NT >= 128 &&
+                   !(d->flags & AM_CONV_NO_EDGE_HALF)) ? 1 : 0;
+    if (p.edge_half) {
+        unsigned long long dims[2] = {64ull, (unsigned long long)total_chunks * d->KH * d->Ntot_pad};
+        unsigned long long strides[1] = {128ull};
+        unsigned box[2] = {64u, (unsigned)(d->NT / 4)};
+        int rc = encode_map(&p.tmBq, (void*)d->weights, 2, dims, strides, box);
+        if (rc) return rc;
+    }
     p.KH = d->KH; p.RT = d->RT; p.YT = d->YT; p.padY = d->padY; p.ystep = ystep;
     p.logRT = 0; while ((1 << p.logRT) < d->RT) ++p.logRT;
     p.nRT = (d->nR + d->RT - 1) / d->RT; p.nYT = (d->Hin + d->YT - 1) / d->YT; p.batch = d->batch;
@@ -1052,6 +1161,24 @@ static int conv_prepare(const am_conv_desc* d, am_conv_plan* plan) {
             return AM_ERR_ARG;
         }
     }
+    p.epi_mode = d->epi_mode; p.frames = d->frames; p.img_H = d->out_H; p.img_W = d->out_W;
+    p.diff_out = (__nv_bfloat16*)d->diff_out; p.diff_C = d->diff_C; p.diff_pad = d->diff_pad;
+    p.text_out = d->text_out; p.rec_out = d->rec_out;
+    p.bits_out = (uint16_t*)d->bits_out; p.bits_hpr = 2 * d->bits_wpr; p.threshold = d->threshold;
+    if (d->epi_mode == AM_EPI_HEADS) {
+        if (d->Cout != 4 || !d->out_f32 || !d->diff_out || !d->frames || (d->diff_C != 4 && d->diff_C != 8) || d->out_sx != 1 ||
+            d->out_sy != d->out_W || d->out_sn != (long long)d->out_H * d->out_W || d->out_padx != 0 || d->out_coff != 0 || d->pool_out) {
+            fprintf(stderr, "[accessmath_b200] am_conv: AM_EPI_HEADS needs Cout = 4, fp32 geometry, a diff buffer with 4 or 8 channels\n");
+            return AM_ERR_ARG;
+        }
+    } else if (d->epi_mode == AM_EPI_THRESHOLD) {
+        if (d->Cout != 1 || !d->out_f32 || !d->bits_out || d->Sx % 16 != 0 || d->out_W % 16 != 0 || d->out_sx != 1 ||
+            d->out_sy != d->out_W || d->out_sn != (long long)d->out_H * d->out_W || d->out_padx != 0 || d->out_coff != 0 || d->pool_out ||
+            d->bits_wpr * 32 < d->out_W) {
+            fprintf(stderr, "[accessmath_b200] am_conv: AM_EPI_THRESHOLD needs Cout = 1, Sx %% 16 == 0, width %% 16 == 0\n");
+            return AM_ERR_ARG;
+        }
+    } else if (d->epi_mode != AM_EPI_PLAIN || !d->out) return AM_ERR_ARG;
     p.cout_magic = d->Cout >= 2 ? (unsigned)((1ull << 32) / (unsigned long long)d->Cout) + 1u : 0u;
     auto magic = [](int dv) -> unsigned { return dv >= 2 ? (unsigned)((1ull << 32) / (unsigned long long)dv) + 1u : 0u; };
     p.nrt_magic = magic(p.nRT); p.nyt_magic = magic(p.nYT); p.nnb_magic = magic(p.nNB);
@@ -1139,21 +1266,25 @@ static int conv_prepare(const am_conv_desc* d, am_conv_plan* plan) {
 
 typedef void (*conv_kernel_t)(const ConvParams);
 static int conv_launch(const am_conv_plan* plan, void* stream) {
-    static const conv_kernel_t kernels[6] = {k_conv_gemm<1, false>, k_conv_gemm<1, true>, k_conv_gemm<2, false>, k_conv_gemm<2, true>,
-                                             k_conv_gemm<4, false>, k_conv_gemm<4, true>};
+    // [fused epilogue][MT 1 / 2 / 4][streamed / resident weights], then the two CTA-pair kernels
+    static const conv_kernel_t kernels[14] = {
+        k_conv_gemm<1, false, false>, k_conv_gemm<1, true, false>, k_conv_gemm<2, false, false>, k_conv_gemm<2, true, false>,
+        k_conv_gemm<4, false, false>, k_conv_gemm<4, true, false>,
+        k_conv_gemm<1, false, true>, k_conv_gemm<1, true, true>, k_conv_gemm<2, false, true>, k_conv_gemm<2, true, true>,
+        k_conv_gemm<4, false, true>, k_conv_gemm<4, true, true>,
+        k_conv_gemm_pair<false>, k_conv_gemm_pair<true>};
     static bool attr_set = false;
     if (!attr_set) {
-        for (int i = 0; i < 6; ++i) AM_CUDA(cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+        for (int i = 0; i < 14; ++i) AM_CUDA(cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
         attr_set = true;
     }
+    const int fused = plan->p.epi_mode != AM_EPI_PLAIN ? 1 : 0;
     if (plan->pair) {
-        static bool pair_attr = false;
-        if (!pair_attr) { AM_CUDA(cudaFuncSetAttribute(k_conv_gemm_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024))); pair_attr = true; }
-        k_conv_gemm_pair<<<plan->grid, CONV_THREADS, plan->smem, (cudaStream_t)stream>>>(plan->p);      // __cluster_dims__(2,1,1)
+        kernels[12 + fused]<<<plan->grid, CONV_THREADS, plan->smem, (cudaStream_t)stream>>>(plan->p);      // __cluster_dims__(2,1,1)
         AM_CUDA(cudaGetLastError());
         return AM_OK;
     }
-    const conv_kernel_t k = kernels[(plan->p.MT == 4 ? 4 : plan->p.MT == 2 ? 2 : 0) + (plan->p.residentB ? 1 : 0)];
+    const conv_kernel_t k = kernels[6 * fused + (plan->p.MT == 4 ? 4 : plan->p.MT == 2 ? 2 : 0) + (plan->p.residentB ? 1 : 0)];
     k<<<plan->grid, CONV_THREADS, plan->smem, (cudaStream_t)stream>>>(plan->p);
     AM_CUDA(cudaGetLastError());
     return AM_OK;
@@ -1186,6 +1317,20 @@ extern "C" void am_conv_plan_destroy(am_conv_plan* plan) {
 extern "C" int am_conv_plan_launch(const am_conv_plan* plan, void* stream) {
     if (!plan) return AM_ERR_ARG;
     return conv_launch(plan, stream);
+}
+extern "C" int am_conv_plan_bind(am_conv_plan* plan, int which, void* ptr) {
+    if (!plan) return AM_ERR_ARG;
+    switch (which) {
+    case AM_BIND_FRAMES: plan->p.frames = (const uint8_t*)ptr; break;
+    case AM_BIND_TEXT_OUT: plan->p.text_out = (float*)ptr; break;
+    case AM_BIND_REC_OUT: plan->p.rec_out = (float*)ptr; break;
+    case AM_BIND_OUT:
+        if (!ptr && plan->p.epi_mode == AM_EPI_PLAIN) return AM_ERR_ARG;
+        plan->p.out = ptr; break;
+    case AM_BIND_THRESHOLD: plan->p.threshold = (int)(intptr_t)ptr; break;
+    default: return AM_ERR_ARG;
+    }
+    return AM_OK;
 }
 // info[8] = MT, residentB, acc_stages, stagesA, stagesB, grid, smem bytes, n_work
 extern "C" int am_conv_plan_info(const am_conv_plan* plan, int* info) {

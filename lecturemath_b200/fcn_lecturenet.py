@@ -78,7 +78,14 @@ class ConvDesc(ctypes.Structure):
                 ("out_sx", ctypes.c_int), ("out_padx", ctypes.c_int), ("out_coff", ctypes.c_int),
                 ("Cout", ctypes.c_int), ("Sy", ctypes.c_int), ("Sx", ctypes.c_int), ("act", ctypes.c_int), ("flags", ctypes.c_int), ("in_ystep", ctypes.c_int),
                 ("pool_out", ctypes.c_void_p), ("pool_H", ctypes.c_int), ("pool_W", ctypes.c_int),
-                ("pool_sn", ctypes.c_longlong), ("pool_sy", ctypes.c_longlong), ("pool_sx", ctypes.c_int), ("pool_padx", ctypes.c_int)]
+                ("pool_sn", ctypes.c_longlong), ("pool_sy", ctypes.c_longlong), ("pool_sx", ctypes.c_int), ("pool_padx", ctypes.c_int),
+                ("epi_mode", ctypes.c_int), ("frames", ctypes.c_void_p), ("diff_out", ctypes.c_void_p), ("diff_C", ctypes.c_int),
+                ("diff_pad", ctypes.c_int), ("text_out", ctypes.c_void_p), ("rec_out", ctypes.c_void_p), ("bits_out", ctypes.c_void_p),
+                ("bits_wpr", ctypes.c_int), ("threshold", ctypes.c_int)]
+
+
+AM_EPI_PLAIN, AM_EPI_HEADS, AM_EPI_THRESHOLD = 0, 1, 2
+AM_BIND_FRAMES, AM_BIND_TEXT_OUT, AM_BIND_REC_OUT, AM_BIND_OUT, AM_BIND_THRESHOLD = 0, 1, 2, 3, 4
 
 
 def fold_bn(w, b, bn_w, bn_b, mean, var, out_dim=0):
@@ -299,8 +306,16 @@ class FCNPlan:
         self.mid = mk(5, mid, 0)
         self.t = [mk(i, ups[i], p3) for i in range(5)]                   # transposed-conv outputs (level i)
         self.u = [mk(i, upc[i], 0 if i > 0 else p7) for i in range(5)]   # conv_up outputs; u[0] = x_up1
-        self.heads = torch.zeros((B, H, W, 4), dtype=torch.float32, device=device)
-        self.diff = mk(0, 8, p7)
+        # `diff` has 3 channels: 4 per pixel when every consumer reads it through a row-run view whose row stride S * 4 * 2 bytes is a
+        # multiple of 16 (TMA), i.e. S even -- the 7x7 layers then pad 35 -> 36 input channels instead of 35 -> 40; else 8
+        dc = 4
+        if not rowrun or self.ov.get("diff_c") == 8:
+            dc = 8
+        else:
+            for name, cout, cin, cap in (("conv_pixels_1", pm1, upc[0], None), ("conv_pixels_2", pm2, pm1, None), ("conv_out", 1, pm2, 64)):
+                if self._pick_config(name, W, H, cout, [cin, 4], pk, pk, cap)[0] % 2:
+                    dc = 8
+        self.diff = mk(0, dc, p7)
         self.px1, self.px2 = mk(0, pm1, p7), mk(0, pm2, p7)
         self.logits = torch.zeros((B, H, W), dtype=torch.float32, device=device)
         self.text_logit = torch.zeros((B, H, W), dtype=torch.float32, device=device)
@@ -350,18 +365,24 @@ class FCNPlan:
         o = (pk - k) // 2
         wh[1:4, :, o:o + k, o:o + k] = wr_
         f0 = self.flops
-        self._conv("heads", wh, torch.cat([bt_, br_]), [(self.u[0], ident(upc[0]))], None, act=0, cap=16, f32_out=self.heads)
+        # ... whose epilogue applies tanh / sigmoid and writes diff = (x0 - rec) * sigmoid(text) (:370-377) directly (AM_EPI_HEADS)
+        self._conv("heads", wh, torch.cat([bt_, br_]), [(self.u[0], ident(upc[0]))], None, act=0, cap=16, epi=AM_EPI_HEADS)
         self.flops = f0 + 2 * H * W * upc[0] * (pk * pk + 3 * k * k)     # algorithmic: 7x7x1 + 3x3x3, not the padded GEMM
         self.op_flops[len(self.ops) - 1] = self.flops - f0
-        self.ops.append(("heads_post", None))
-        dmap = [0, 1, 2] + [-1] * 5
+        self.heads_op = len(self.ops) - 1
+        dmap = [0, 1, 2] + [-1] * (dc - 3)
         w, b = cbn("conv_pixels_1")       # reference input order: (diff 0..2, x_up1)  (:383)
         self._conv("conv_pixels_1", w, b, [(self.u[0], [3 + c for c in range(upc[0])]), (self.diff, dmap)], self.px1, act=1)
         w, b = cbn("conv_pixels_2")
         self._conv("conv_pixels_2", w, b, [(self.px1, [3 + c for c in range(pm1)]), (self.diff, dmap)], self.px2, act=1)
         w, b = cbn("conv_out")
-        self._conv("conv_out", w, b, [(self.px2, [3 + c for c in range(pm2)]), (self.diff, dmap)], None, act=0, cap=64, f32_out=self.logits)
-        self.ops.append(("threshold", None))
+        # conv_out: sigmoid-threshold + bit-packing in the epilogue (AM_EPI_THRESHOLD) when a GEMM row holds whole 16-pixel runs
+        self._conv("conv_out", w, b, [(self.px2, [3 + c for c in range(pm2)]), (self.diff, dmap)], None, act=0, cap=64, f32_out=self.logits,
+                   epi=AM_EPI_THRESHOLD)
+        self.out_op = len(self.ops) - 1
+        self.fused_threshold = self.ops[self.out_op][1].epi_mode == AM_EPI_THRESHOLD
+        if not self.fused_threshold:
+            self.ops.append(("threshold", None))
 
     @staticmethod
     def count_flops(net, H, W):
@@ -419,14 +440,15 @@ class FCNPlan:
                 best = c
         return best[1], best[2], best[3], best[4]
 
-    def _conv(self, name, w, b, srcs, dst, act, cap=None, f32_out=None, pool_dst=None):
-        """pool_dst: buffer for MaxPool2d(2) of the output; returns True when the pool was fused into this conv's epilogue."""
+    def _conv(self, name, w, b, srcs, dst, act, cap=None, f32_out=None, pool_dst=None, epi=AM_EPI_PLAIN):
+        """pool_dst: buffer for MaxPool2d(2) of the output; returns True when the pool was fused into this conv's epilogue.
+        epi: fused epilogue of the fp32 layers (AM_EPI_HEADS / AM_EPI_THRESHOLD, include/accessmath_b200.h)."""
         nrows, cin_total, KH, KW = w.shape
         first = srcs[0][0]
         cfg = self._pick_config(name, first.W, first.H, nrows, [buf.C for buf, _ in srcs], KW, KH, cap)
         self.specs[name] = dict(kind="conv", w=w, b=b, srcs=srcs, dst=dst, act=act, cap=cap, f32_out=f32_out, op=len(self.ops), cfg=cfg,
-                                pool_dst=pool_dst)
-        d, keep = self._conv_desc(w, b, srcs, dst, act, f32_out, cfg, pool_dst)
+                                pool_dst=pool_dst, epi=epi)
+        d, keep = self._conv_desc(w, b, srcs, dst, act, f32_out, cfg, pool_dst, epi)
         self.keep += keep
         self.ops.append(("conv", d))
         fused = bool(d.pool_out)
@@ -434,7 +456,7 @@ class FCNPlan:
         self.flops += 2 * first.H * first.W * nrows * cin_total * KH * KW
         return fused
 
-    def _conv_desc(self, w, b, srcs, dst, act, f32_out, cfg, pool_dst=None):
+    def _conv_desc(self, w, b, srcs, dst, act, f32_out, cfg, pool_dst=None, epi=AM_EPI_PLAIN):
         """Kernel descriptor (+ the packed tensors it points to) of one convolution for configuration cfg = (S, Sy, NT, MT)."""
         nrows, cin_total, KH, KW = w.shape
         first = srcs[0][0]
@@ -457,7 +479,20 @@ class FCNPlan:
         d.nR, d.Hin, d.batch = Win // S, Hin, self.B
         d.RT, d.YT = (8, 16) if Sy == 2 else choose_tile(d.nR, Hin, KH)
         d.NT, d.Ntot, d.Ntot_pad = NT, ntot, ntot_pad
-        if f32_out is not None:
+        if epi == AM_EPI_THRESHOLD and (nrows != 1 or S % 16 or Win % 16 or not self.rowrun):
+            epi = AM_EPI_PLAIN                                            # legacy path: fp32 logits + k_threshold_pack
+        d.epi_mode = epi
+        if epi != AM_EPI_PLAIN:                                           # pixel geometry: element = pixel of the fp32 [B][H][W] planes
+            d.out, d.out_f32 = (f32_out.data_ptr() if f32_out is not None else None), 1
+            d.out_H, d.out_W = Himg, Win
+            d.out_sx, d.out_sy, d.out_sn = 1, Win, Himg * Win
+            d.out_padx, d.out_coff = 0, 0
+            if epi == AM_EPI_HEADS:
+                d.frames = self.frames.data_ptr()
+                d.diff_out, d.diff_C, d.diff_pad = self.diff.ptr, self.diff.C, self.diff.pad
+            else:
+                d.bits_out, d.bits_wpr, d.threshold = self.bits.data_ptr(), self.wpr, 128
+        elif f32_out is not None:
             d.out, d.out_f32 = f32_out.data_ptr(), 1
             d.out_H, d.out_W = Himg, Win
             d.out_sx = nrows
@@ -501,7 +536,8 @@ class FCNPlan:
         sp = self.specs[name]
         if sp["kind"] == "tconv":
             return self._tconv_desc(sp["wt"], sp["bt"], sp["src"], sp["dst"], cfg[2], cfg[3])[:2]
-        return self._conv_desc(sp["w"], sp["b"], sp["srcs"], sp["dst"], sp["act"], sp["f32_out"], tuple(cfg), sp.get("pool_dst"))
+        return self._conv_desc(sp["w"], sp["b"], sp["srcs"], sp["dst"], sp["act"], sp["f32_out"], tuple(cfg), sp.get("pool_dst"),
+                               sp.get("epi", AM_EPI_PLAIN))
 
     def _tconv(self, name, wt, bt, src, dst):
         """ConvTranspose2d(k=2,s=2) + BN + GELU as a 1x1 GEMM with N = (sy,sx,co); odd output sizes get the
@@ -585,10 +621,11 @@ class FCNPlan:
     def launches_per_run(self):
         return 1 + len(self.ops)
 
-    def run(self, stream, want_others=False, threshold=128, timing=None, frames=None):
+    def run(self, stream, want_others=False, threshold=128, timing=None, frames=None, want_logits=True):
         """frames (uint8 BGR [B][H][W][3] device tensor; default self.frames) -> self.logits / self.bits (and text_logit /
         rec when asked).  The plan is shared by every extractor of one (net, batch, size): callers that own their input
         buffers pass them here instead of rebinding self.frames.
+        want_logits=False (the fused pipelines): the fp32 logits never reach HBM, only the bit-packed mask does.
         timing: optional list; gets (op_index, start_event, end_event) per conv GEMM launch (CUDA events on the
         launching stream, which must be torch's current stream)."""
         lib, B, H, W = _lib.lib(), self.B, self.H, self.W
@@ -597,6 +634,16 @@ class FCNPlan:
         frames = self.frames if frames is None else frames
         assert frames.is_cuda and frames.dtype == torch.uint8 and tuple(frames.shape) == (B, H, W, 3) and frames.is_contiguous()
         chk(lib.am_fcn_prep_input(frames.data_ptr(), B, H, W, self.x0.ptr, self.x0.C, self.x0.pad, st), "am_fcn_prep_input")
+        # per-call pointers of the two fused epilogues (kernel arguments of the prepared launches)
+        vp = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+        hp = self._conv_plan(self.heads_op, self.ops[self.heads_op][1])
+        chk(lib.am_conv_plan_bind(hp, AM_BIND_FRAMES, vp(frames)), "am_conv_plan_bind")
+        chk(lib.am_conv_plan_bind(hp, AM_BIND_TEXT_OUT, vp(self.text_logit if want_others else None)), "am_conv_plan_bind")
+        chk(lib.am_conv_plan_bind(hp, AM_BIND_REC_OUT, vp(self.rec if want_others else None)), "am_conv_plan_bind")
+        if self.fused_threshold:
+            op = self._conv_plan(self.out_op, self.ops[self.out_op][1])
+            chk(lib.am_conv_plan_bind(op, AM_BIND_OUT, vp(self.logits if want_logits else None)), "am_conv_plan_bind")
+            chk(lib.am_conv_plan_bind(op, AM_BIND_THRESHOLD, ctypes.c_void_p(int(threshold))), "am_conv_plan_bind")
         for i, (kind, a) in enumerate(self.ops):
             if kind == "conv":
                 if timing is not None:
@@ -612,10 +659,6 @@ class FCNPlan:
             elif kind == "border":
                 dst, yf, xf, vals = a
                 chk(lib.am_fcn_fill_border(dst.ptr, B, dst.H, dst.W, dst.C, dst.pad, yf, xf, vals.data_ptr(), st), "am_fcn_fill_border")
-            elif kind == "heads_post":
-                chk(lib.am_fcn_heads_post(self.heads.data_ptr(), frames.data_ptr(), B, H, W, self.diff.ptr, self.diff.C, self.diff.pad,
-                                          self.text_logit.data_ptr() if want_others else None,
-                                          self.rec.data_ptr() if want_others else None, st), "am_fcn_heads_post")
             elif kind == "threshold":
                 chk(lib.am_fcn_threshold_pack(self.logits.data_ptr(), B, H, W, int(threshold), self.bits.data_ptr(), st), "am_fcn_threshold_pack")
 

@@ -38,7 +38,7 @@ class ContentExtractor:
         st = torch.cuda.current_stream().cuda_stream
         if self.large.active:
             self.large.downscale(self.plan.frames, st)
-        self.plan.run(st, False, 128, timing)
+        self.plan.run(st, False, 128, timing, want_logits=False)
         self.launches += self.plan.launches_per_run + self.large.launches_per_run
         return self.large.upscale_bits(self.plan.bits, st) if self.large.active else self.plan.bits
 
@@ -241,9 +241,9 @@ class StreamingExtractor:
             main.wait_event(self.ev_in_ready[kin])
         if self.large.active:                                            # FCN_lecturenet.py:434-437 on the device
             self.large.downscale(self.fcn_in, main.cuda_stream, src=src)
-            plan.run(main.cuda_stream, False, 128, timing, frames=self.fcn_in)
+            plan.run(main.cuda_stream, False, 128, timing, frames=self.fcn_in, want_logits=False)
         else:                                                            # the plan is shared (net.plan caches it): never rebind plan.frames
-            plan.run(main.cuda_stream, False, 128, timing, frames=src)
+            plan.run(main.cuda_stream, False, 128, timing, frames=src, want_logits=False)
         if self.ev_in_free[kin] is None:
             self.ev_in_free[kin] = torch.cuda.Event()
         self.ev_in_free[kin].record(main)

@@ -11,8 +11,9 @@ def _flat_of(plan):
     m = {}
     for b in [plan.x0, plan.mid, plan.diff, plan.px1, plan.px2] + plan.d + plan.p + plan.t + plan.u:
         m[b.ptr] = b.t
-    for t in plan.keep + [plan.heads, plan.logits]:
+    for t in plan.keep + [plan.logits, plan.text_logit, plan.rec, plan.frames]:
         m[t.data_ptr()] = t.view(-1)
+    m[plan.bits.data_ptr()] = plan.bits
     return m
 
 
@@ -55,8 +56,38 @@ def emulate_conv(d, mem):
                     a = torch.where(ok, flat[idx.reshape(-1)].view(idx.shape), torch.zeros(()))
                     acc += torch.einsum("byrk,nk->byrn", a, Wmat[chunk, dy])
                 chunk += 1
-    out = mem[d.out]
     x = acc + bias.view(1, 1, 1, -1)
+    if d.epi_mode:                                                         # fused epilogues: gather the fp32 planes the kernel keeps in registers
+        planes = torch.zeros((B, d.out_H, d.out_W, d.Cout), dtype=torch.float32)
+        for j in range(d.Ntot):
+            grp, co = j // d.Cout, j % d.Cout
+            sy, sx = grp // d.Sx, grp % d.Sx
+            oy, ox = d.Sy * torch.arange(Hin) + sy, d.Sx * torch.arange(nR) + sx
+            vy, vx = oy < d.out_H, ox < d.out_W
+            planes[:, oy[vy].view(-1, 1), ox[vx].view(1, -1), co] = x[:, vy][:, :, vx][..., j]
+        if d.epi_mode == 1:                                                # AM_EPI_HEADS
+            fr = mem[d.frames].view(B, d.out_H, d.out_W, 3)
+            rgb = _norm(fr.flip(-1))
+            text, rec = planes[..., 0], torch.tanh(planes[..., 1:4])
+            diff = ((rgb - rec) * torch.sigmoid(text).unsqueeze(-1)).to(torch.bfloat16)
+            dbuf = mem[d.diff_out][:B * d.out_H * (d.out_W + 2 * d.diff_pad) * d.diff_C].view(B, d.out_H, d.out_W + 2 * d.diff_pad, d.diff_C)
+            dbuf[:, :, d.diff_pad:d.diff_pad + d.out_W, :3] = diff
+            dbuf[:, :, d.diff_pad:d.diff_pad + d.out_W, 3:] = 0
+            if d.text_out:
+                mem[d.text_out].view(B, d.out_H, d.out_W)[:] = text
+            if d.rec_out:
+                mem[d.rec_out].view(B, d.out_H, d.out_W, 3)[:] = rec
+        else:                                                              # AM_EPI_THRESHOLD
+            assert d.Cout == 1 and d.Sx % 16 == 0 and d.out_W % 16 == 0
+            z = planes[..., 0]
+            ink = ((torch.sigmoid(z).numpy() * 255).astype("uint8") < d.threshold)
+            import numpy as np
+            packed = np.packbits(np.pad(ink, ((0, 0), (0, 0), (0, d.bits_wpr * 32 - d.out_W))), axis=-1, bitorder="little")
+            mem[d.bits_out][:] = torch.from_numpy(packed.view("<i4").reshape(B, d.out_H, d.bits_wpr))
+            if d.out:
+                mem[d.out].view(B, d.out_H, d.out_W)[:] = z
+        return
+    out = mem[d.out]
     if d.act == 1:
         x = 0.5 * x * (1.0 + torch.erf(x / math.sqrt(2.0)))
     n = torch.arange(d.Ntot)
@@ -91,8 +122,10 @@ def emulate_plan(plan, frames_bgr):
     fr = torch.as_tensor(frames_bgr)
     rgb = _norm(fr.flip(-1))
     plan.x0.view()[..., :3] = rgb.to(torch.bfloat16)
-    text = rec = None
+    plan.frames.copy_(fr)
     for kind, a in plan.ops:
+        if kind == "conv" and a.epi_mode == 1:                             # what FCNPlan.run binds per call
+            a.text_out, a.rec_out = plan.text_logit.data_ptr(), plan.rec.data_ptr()
         if kind == "conv":
             emulate_conv(a, mem)
         elif kind == "pool":
@@ -106,14 +139,9 @@ def emulate_plan(plan, frames_bgr):
             v = dst.view()
             v[:, yf:, :, :] = vals
             v[:, :, xf:, :] = vals
-        elif kind == "heads_post":
-            h = plan.heads
-            text = h[..., 0].clone()
-            rec = torch.tanh(h[..., 1:4])
-            diff = (rgb - rec) * torch.sigmoid(text).unsqueeze(-1)
-            plan.diff.view()[..., :3] = diff.to(torch.bfloat16)
         elif kind == "threshold":
             pass
+    text, rec = plan.text_logit.clone(), plan.rec.clone()
     logits = plan.logits.clone()
     u8 = (torch.sigmoid(logits).numpy() * 255).astype("uint8")
     ink = (u8 < 128)
