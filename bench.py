@@ -198,6 +198,63 @@ def gpu_reference(dev, net, frames_u8, flops_per_frame, iters=3):
     return out
 
 
+def dropin_e2e(dev, net, pool_np, n_frames, batch):
+    """The same metric through the REFERENCE'S OWN per-frame calls with host buffers, as its two stage scripts make them
+    (R/pre_ST3D_v3.0_01_binarize.py:31-55, R/pre_ST3D_v3.0_02_cc_analaysis.py:19-41):
+        worker.initialize; worker.handleFrame(frame, ...) per frame; worker.finalize()              -> compressed_frames (PNG per frame)
+        Helper.decompress_binary_images(compressed_frames); estimator.add_frame(mask, True) per frame; estimator.finish_processing()
+    `value` = frames / (stage 01 + stage 02 wall time), the two stages run one after the other like the reference's processes;
+    `fused` = handleFrame per frame with the estimator attached to the worker (masks stay on the device, PNGs still written).
+    Wall clock around device-synchronised phases: the host work (frame memcpy, PNG parse) is part of what is measured."""
+    import torch
+    from lecturemath_b200.cc_stability_estimator import CCStabilityEstimator
+    from lecturemath_b200.fcn_binarizer_worker import FCN_LectureNet_Binarizer
+    from lecturemath_b200.helper import Helper
+    frames = [pool_np[i % len(pool_np)] for i in range(n_frames)]
+
+    def stage01(worker):
+        worker.initialize(W, H)
+        for i, fr in enumerate(frames):
+            worker.handleFrame(fr, None, 0, 33.3 * i, 33.3 * i, i)
+        worker.finalize()
+        torch.cuda.synchronize(dev)
+
+    def stage02(est, masks):
+        for m in masks:
+            est.add_frame(m, True)
+        est.flush()
+        torch.cuda.synchronize(dev)
+
+    out = {}
+    for rep in range(2):                                  # first repetition = warm-up (plans, pinned buffers, PNG tables)
+        # objects are built outside the timed regions (a stage script builds them once per video, not per 80-frame sample)
+        worker = FCN_LectureNet_Binarizer(net, batch=batch)
+        est = CCStabilityEstimator(W, H, 0.85, 0.85, 85, max_batch=batch)
+        fused_est = CCStabilityEstimator(W, H, 0.85, 0.85, 85, max_batch=batch)
+        fused = FCN_LectureNet_Binarizer(net, batch=batch, estimator=fused_est)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        stage01(worker)
+        t1 = time.perf_counter()
+        masks = Helper.decompress_binary_images(worker.compressed_frames)
+        stage02(est, masks)
+        t2 = time.perf_counter()
+        t3 = time.perf_counter()
+        stage01(fused)
+        t4 = time.perf_counter()
+        out = {"value": n_frames / (t2 - t0), "unit": "frames/s", "frames": n_frames, "frames_per_gpu_step": batch,
+               "stage01_frames_per_s": n_frames / (t1 - t0), "stage02_frames_per_s": n_frames / (t2 - t1),
+               "fused": {"value": n_frames / (t4 - t3), "unit": "frames/s",
+                         "what": "handleFrame per frame, estimator attached to the worker (stage 01 + 02 in one pass)"},
+               "png_kb_per_frame": float(np.mean([len(f) for f in worker.compressed_frames])) / 1e3,
+               "h2d_bytes_per_frame": H * W * 3, "identical_state": bool(
+                   est.tempo_count == fused_est.tempo_count and est.get_raw_cc_count() == fused_est.get_raw_cc_count()),
+               "what": "FCN_LectureNet_Binarizer.handleFrame -> finalize -> Helper.decompress_binary_images -> CCStabilityEstimator.add_frame "
+                       "-> flush, one call per 1080p frame, host numpy frames in, PNG bytes + estimator state out"}
+        del worker, est, fused, fused_est, masks
+    return out
+
+
 def conv_traffic(args):
     """dram__bytes_read.sum + dram__bytes_write.sum of the conv launches of one step, from the committed ncu capture
     (profiles/conv_traffic.json, written by tools/summarize_profile.py); None when no capture of this build exists."""
@@ -452,6 +509,9 @@ def run_ours(args):
                 "frac_vs_burst": achieved / burst, "frac_vs_sustained": achieved / sustained,
                 "traffic": conv_traffic(args), "flop_per_step": flops_step, "conv_ms_per_step": conv_ms_step,
                 "conv_share_of_step": conv_ms_step / (ms_total / K)}
+        dropin = None
+        if world == 1 and not args.no_dropin:
+            dropin = dropin_e2e(dev, net, pool_h.numpy(), K * B, B)
         gref = None
         if world == 1 and not args.no_gpu_reference and (H, W) == (1080, 1920):
             gref = gpu_reference(dev, net, pool_h[:8], sx.plan.flops)
@@ -487,6 +547,8 @@ def run_ours(args):
                 "e2e": {"value": world * K * B / (e2e_ms / 1000.0), "unit": "frames/s", "h2d_bytes_per_step": B * H * W * 3,
                         "d2h_bytes_per_step": int(d2h / max(K, 1))},
                 "gpu_launches": launches}
+        if dropin is not None:
+            line["e2e_dropin"] = dropin
         if gref is not None:
             line["gpu_reference"] = gref
         if ring_parity is not None:
@@ -521,6 +583,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cc-stage", action="store_true", help="skip the secondary CC-stage roofline measurement")
+    ap.add_argument("--no-dropin", action="store_true", help="skip the measurement through the reference's per-frame calls")
     ap.add_argument("--no-gpu-reference", action="store_true", help="skip timing the reference's torch/cuDNN GPU arm")
     ap.add_argument("--no-ring-parity", action="store_true", help="N > 1: skip the 1-rank replay that checks the ring's results")
     ap.add_argument("--masks", default="fcn", choices=["fcn", "glyph"],

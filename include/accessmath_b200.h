@@ -294,6 +294,14 @@ int am_paint_frames(int n_items, const int* d_item_frame, const int* d_item_img,
 long long am_png1_size(int width, int height);          /* bytes per frame (fixed for a frame size); host-only helper */
 /* d_bits [batch][height][am_words_per_row(width)] -> d_out [batch][am_png1_size(width, height)] */
 int am_png1_encode(const uint32_t* d_bits, int batch, int height, int width, uint8_t* d_out, void* stream);
+/* the same file with a COMPRESSED zlib stream (RFC 1951 fixed Huffman codes + run-length matches, written in parallel: one deflate
+ * block per 8 KB of scanline bytes; whiteboard masks shrink ~20-60x against the stored form).  d_out [batch][am_png1_capacity()]
+ * (16-byte aligned), file sizes in d_sizes[batch]; frame f starts at d_out + f * capacity. */
+long long am_png1_capacity(int width, int height);      /* host-only helper */
+int am_png1_encode_deflate(const uint32_t* d_bits, int batch, int height, int width, uint8_t* d_out, long long* d_sizes, void* stream);
+/* decode half on the device: the scanline bytes a 1-bit filter-0 PNG inflates to (d_scan [batch][height][1 + ceil(width / 8)], what
+ * Helper.decompress_binary_images keeps of such a file, R/AccessMath/preprocessing/content/helper.py:27-34) -> mask words */
+int am_png1_scanlines_to_bits(const uint8_t* d_scan, int batch, int height, int width, uint32_t* d_bits, void* stream);
 
 #ifdef __cplusplus
 }

@@ -66,6 +66,9 @@ SIGNATURES = {
     "am_fcn_working_size": (c_int, [c_int, c_int, c_void_p, c_void_p]),
     "am_png1_size": (c_ll, [c_int, c_int]),
     "am_png1_encode": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "am_png1_capacity": (c_ll, [c_int, c_int]),
+    "am_png1_encode_deflate": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "am_png1_scanlines_to_bits": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "am_est_unique_view": (c_int, [c_void_p, c_void_p, c_void_p]),
     "am_group_overlaps": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_ll, c_void_p, c_void_p]),
     "am_group_images": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_double, c_void_p, c_void_p, c_void_p]),

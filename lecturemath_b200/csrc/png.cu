@@ -61,13 +61,21 @@ void crc_shift_matrix(long long nbytes, uint32_t* out) {
 void be32(uint8_t* p, uint32_t v) { p[0] = v >> 24; p[1] = v >> 16; p[2] = v >> 8; p[3] = v; }
 
 std::mutex g_mu;
-std::map<std::tuple<int, int, int>, PngPlan*> g_plans;
+std::map<std::tuple<int, int, int, int>, PngPlan*> g_plans;
 
-int png_plan(int width, int height, PngPlan** out) {
+constexpr int kLaneBytes = 256;                  // deflate writer: raw bytes one lane tokenises (a run never exceeds the 258-byte match)
+constexpr int kSegBytes = 32 * kLaneBytes;       // ... and one warp turns into one fixed-Huffman block
+long long deflate_capacity(long long raw) {      // zlib stream bytes in the worst case: every byte a 9-bit literal
+    const long long n_seg = (raw + kSegBytes - 1) / kSegBytes;
+    return 2 + (raw * 9 + 7) / 8 + 8 * n_seg + 4;
+}
+
+// deflate = 0: the stored-block container (fixed size); 1: the fixed-Huffman writer, zlen / total are then CAPACITIES
+int png_plan(int width, int height, int deflate, PngPlan** out) {
     int dev = 0;
     AM_CUDA(cudaGetDevice(&dev));
     std::lock_guard<std::mutex> lk(g_mu);
-    auto key = std::make_tuple(dev, width, height);
+    auto key = std::make_tuple(dev, width, height, deflate);
     auto it = g_plans.find(key);
     if (it == g_plans.end()) {
         PngPlan* p = new PngPlan();
@@ -75,8 +83,9 @@ int png_plan(int width, int height, PngPlan** out) {
         p->row_bytes = 1 + (width + 7) / 8;
         p->raw = (long long)height * p->row_bytes;
         p->n_blocks = (p->raw + 65534) / 65535;
-        p->zlen = 2 + p->raw + 5 * p->n_blocks + 4;
+        p->zlen = deflate ? deflate_capacity(p->raw) : 2 + p->raw + 5 * p->n_blocks + 4;
         p->total = 8 + 25 + 12 + p->zlen + 12;
+        if (deflate) p->total = (p->total + 15) & ~15LL;                // frames start on word boundaries (bit writer: 32-bit atomicOr)
         const long long crc_len = 4 + p->zlen;                       // "IDAT" + chunk data
         p->seg = (int)((crc_len + kThreads - 1) / kThreads);
         uint8_t* h = p->head;
@@ -164,18 +173,27 @@ k_png1_scanlines(const uint32_t* __restrict__ bits, const PngArgs a, uint8_t* __
 
 // Kernel B, one CTA per frame: Adler-32 from the partial sums, then CRC-32 of "IDAT" + data (thread e, counted from the END of
 // the region, owns bytes [end - (e+1) seg, end - e seg); partial CRCs merged by a tree of zero-shift matrices), then IEND.
+// d_zlen != NULL (deflate writer): the zlib stream of frame f is d_zlen[f] bytes long (<= a.zlen, which then is the CAPACITY the CRC
+// segment size was derived from); the IDAT length field is patched and the file size goes to d_sizes[f].
 __global__ void __launch_bounds__(kThreads)
-k_png1_checksums(const PngArgs a, const uint32_t* __restrict__ tables, const unsigned long long* __restrict__ partial, int n_slices,
-                 uint8_t* __restrict__ out) {
+k_png1_checksums(PngArgs a, const uint32_t* __restrict__ tables, const unsigned long long* __restrict__ partial, int n_slices,
+                 uint8_t* __restrict__ out, const long long* __restrict__ d_zlen, long long* __restrict__ d_sizes) {
     __shared__ uint32_t s_tab[256];
     __shared__ uint32_t s_mat[kLevels * 32];
     __shared__ uint32_t s_crc[kThreads];
     const int f = blockIdx.x, tid = threadIdx.x;
     uint8_t* o = out + (size_t)f * a.total;
     uint8_t* z = o + 41;
+    if (d_zlen) {
+        a.zlen = d_zlen[f];
+        if (tid == 0) {
+            o[33] = (uint8_t)(a.zlen >> 24); o[34] = (uint8_t)(a.zlen >> 16); o[35] = (uint8_t)(a.zlen >> 8); o[36] = (uint8_t)a.zlen;
+            d_sizes[f] = 41 + a.zlen + 16;
+        }
+    }
     if (tid < 256) s_tab[tid] = tables[tid];
     if (tid < kLevels * 32) s_mat[tid] = tables[256 + tid];
-    if (tid == 0) {
+    if (tid == 0 && !d_zlen) {                                        // (the deflate writer has placed its Adler-32 itself)
         unsigned long long A = 1, B = (unsigned long long)(a.raw % 65521);
         for (int w = 0; w < n_slices; ++w) { A += partial[2 * ((size_t)f * n_slices + w)]; B = (B + partial[2 * ((size_t)f * n_slices + w) + 1] % 65521) % 65521; }
         const uint32_t adler = (uint32_t)((B % 65521) << 16) | (uint32_t)(A % 65521);
@@ -229,7 +247,227 @@ k_png1_checksums(const PngArgs a, const uint32_t* __restrict__ tables, const uns
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------------------
+// Deflate writer: the same 1-bit PNG with a COMPRESSED zlib stream (RFC 1951 fixed Huffman codes, run-length matches of distance 1).
+// Whiteboard / chalkboard masks are > 95 % zero bytes: a run of n equal bytes becomes one literal + one (length n - 1, distance 1)
+// match, 26 bits per 256 empty bytes.  No serial pass over the stream:
+//   * warp-segment s = raw bytes [s * 8192, (s + 1) * 8192) is ONE deflate block; lane l tokenises bytes [256 l, 256 l + 256) of it
+//     on its own (runs are cut at lane boundaries), pass 1 counts bits, a warp scan + a CTA scan over the segments place every lane;
+//   * blocks end on a byte boundary -- a fixed block is followed by an EMPTY stored block (3 header bits, pad, 00 00 FF FF), the
+//     classic sync-flush marker -- so segment offsets are byte counts and the stream stays one valid deflate stream;
+//   * the emit pass re-tokenises and ORs the codes into the zero-initialised output with 32-bit atomics (neighbouring lanes share words).
+// Adler-32 over the raw bytes falls out of the counting pass; k_png1_checksums (above) adds the CRC-32 over the variable-length chunk.
+struct BitWriter {
+    uint32_t* words; unsigned long long w; uint64_t acc; int fill;
+    __device__ void init(uint32_t* base, unsigned long long bitpos) { words = base; w = bitpos >> 5; fill = (int)(bitpos & 31); acc = 0; }
+    __device__ void put(uint32_t code, int n) {                     // n <= 32 bits, LSB first
+        acc |= (uint64_t)code << fill;
+        fill += n;
+        if (fill >= 32) { atomicOr(&words[w], (uint32_t)acc); ++w; acc >>= 32; fill -= 32; }
+    }
+    __device__ void flush() { if (fill > 0) atomicOr(&words[w], (uint32_t)acc); fill = 0; acc = 0; }
+    __device__ unsigned long long bitpos() const { return (w << 5) + (unsigned)fill; }
+};
+// literal / length symbol -> (code bits reversed for the LSB-first stream, length); RFC 1951 3.2.6
+__device__ __forceinline__ uint32_t fixed_code(uint32_t sym, int& n) {
+    uint32_t code;
+    if (sym < 144) { code = 0x30 + sym; n = 8; }
+    else if (sym < 256) { code = 0x190 + (sym - 144); n = 9; }
+    else if (sym < 280) { code = sym - 256; n = 7; }
+    else { code = 0xC0 + (sym - 280); n = 8; }
+    return __brev(code) >> (32 - n);
+}
+// match length 3 .. 258 -> (symbol, extra-bit count, extra value); RFC 1951 3.2.5
+__device__ __forceinline__ void length_symbol(int len, uint32_t& sym, int& eb, uint32_t& ev) {
+    if (len == 258) { sym = 285; eb = 0; ev = 0; return; }
+    const int l = len - 3;
+    if (l < 8) { sym = 257 + l; eb = 0; ev = 0; return; }
+    eb = (31 - __clz(l)) - 2;
+    sym = 265 + 4 * (eb - 1) + ((l >> eb) - 4);
+    ev = (uint32_t)l & ((1u << eb) - 1u);
+}
+// A warp's segment of the raw stream, staged in shared memory: byte i of the segment at sm[(i / 256) * 260 + i % 256] (every lane's
+// 256 bytes start 65 words apart: conflict-free when all lanes walk their ranges in step).  Raw stream byte r of a frame = the filter
+// byte (0) in front of every scanline, else 8 pixels with the leftmost in the MSB.  Coalesced, independent loads: a lane that fetched
+// its bytes one by one from global memory was latency bound at ~1 us per byte (240 us per pass and batch, profile r02_h).
+constexpr int kLanePitch = kLaneBytes + 4;
+__device__ __forceinline__ void stage_segment(const uint32_t* __restrict__ fb, const PngArgs& a, unsigned seg_r0, uint8_t* sm, int lane) {
+    const unsigned raw = (unsigned)a.raw, rb = (unsigned)a.row_bytes, last_bits = (unsigned)a.W & 7u;
+#pragma unroll 4
+    for (unsigned i = lane; i < (unsigned)kSegBytes; i += 32) {
+        const unsigned r = seg_r0 + i;
+        uint32_t d = 0;
+        if (r < raw) {
+            const unsigned y = r / rb, c = r - y * rb;
+            if (c > 0) {
+                const unsigned k = c - 1;
+                d = (fb[(size_t)y * a.WPR + (k >> 2)] >> (8 * (k & 3))) & 0xFFu;
+                if (last_bits && k == rb - 2) d &= (1u << last_bits) - 1u;
+                d = __brev(d) >> 24;
+            }
+        }
+        sm[(i >> 8) * kLanePitch + (i & 255u)] = (uint8_t)d;
+    }
+    __syncwarp();
+}
+// tokens of the n raw bytes b[0 .. n) (stream position r0): bit count (kEmit = false) or emission; also the lane's Adler partial sums
+// in the counting pass
+template <bool kEmit>
+__device__ __forceinline__ unsigned tokenize(const uint8_t* b, unsigned n, unsigned r0, unsigned raw, BitWriter* bw,
+                                             unsigned long long* sa, unsigned long long* sb) {
+    unsigned nbits = 0, i = 0;
+    while (i < n) {
+        const uint32_t cur = b[i];
+        unsigned run = 1;
+        while (i + run < n && b[i + run] == cur) ++run;
+        if (!kEmit) {
+            const unsigned r = r0 + i;
+            *sa += (unsigned long long)cur * run;
+            *sb += (unsigned long long)cur * ((unsigned long long)run * (raw - r) - (unsigned long long)run * (run - 1) / 2);
+        }
+        int ln; const uint32_t lc = fixed_code(cur, ln);
+        if (run >= 4) {                                             // literal + (length run - 1, distance 1)
+            uint32_t sym, ev; int eb, sn;
+            length_symbol((int)run - 1, sym, eb, ev);
+            const uint32_t sc = fixed_code(sym, sn);
+            if (kEmit) { bw->put(lc, ln); bw->put(sc | (ev << sn), sn + eb); bw->put(0, 5); }
+            nbits += ln + sn + eb + 5;
+        } else {
+            if (kEmit) for (unsigned k = 0; k < run; ++k) bw->put(lc, ln);
+            nbits += ln * run;
+        }
+        i += run;
+    }
+    return nbits;
+}
+
+// Three launches per batch, a warp per segment (the only dependency between segments is the scan of their byte sizes):
+constexpr int kDefWarps = 4;                     // warps (= segments) per CTA of the count / emit kernels
+
+// pass 1, grid (ceil(n_seg / kDefWarps), frames): bits per lane -> lane_off[frame][seg][lane]; bytes per segment; Adler partial sums
+__global__ void __launch_bounds__(kDefWarps * 32)
+k_png1_deflate_count(const uint32_t* __restrict__ bits, const PngArgs a, int n_seg, unsigned* __restrict__ lane_off,
+                     unsigned* __restrict__ seg_bytes, unsigned long long* __restrict__ seg_adler) {
+    const int f = blockIdx.y, lane = threadIdx.x & 31, s = blockIdx.x * kDefWarps + (threadIdx.x >> 5);
+    if (s >= n_seg) return;
+    __shared__ __align__(16) uint8_t s_seg[kDefWarps][32 * kLanePitch];
+    const uint32_t* fb = bits + (size_t)f * a.H * a.WPR;
+    const unsigned raw = (unsigned)a.raw;
+    const unsigned r0 = min(raw, (unsigned)s * kSegBytes + (unsigned)lane * kLaneBytes), r1 = min(raw, r0 + kLaneBytes);
+    uint8_t* sm = s_seg[threadIdx.x >> 5];
+    stage_segment(fb, a, (unsigned)s * kSegBytes, sm, lane);
+    unsigned long long sa = 0, sb = 0;
+    const unsigned nb = tokenize<false>(sm + lane * kLanePitch, r1 - r0, r0, raw, nullptr, &sa, &sb);
+    unsigned incl = nb;
+    for (int d = 1; d < 32; d <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+    lane_off[((size_t)f * n_seg + s) * 32 + lane] = 3 + incl - nb;   // behind the 3-bit block header
+    for (int off = 16; off; off >>= 1) { sa += __shfl_down_sync(0xffffffffu, sa, off); sb += __shfl_down_sync(0xffffffffu, sb, off); }
+    if (lane == 31) {
+        const unsigned body = 3 + incl + 7;                          // header, tokens, end-of-block
+        seg_bytes[(size_t)f * n_seg + s] = (s == n_seg - 1) ? (body + 7) / 8 : (body + 3 + 7) / 8 + 4;   // (the last block is followed by Adler-32)
+    }
+    if (lane == 0) { seg_adler[2 * ((size_t)f * n_seg + s)] = sa; seg_adler[2 * ((size_t)f * n_seg + s) + 1] = sb; }
+}
+
+// pass 2, one warp per frame: exclusive scan of the segment sizes (in place), Adler-32, stream length; file header
+__global__ void k_png1_deflate_scan(const PngArgs a, int n_seg, unsigned* __restrict__ seg_bytes, const unsigned long long* __restrict__ seg_adler,
+                                    uint32_t* __restrict__ adler_out, long long* __restrict__ d_zlen, uint8_t* __restrict__ out) {
+    const int f = blockIdx.x, lane = threadIdx.x;
+    uint8_t* o = out + (size_t)f * a.total;
+    for (int i = lane; i < 41; i += 32) o[i] = a.head[i];             // (IDAT length is patched by k_png1_checksums)
+    if (lane == 0) { o[41] = 0x78; o[42] = 0x01; }
+    unsigned* sz = seg_bytes + (size_t)f * n_seg;
+    unsigned carry = 0;
+    unsigned long long A = 0, B = 0;
+    for (int base = 0; base < n_seg; base += 32) {
+        const bool ok = base + lane < n_seg;
+        const unsigned v = ok ? sz[base + lane] : 0;
+        unsigned incl = v;
+        for (int d = 1; d < 32; d <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+        if (ok) {
+            sz[base + lane] = carry + incl - v;
+            A += seg_adler[2 * ((size_t)f * n_seg + base + lane)];
+            B = (B + seg_adler[2 * ((size_t)f * n_seg + base + lane) + 1] % 65521) % 65521;
+        }
+        carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    for (int off = 16; off; off >>= 1) { A += __shfl_down_sync(0xffffffffu, A, off); B += __shfl_down_sync(0xffffffffu, B, off); }
+    if (lane == 0) {
+        A += 1; B += (unsigned long long)(a.raw % 65521);
+        adler_out[f] = (uint32_t)((B % 65521) << 16) | (uint32_t)(A % 65521);
+        d_zlen[f] = 2 + (long long)carry + 4;                        // zlib header + blocks + Adler-32
+    }
+}
+
+// pass 3, same grid as pass 1: emit
+__global__ void __launch_bounds__(kDefWarps * 32)
+k_png1_deflate_emit(const uint32_t* __restrict__ bits, const PngArgs a, int n_seg, const unsigned* __restrict__ lane_off,
+                    const unsigned* __restrict__ seg_off, const uint32_t* __restrict__ adler, uint8_t* __restrict__ out) {
+    const int f = blockIdx.y, lane = threadIdx.x & 31, s = blockIdx.x * kDefWarps + (threadIdx.x >> 5);
+    if (s >= n_seg) return;
+    __shared__ __align__(16) uint8_t s_seg[kDefWarps][32 * kLanePitch];
+    const uint32_t* fb = bits + (size_t)f * a.H * a.WPR;
+    uint32_t* words = (uint32_t*)(out + (size_t)f * a.total);         // frame buffers start on 16-byte boundaries
+    const unsigned raw = (unsigned)a.raw;
+    const unsigned r0 = min(raw, (unsigned)s * kSegBytes + (unsigned)lane * kLaneBytes), r1 = min(raw, r0 + kLaneBytes);
+    uint8_t* sm = s_seg[threadIdx.x >> 5];
+    stage_segment(fb, a, (unsigned)s * kSegBytes, sm, lane);
+    const unsigned long long seg_bit = 8ull * (43 + seg_off[(size_t)f * n_seg + s]);
+    const bool last = s == n_seg - 1;
+    BitWriter bw;
+    if (lane == 0) { bw.init(words, seg_bit); bw.put(last ? 3u : 2u, 3); }               // BFINAL, BTYPE = 01 (fixed Huffman), LSB first
+    else bw.init(words, seg_bit + lane_off[((size_t)f * n_seg + s) * 32 + lane]);
+    tokenize<true>(sm + lane * kLanePitch, r1 - r0, r0, raw, &bw, nullptr, nullptr);
+    if (lane == 31) {
+        bw.put(0, 7);                                                // end of block (symbol 256)
+        if (!last) bw.put(0, 3);                                     // empty stored block: BFINAL = 0, BTYPE = 00 ...
+        const int pad = (int)((8 - (bw.bitpos() & 7)) & 7);
+        if (pad) bw.put(0, pad);                                     // ... pad to the byte boundary ...
+        if (!last) { bw.put(0x0000u, 16); bw.put(0xFFFFu, 16); }     // ... LEN = 0, NLEN = 0xFFFF
+        else bw.put(__byte_perm(adler[f], 0, 0x0123), 32);           // Adler-32, big endian
+    }
+    bw.flush();
+}
+
+// PNG scanlines (what zlib.decompress returns for a 1-bit, filter-0 PNG: per row one filter byte + ceil(W / 8) bytes, leftmost pixel in
+// the MSB) -> device-layout mask words; one thread per word.  The decode half of the wire format that has to run on the device.
+__global__ void k_png1_scan_to_bits(const uint8_t* __restrict__ scan, int H, int W, int WPR, int rb, uint32_t* __restrict__ bits) {
+    const int f = blockIdx.z, y = blockIdx.y, w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= WPR) return;
+    const uint8_t* row = scan + ((size_t)f * H + y) * (size_t)(1 + rb) + 1;
+    uint32_t v = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int b = 4 * w + k;
+        uint32_t d = b < rb ? row[b] : 0u;
+        d = __brev(d) >> 24;
+        if (b == rb - 1 && (W & 7)) d &= (1u << (W & 7)) - 1u;
+        v |= d << (8 * k);
+    }
+    bits[((size_t)f * H + y) * WPR + w] = v;
+}
+
 }  // namespace
+
+// scratch for the Adler partial sums (kSliceBlocks x 2 per frame; the deflate writer keeps its per-frame stream length in the same
+// block): cached per device, grown on demand (stream-ordered use only)
+static int png_scratch(int batch, unsigned long long** out) {
+    static std::mutex mu;
+    static std::map<int, std::pair<unsigned long long*, int>> scratch;
+    int dev = 0;
+    AM_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(mu);
+    auto& sc = scratch[dev];
+    if (sc.second < batch) {
+        if (sc.first) cudaFree(sc.first);
+        sc.first = nullptr; sc.second = 0;
+        AM_CUDA(cudaMalloc(&sc.first, (size_t)batch * (kSliceBlocks * 2 + 2) * sizeof(unsigned long long)));
+        sc.second = batch;
+    }
+    *out = sc.first;
+    return AM_OK;
+}
 
 extern "C" long long am_png1_size(int width, int height) {
     if (width <= 0 || height <= 0) return 0;
@@ -240,32 +478,81 @@ extern "C" long long am_png1_size(int width, int height) {
 extern "C" int am_png1_encode(const uint32_t* d_bits, int batch, int height, int width, uint8_t* d_out, void* stream) {
     if (!d_bits || !d_out || batch <= 0 || width <= 0 || height <= 0) return AM_ERR_ARG;
     PngPlan* p = nullptr;
-    int rc = png_plan(width, height, &p);
+    int rc = png_plan(width, height, 0, &p);
     if (rc) return rc;
     if (p->zlen > 0x7FFFFFFFLL) return AM_ERR_ARG;                    // chunk length field; also keeps raw < 2^31
     PngArgs a;
     a.W = p->W; a.H = p->H; a.WPR = p->WPR; a.row_bytes = p->row_bytes; a.seg = p->seg;
     a.raw = p->raw; a.n_blocks = p->n_blocks; a.zlen = p->zlen; a.total = p->total;
     memcpy(a.head, p->head, 41);
-    // scratch for the Adler partial sums: cached per device, grown on demand (stream-ordered use only)
-    static std::mutex mu;
-    static std::map<int, std::pair<unsigned long long*, int>> scratch;
     unsigned long long* d_partial = nullptr;
+    rc = png_scratch(batch, &d_partial);
+    if (rc) return rc;
+    k_png1_scanlines<<<dim3(kSliceBlocks, batch), kThreads, 0, (cudaStream_t)stream>>>(d_bits, a, d_out, d_partial);
+    k_png1_checksums<<<batch, kThreads, 0, (cudaStream_t)stream>>>(a, p->d_tables, d_partial, kSliceBlocks, d_out, nullptr, nullptr);
+    AM_CUDA(cudaGetLastError());
+    return AM_OK;
+}
+
+// ---- compressed variant ---------------------------------------------------------------------------------------------------------
+extern "C" long long am_png1_capacity(int width, int height) {
+    if (width <= 0 || height <= 0) return 0;
+    const long long raw = (long long)height * (1 + (width + 7) / 8);
+    return ((8 + 25 + 12 + deflate_capacity(raw) + 12) + 15) & ~15LL;
+}
+
+extern "C" int am_png1_encode_deflate(const uint32_t* d_bits, int batch, int height, int width, uint8_t* d_out, long long* d_sizes,
+                                      void* stream) {
+    if (!d_bits || !d_out || !d_sizes || batch <= 0 || width <= 0 || height <= 0) return AM_ERR_ARG;
+    if (((uintptr_t)d_out & 15) != 0) return AM_ERR_ARG;
+    PngPlan* p = nullptr;
+    int rc = png_plan(width, height, 1, &p);
+    if (rc) return rc;
+    const long long n_seg = (p->raw + kSegBytes - 1) / kSegBytes;
+    if (p->zlen > 0x7FFFFFFFLL) return AM_ERR_ARG;
+    PngArgs a;
+    a.W = p->W; a.H = p->H; a.WPR = p->WPR; a.row_bytes = p->row_bytes; a.seg = p->seg;
+    a.raw = p->raw; a.n_blocks = p->n_blocks; a.zlen = p->zlen; a.total = p->total;
+    memcpy(a.head, p->head, 41);
+    cudaStream_t st = (cudaStream_t)stream;
+    // scratch: per frame n_seg x (32 lane offsets + segment bytes) unsigned, n_seg x 2 Adler sums, stream length, Adler-32
+    static std::mutex mu;
+    static std::map<int, std::pair<char*, size_t>> scratch;
+    const size_t per_frame = (size_t)n_seg * (33 * sizeof(unsigned) + 2 * sizeof(unsigned long long)) + 16;
+    const size_t need = (size_t)batch * per_frame + 64;
+    char* base = nullptr;
     {
         int dev = 0;
         AM_CUDA(cudaGetDevice(&dev));
         std::lock_guard<std::mutex> lk(mu);
         auto& sc = scratch[dev];
-        if (sc.second < batch) {
+        if (sc.second < need) {
             if (sc.first) cudaFree(sc.first);
             sc.first = nullptr; sc.second = 0;
-            AM_CUDA(cudaMalloc(&sc.first, (size_t)batch * kSliceBlocks * 2 * sizeof(unsigned long long)));
-            sc.second = batch;
+            AM_CUDA(cudaMalloc(&sc.first, need));
+            sc.second = need;
         }
-        d_partial = sc.first;
+        base = sc.first;
     }
-    k_png1_scanlines<<<dim3(kSliceBlocks, batch), kThreads, 0, (cudaStream_t)stream>>>(d_bits, a, d_out, d_partial);
-    k_png1_checksums<<<batch, kThreads, 0, (cudaStream_t)stream>>>(a, p->d_tables, d_partial, kSliceBlocks, d_out);
+    unsigned long long* seg_adler = (unsigned long long*)base;
+    long long* d_zlen = (long long*)(seg_adler + (size_t)batch * n_seg * 2);
+    unsigned* lane_off = (unsigned*)(d_zlen + batch);
+    unsigned* seg_bytes = lane_off + (size_t)batch * n_seg * 32;
+    uint32_t* adler = seg_bytes + (size_t)batch * n_seg;
+    AM_CUDA(cudaMemsetAsync(d_out, 0, (size_t)batch * p->total, st));       // the bit writer ORs into zeroed words
+    const dim3 grid((unsigned)((n_seg + kDefWarps - 1) / kDefWarps), (unsigned)batch);
+    k_png1_deflate_count<<<grid, kDefWarps * 32, 0, st>>>(d_bits, a, (int)n_seg, lane_off, seg_bytes, seg_adler);
+    k_png1_deflate_scan<<<batch, 32, 0, st>>>(a, (int)n_seg, seg_bytes, seg_adler, adler, d_zlen, d_out);
+    k_png1_deflate_emit<<<grid, kDefWarps * 32, 0, st>>>(d_bits, a, (int)n_seg, lane_off, seg_bytes, adler, d_out);
+    k_png1_checksums<<<batch, kThreads, 0, st>>>(a, p->d_tables, nullptr, 0, d_out, d_zlen, d_sizes);
+    AM_CUDA(cudaGetLastError());
+    return AM_OK;
+}
+
+extern "C" int am_png1_scanlines_to_bits(const uint8_t* d_scan, int batch, int height, int width, uint32_t* d_bits, void* stream) {
+    if (!d_scan || !d_bits || batch <= 0 || width <= 0 || height <= 0) return AM_ERR_ARG;
+    const int WPR = am_words_per_row_impl(width), rb = (width + 7) / 8;
+    k_png1_scan_to_bits<<<dim3(am_div_up(WPR, 64), height, batch), 64, 0, (cudaStream_t)stream>>>(d_scan, height, width, WPR, rb, d_bits);
     AM_CUDA(cudaGetLastError());
     return AM_OK;
 }
