@@ -348,8 +348,10 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # rank 0 prints ONE JSON line on stdout: NCCL's version banner (printed at the VERSION and WARN levels) and warnings go to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"             # keeps NCCL's version banner off stdout (rank 0 prints ONE JSON line)
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     B, K, Wm = args.batch, args.steps, max(args.warmup, 3)
     net = make_net()

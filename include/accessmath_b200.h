@@ -68,6 +68,8 @@ int am_words_per_row(int width);           /* uint32 words per bit-packed mask r
  * stage 01 and 02 (R/AccessMath/preprocessing/video_worker/FCN_lecturenet_binarizer.py:54-64,
  * R/AccessMath/preprocessing/content/helper.py:27-34). */
 int am_pack_mask_u8(const uint8_t* d_mask, int width, int height, int batch, uint32_t* d_bits, void* stream);
+/* am_pack_mask_u8, and d_flags[f] = 1 when frame f holds a value other than 0 / 255 (no exact 1-bit form) */
+int am_pack_mask_u8_exact(const uint8_t* d_mask, int width, int height, int batch, uint32_t* d_bits, int* d_flags, void* stream);
 int am_unpack_mask_u8(const uint32_t* d_bits, int width, int height, int batch, uint8_t* d_mask, void* stream);
 
 /* ===== 4. CC labeling + statistics + crops ==================================================
@@ -250,6 +252,11 @@ int am_fcn_working_size(int width, int height, int* out_width, int* out_height);
  * to Pillow's fixed-point two-pass resampler (FCN_lecturenet.py:436; algorithm: Pillow libImaging/Resample.c) */
 int am_lanczos_resize_u8(const uint8_t* d_in, int batch, int in_h, int in_w, int channels, int out_h, int out_w,
                          uint8_t* d_out, void* stream);
+/* cv2.resize(frame, (out_w, out_h)) -- INTER_LINEAR, VideoProcessor's forced-resolution resize
+ * (R/AccessMath/preprocessing/video_processor/video_processor.py:164-165) -- on uint8 interleaved frames [B][H][W][channels]
+ * (channels 1 or 3): OpenCV's 8-bit fixed-point algorithm (11-bit coefficients, int32 rows), bit-identical to its generic code path */
+int am_resize_linear_u8(const uint8_t* d_in, int batch, int in_h, int in_w, int channels, int out_h, int out_w,
+                        uint8_t* d_out, void* stream);
 /* cv2.resize(mask, (out_w, out_h), interpolation=cv2.INTER_NEAREST) on bit-packed masks (FCN_lecturenet.py:481-486; the ink
  * inversion `255 - binary` commutes with it) */
 int am_bits_resize_nearest(const uint32_t* d_bits, int batch, int in_h, int in_w, int out_h, int out_w,
@@ -287,6 +294,13 @@ int am_paint_frames(int n_items, const int* d_item_frame, const int* d_item_img,
                     const unsigned long long* d_img_off, const uint32_t* d_imgs, int frame0, int n_frames, int height, int width,
                     uint8_t* d_out, void* stream);
 
+/* ===== 7b. Small downstream reducer: VideoSegmenter.compute_binary_sums ========================
+ * R/AccessMath/preprocessing/content/video_segmenter.py:21-28 (`binary.sum() / 255` per frame; caller
+ * R/pre_ST3D_v3.0_04_vid_segmentation.py:39).  d_sums[f] = exact integer sum of the pixel VALUES of frame f: 255 * popcount for
+ * bit-packed frames [batch][height][am_words_per_row(width)], the byte sum for uint8 frames [batch][bytes_per_frame]. */
+int am_frame_sums_bits(const uint32_t* d_bits, int batch, int height, int width, unsigned long long* d_sums, void* stream);
+int am_frame_sums_u8(const uint8_t* d_frames, int batch, long long bytes_per_frame, unsigned long long* d_sums, void* stream);
+
 /* ===== 8. Wire format 01 -> 02 written on the device ========================================
  * Replaces cv2.imencode(".png", binary) (R/AccessMath/preprocessing/video_worker/FCN_lecturenet_binarizer.py:56); the reader stays
  * cv2.imdecode(raw, IMREAD_GRAYSCALE) (R/AccessMath/preprocessing/content/helper.py:31).  The file is a 1-bit grayscale PNG
@@ -299,6 +313,10 @@ int am_png1_encode(const uint32_t* d_bits, int batch, int height, int width, uin
  * (16-byte aligned), file sizes in d_sizes[batch]; frame f starts at d_out + f * capacity. */
 long long am_png1_capacity(int width, int height);      /* host-only helper */
 int am_png1_encode_deflate(const uint32_t* d_bits, int batch, int height, int width, uint8_t* d_out, long long* d_sizes, void* stream);
+/* the same writer for 8-bit grayscale frames d_frames [batch][height][width] (the 03 -> 04 clean frames of
+ * R/AccessMath/preprocessing/content/cc_stability_estimator.py:677-678 when overlapping groups wrapped a pixel to 254) */
+long long am_png8_capacity(int width, int height);
+int am_png8_encode_deflate(const uint8_t* d_frames, int batch, int height, int width, uint8_t* d_out, long long* d_sizes, void* stream);
 /* decode half on the device: the scanline bytes a 1-bit filter-0 PNG inflates to (d_scan [batch][height][1 + ceil(width / 8)], what
  * Helper.decompress_binary_images keeps of such a file, R/AccessMath/preprocessing/content/helper.py:27-34) -> mask words */
 int am_png1_scanlines_to_bits(const uint8_t* d_scan, int batch, int height, int width, uint32_t* d_bits, void* stream);

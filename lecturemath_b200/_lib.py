@@ -25,6 +25,7 @@ SIGNATURES = {
     "am_device_count": (c_int, []),
     "am_words_per_row": (c_int, [c_int]),
     "am_pack_mask_u8": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "am_pack_mask_u8_exact": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "am_unpack_mask_u8": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "am_cc_create": (c_void_p, [c_int] * 8),
     "am_cc_destroy": (None, [c_void_p]),
@@ -64,16 +65,21 @@ SIGNATURES = {
     "am_fcn_heads_post": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "am_fcn_threshold_pack": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "am_fcn_working_size": (c_int, [c_int, c_int, c_void_p, c_void_p]),
+    "am_frame_sums_bits": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "am_frame_sums_u8": (c_int, [c_void_p, c_int, c_ll, c_void_p, c_void_p]),
     "am_png1_size": (c_ll, [c_int, c_int]),
     "am_png1_encode": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "am_png1_capacity": (c_ll, [c_int, c_int]),
     "am_png1_encode_deflate": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "am_png8_capacity": (c_ll, [c_int, c_int]),
+    "am_png8_encode_deflate": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "am_png1_scanlines_to_bits": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "am_est_unique_view": (c_int, [c_void_p, c_void_p, c_void_p]),
     "am_group_overlaps": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_ll, c_void_p, c_void_p]),
     "am_group_images": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_double, c_void_p, c_void_p, c_void_p]),
     "am_paint_frames": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "am_lanczos_resize_u8": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "am_resize_linear_u8": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "am_bits_resize_nearest": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
 }
 

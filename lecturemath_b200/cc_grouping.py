@@ -96,16 +96,17 @@ class GroupingMixin:
         out = []
         tables = getattr(self, "_frame_tables", None)
         fast = tables is not None and len(tables) == len(self.cc_idx_per_frame)
-        for f0 in range(0, len(self.cc_idx_per_frame), chunk):
-            rows = self.cc_idx_per_frame[f0:f0 + chunk]
+        n_frames = len(self.cc_idx_per_frame)
+        for f0 in range(0, n_frames, chunk):
             if fast:                                                  # the per-frame tables exactly as stage 02 read them back
                 tb = tables[f0:f0 + chunk]
                 base = np.concatenate([[0], np.cumsum([len(t[2]) for t in tb])])
-                out.extend(self._paint_arrays(len(rows), np.repeat(np.arange(len(tb)), [len(t[0]) for t in tb]),
+                out.extend(self._paint_arrays(len(tb), np.repeat(np.arange(len(tb)), [len(t[0]) for t in tb]),
                                               np.concatenate([t[0] for t in tb]).reshape(-1, 4),
                                               np.concatenate([t[1] + np.uint64(b) for t, b in zip(tb, base[:-1])]),
                                               np.concatenate([t[2] for t in tb])))
             else:
+                rows = self.cc_idx_per_frame[f0:f0 + chunk]
                 ccs = [(t, cc) for t, row in enumerate(rows) for _, cc in row]
                 out.extend(self._paint(len(rows), [t for t, _ in ccs], [c for _, c in ccs]))
         return out
@@ -141,19 +142,22 @@ class GroupingMixin:
     # ---- :181-228 (list bookkeeping; no arithmetic) ----------------------------------------------------------------
     def split_stable_cc_by_gaps(self, max_gap, stable_min_frames):
         split = 0
-        for u in range(len(self.unique_cc_objects)):
-            frames = self.unique_cc_frames[u]
+        objects, uframes, per_frame = self.unique_cc_objects, self.unique_cc_frames, self.cc_idx_per_frame
+        for u in range(len(objects)):
+            frames = uframes[u]
+            if len(frames) < stable_min_frames or frames[-1][0] - frames[0][0] <= max_gap:
+                continue                                                  # too short to matter / too compact to hold a gap > max_gap
             cuts = [i for i in range(1, len(frames)) if frames[i][0] - frames[i - 1][0] > max_gap]
-            if not cuts or len(frames) < stable_min_frames:
+            if not cuts:
                 continue
             edges = [0] + cuts + [len(frames)]
-            self.unique_cc_frames[u] = frames[:cuts[0]]
+            uframes[u] = frames[:cuts[0]]
             for a, b in zip(edges[1:-1], edges[2:]):
-                new_u = len(self.unique_cc_objects)
-                self.unique_cc_objects.append(self.unique_cc_objects[u])
-                self.unique_cc_frames.append(frames[a:b])
+                new_u = len(objects)
+                objects.append(objects[u])
+                uframes.append(frames[a:b])
                 for t, _ in frames[a:b]:
-                    row = self.cc_idx_per_frame[t]
+                    row = per_frame[t]
                     k = next((i for i, (uk, _) in enumerate(row) if uk == u), None)      # the FIRST instance with the old index
                     if k is not None:
                         row[k] = (new_u, row[k][1])
@@ -164,7 +168,10 @@ class GroupingMixin:
         return [u for u, f in enumerate(self.unique_cc_frames) if len(f) >= min_stable_frames]
 
     def get_temporal_index(self):                                            # :238-243
-        return [[u for u, _ in row] for row in self.cc_idx_per_frame]
+        pf = self.cc_idx_per_frame
+        if hasattr(pf, "unique_indices"):                                        # live estimator: straight from the result rows
+            return [pf.unique_indices(t) for t in range(len(pf))]
+        return [[u for u, _ in row] for row in pf]
 
     # ---- :245-306 ---------------------------------------------------------------------------------------------
     def stable_overlaps_device(self, stable_idxs):
@@ -255,25 +262,47 @@ class GroupingMixin:
 
     # ---- :446-500 ---------------------------------------------------------------------------------------------
     def compute_conflicting_groups(self, stable_idxs, all_overlapping_cc, n_groups, group_idx_per_cc):
+        """Same dictionary as the reference's loop (:446-500); the per-pair arithmetic (box areas, intersection, unmatched pixels) runs
+        on arrays, only the dictionary is filled pair by pair, in the reference's order."""
         conflicts = {g: {} for g in range(n_groups)}
-        for u1 in stable_idxs:
-            cc1 = self.unique_cc_objects[u1]
-            for u2, matched, size2, size1 in all_overlapping_cc[u1]:
-                if u1 >= u2 or group_idx_per_cc[u1] == group_idx_per_cc[u2]:
-                    continue
-                cc2 = self.unique_cc_objects[u2]
-                inter = cc1.getOverlapArea(cc2)
-                entry = {"matched": matched, "unmatched": size1 + size2 - matched * 2,
-                         "area_union": cc1.getBoxArea() + cc2.getBoxArea() - inter, "area_intersection": inter}
-                g1, g2 = group_idx_per_cc[u1], group_idx_per_cc[u2]
-                for a, b in ((g1, g2), (g2, g1)):
-                    slot = conflicts[a].get(b)
-                    if slot is None:
-                        conflicts[a][b] = dict(entry)
-                    else:
-                        for k, v in entry.items():
-                            slot[k] += v
+        pairs = [(u1, u2, m, s2, s1) for u1 in stable_idxs for (u2, m, s2, s1) in all_overlapping_cc[u1] if u1 < u2]
+        if not pairs:
+            return conflicts
+        p = np.array(pairs, dtype=np.int64).reshape(-1, 5)
+        n = len(self.unique_cc_objects)
+        gi = np.full(n, -1, dtype=np.int64)
+        gi[np.fromiter(group_idx_per_cc.keys(), dtype=np.int64, count=len(group_idx_per_cc))] = \
+            np.fromiter(group_idx_per_cc.values(), dtype=np.int64, count=len(group_idx_per_cc))
+        g1, g2 = gi[p[:, 0]], gi[p[:, 1]]
+        keep = g1 != g2
+        p, g1, g2 = p[keep], g1[keep], g2[keep]
+        box = self._box_table()                                              # int64 [n][4] = min_x, max_x, min_y, max_y
+        a, b = box[p[:, 0]], box[p[:, 1]]
+        w = np.minimum(a[:, 1], b[:, 1]) - np.maximum(a[:, 0], b[:, 0]) + 1  # connected_component.py getOverlapArea
+        h = np.minimum(a[:, 3], b[:, 3]) - np.maximum(a[:, 2], b[:, 2]) + 1
+        inter = np.where((w > 0) & (h > 0), w * h, 0)
+        area = lambda q: (q[:, 1] - q[:, 0] + 1) * (q[:, 3] - q[:, 2] + 1)
+        vals = np.stack([p[:, 2], p[:, 4] + p[:, 3] - 2 * p[:, 2], area(a) + area(b) - inter, inter], axis=1)
+        keys = ("matched", "unmatched", "area_union", "area_intersection")
+        for ga, gb, v in zip(g1.tolist(), g2.tolist(), vals.tolist()):
+            for x, y in ((ga, gb), (gb, ga)):
+                slot = conflicts[x].get(y)
+                if slot is None:
+                    conflicts[x][y] = dict(zip(keys, v))
+                else:
+                    for k, q in zip(keys, v):
+                        slot[k] += q
         return conflicts
+
+    def _box_table(self):
+        """int64 [n_uniques][4] = min_x, max_x, min_y, max_y (aliases appended by split_stable_cc_by_gaps included)."""
+        objs = self.unique_cc_objects
+        cached = getattr(self, "_box_cache", None)
+        if cached is not None and len(cached) == len(objs):
+            return cached
+        t = np.array([(c.min_x, c.max_x, c.min_y, c.max_y) for c in objs], dtype=np.int64).reshape(-1, 4)
+        self._box_cache = t
+        return t
 
     # ---- :575-636 ---------------------------------------------------------------------------------------------
     def compute_group_images(self, cc_groups, group_ages, segment_threshold):
@@ -343,12 +372,17 @@ class GroupingMixin:
                 items.append((t, seg_index[(g, seg_of[g])]))
         items = np.array(items, dtype=np.int32).reshape(-1, 2)
         clean, n_frames = [], len(groups_per_frame)
-        from concurrent.futures import ThreadPoolExecutor
-        pool = ThreadPoolExecutor(max_workers=max(1, min(16, os.cpu_count() or 1)))
+        from .wire import PngEncoder
+        chunk = min(chunk, max(n_frames, 1))
+        enc = PngEncoder(self.width, self.height, chunk, torch.device("cuda", torch.cuda.current_device()), compress=True)
+        wpr = lib.am_words_per_row(self.width)
+        d_bits = torch.empty((chunk, self.height, wpr), dtype=torch.int32, device="cuda")
+        d_flags = torch.zeros((chunk,), dtype=torch.int32, device="cuda")
+        out = torch.empty(chunk * self.height * self.width + 8, dtype=torch.uint8, device="cuda")
+        enc8 = None
         for f0 in range(0, n_frames, chunk):
             nf = min(chunk, n_frames - f0)
             sel = items[(items[:, 0] >= f0) & (items[:, 0] < f0 + nf)]
-            out = torch.empty(nf * self.height * self.width + 8, dtype=torch.uint8, device="cuda")
             if len(sel):
                 d_f, d_i = _dev(sel[:, 0], np.int32), _dev(sel[:, 1], np.int32)
                 args = (len(sel), d_f.data_ptr(), d_i.data_ptr(), d_boxes.data_ptr(), d_off.data_ptr(), d_imgs.data_ptr())
@@ -356,10 +390,18 @@ class GroupingMixin:
                 args = (0, None, None, None, None, None)
             _lib.check(self._timed("am_paint_frames", lib.am_paint_frames, *args, f0, nf, self.height, self.width, out.data_ptr(), _stream()),
                        "am_paint_frames")
-            host = out[:nf * self.height * self.width].cpu().numpy().reshape(nf, self.height, self.width)
-            # the 03 -> 04 wire format (:677-678) stays cv2's PNG; the encoder releases the GIL, so frames encode in parallel
-            clean.extend(pool.map(lambda fr: cv2.imencode(".png", fr)[1], [host[t] for t in range(nf)]))
-        pool.shutdown()
+            # the 03 -> 04 wire format (`cv2.imencode(".png", reconstructed[:, :, 0])`, :677-678) written on the device: a clean frame
+            # whose pixels are all 0 / 255 is exactly a 1-bit image (csrc/png.cu, decodes to the same array); a frame where two groups
+            # overlap wraps to 254 (uint8 `+=`) and is written as an 8-bit grayscale PNG by the same writer
+            _lib.check(lib.am_pack_mask_u8_exact(out.data_ptr(), self.width, self.height, nf, d_bits.data_ptr(), d_flags.data_ptr(), _stream()),
+                       "am_pack_mask_u8_exact")
+            files = enc.encode(d_bits, nf)
+            flags = d_flags[:nf].cpu().numpy()
+            for t in np.nonzero(flags)[0].tolist():                       # the 8-bit form of the same writer keeps the 254s
+                if enc8 is None:
+                    enc8 = PngEncoder(self.width, self.height, 1, enc.device, compress=True, depth=8)
+                files[t] = enc8.encode(out[t * self.height * self.width:(t + 1) * self.height * self.width].view(1, self.height, self.width), 1)[0]
+            clean.extend(files)
         return clean
 
     def _upload_group_images(self, group_images, group_boundaries):

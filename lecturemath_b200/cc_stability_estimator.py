@@ -21,14 +21,68 @@ from .cc_grouping import GroupingMixin
 from .connected_component import ConnectedComponent
 from .packed_mask import PackedMask
 
-_LAZY = ("unique_cc_objects", "unique_cc_frames", "cc_idx_per_frame")
+
+
+class _LazyFrames:
+    """cc_idx_per_frame of a live estimator: per frame the list [(unique_idx, ConnectedComponent), ...] of the reference
+    (cc_stability_estimator.py:57, 102, 115, 145), built from the frame's result rows the first time somebody looks at that frame.
+    A long video holds millions of (frame, CC) instances, stage 03 touches a handful of frames (split_stable_cc_by_gaps) -- creating
+    them all up front was the single largest cost of the drop-in (1 s per 160k instances)."""
+
+    def __init__(self, est):
+        self._est = est
+        self._rows = []                  # per frame: the materialised list, or the raw (rows int32 [n][8], packed crops) pair
+
+    def _push_raw(self, rows, crops):
+        self._rows.append((rows, crops))
+
+    def _get(self, t):
+        r = self._rows[t]
+        if isinstance(r, tuple):
+            if t < 0:
+                t += len(self._rows)
+            r = self._rows[t] = self._est._build_row(t, *r)
+        return r
+
+    def row_len(self, t):
+        r = self._rows[t]
+        return len(r[0]) if isinstance(r, tuple) else len(r)
+
+    def unique_indices(self, t):
+        r = self._rows[t]
+        return r[0][:, 0].tolist() if isinstance(r, tuple) else [u for u, _ in r]
+
+    def __len__(self):
+        return len(self._rows)
+
+    def __getitem__(self, t):
+        if isinstance(t, slice):
+            return [self._get(i) for i in range(*t.indices(len(self._rows)))]
+        return self._get(t)
+
+    def __setitem__(self, t, value):
+        self._rows[t] = value
+
+    def __iter__(self):
+        for t in range(len(self._rows)):
+            yield self._get(t)
+
+    def append(self, value):
+        self._rows.append(value)
+
+    def __eq__(self, other):
+        return list(self) == list(other)
+
+    def __reduce__(self):                # pickles as the plain list it stands for
+        return (list, (list(self),))
 
 
 class CCStabilityEstimator(GroupingMixin):
     def __init__(self, width, height, min_recall, min_precision, max_gap, verbose=False, max_batch=16):
         self.width, self.height = width, height
         self.min_recall, self.min_precision, self.max_gap = min_recall, min_precision, max_gap
-        self._uniques, self._uframes, self._per_frame = [], [], []
+        self._uniques, self._uframes, self._per_frame = [], [], _LazyFrames(self)
+        self._ufirst = []                # per unique of the device numbering: (frame, raw label) of its first appearance
         self.fake_age = None
         self.img_idx = 0                 # frames handed in (staged frames included)
         self._tempo = 0
@@ -98,7 +152,7 @@ class CCStabilityEstimator(GroupingMixin):
         (lecturemath_b200.compat.dump_reference_pickle writes it under the reference's own class paths.)"""
         self._materialise()
         keep = {k: v for k, v in self.__dict__.items() if not k.startswith("_") and k != "device_ms"}
-        keep.update(unique_cc_objects=self._uniques, unique_cc_frames=self._uframes, cc_idx_per_frame=self._per_frame,
+        keep.update(unique_cc_objects=self._uniques, unique_cc_frames=self._uframes, cc_idx_per_frame=list(self._per_frame),
                     tempo_count=self._tempo)
         return keep
 
@@ -112,7 +166,9 @@ class CCStabilityEstimator(GroupingMixin):
 
     def get_raw_cc_count(self):                                          # :33-39
         self.flush()
-        return sum(len(f) for f in self._per_frame) + sum(len(r[0]) for r in getattr(self, "_raw", []))
+        pf = self._per_frame
+        done = sum(pf.row_len(t) for t in range(len(pf))) if isinstance(pf, _LazyFrames) else sum(len(f) for f in pf)
+        return done + sum(len(r[0]) for r in getattr(self, "_raw", []))
 
     # ---- reference-compatible per-frame entry point -------------------------------------------------
     def add_frame(self, img, input_binary=False):
@@ -248,34 +304,73 @@ class CCStabilityEstimator(GroupingMixin):
         self._n_unique_dev = st["n_unique"]
 
     def _materialise(self):
+        """Host view of everything the device has processed so far.  Vectorised over all outstanding frames: one ConnectedComponent
+        per NEW unique (its first-seen instance), the (frame, label) lists per unique, the per-frame tables stage 03 paints from;
+        the per-frame instance lists stay raw (see _LazyFrames)."""
         if getattr(self, "_engines", None) is None or (not self._raw and not self._staged and self._inflight == [None, None]):
             return
         self.flush()
         raw, self._raw = self._raw, []
+        if not raw:
+            return
+        t0 = self._absorbed
+        if len(self._uniques) != len(self._ufirst):
+            raise RuntimeError("frames were added after split_stable_cc_by_gaps renumbered the unique CCs (stage 03 runs on a finished estimator)")
+        lazy = isinstance(self._per_frame, _LazyFrames)
         for rows, crops in raw:
-            self._absorb(rows, crops)
-        if len(self._uniques) != self._n_unique_dev:
-            raise RuntimeError("device estimator holds %d uniques, the host view %d" % (self._n_unique_dev, len(self._uniques)))
+            self._frame_tables.append((np.ascontiguousarray(rows[:, 2:6]), rows[:, 7].astype(np.uint64),
+                                       crops if crops is not None else np.zeros(1, np.uint32)))
+            if lazy:
+                self._per_frame._push_raw(rows, crops)
+        counts = np.fromiter((len(r[0]) for r in raw), dtype=np.int64, count=len(raw))
+        self._absorbed += len(raw)
+        if counts.sum():
+            rows = np.concatenate([r[0] for r in raw if len(r[0])])
+            frame_of = np.repeat(np.arange(t0, t0 + len(raw)), counts)
+            u, lab = rows[:, 0].astype(np.int64), rows[:, 1].astype(np.int64)
+            n_old = len(self._ufirst)
+            # new uniques are numbered in order of appearance: the first row carrying each index >= n_old is its first-seen instance
+            new_u, first_row = np.unique(u, return_index=True)
+            first_row = first_row[new_u >= n_old]
+            crop_of = {}
+            for i in first_row.tolist():                                 # (:111-124)
+                f = int(frame_of[i]) - t0
+                _, lb, x0, x1, y0, y1, size, off = (int(v) for v in rows[i])
+                words = ((x1 >> 5) - (x0 >> 5) + 1) * (y1 - y0 + 1)
+                cc = ConnectedComponent(lb - 1, np.int32(x0), np.int32(x1), np.int32(y0), np.int32(y1), np.int32(size),
+                                        packed=raw[f][1][off:off + words])
+                cc.start_time = cc.end_time = np.float32(0.0)
+                self._uniques.append(cc)
+                self._uframes.append([])
+                self._ufirst.append((int(frame_of[i]), lb))
+            order = np.argsort(u, kind="stable")                          # (frame, label) order is kept inside every unique
+            us, fs, ls = u[order], frame_of[order].tolist(), lab[order].tolist()
+            cuts = np.flatnonzero(np.diff(us)) + 1
+            starts = np.concatenate([[0], cuts]).tolist()
+            ends = np.concatenate([cuts, [len(us)]]).tolist()
+            uframes = self._uframes
+            for a, b in zip(starts, ends):                                # (:99-104) / (:113)
+                uframes[int(us[a])].extend(zip(fs[a:b], ls[a:b]))
+        if not lazy:                                                      # somebody replaced cc_idx_per_frame by a plain list
+            for k, (rows_k, crops_k) in enumerate(raw):
+                self._per_frame.append(self._build_row(t0 + k, rows_k, crops_k))
+        if len(self._ufirst) != self._n_unique_dev:
+            raise RuntimeError("device estimator holds %d uniques, the host view %d" % (self._n_unique_dev, len(self._ufirst)))
 
-    def _absorb(self, rows, crops):
+    def _build_row(self, t, rows, crops):
+        """[(unique_idx, ConnectedComponent)] of frame t; the instance that founded a unique IS that unique's object (:113-115)."""
         current = []
-        t = self._absorbed
-        self._frame_tables.append((np.ascontiguousarray(rows[:, 2:6]), rows[:, 7].astype(np.uint64),
-                                   crops if crops is not None else np.zeros(1, np.uint32)))
         for r in rows:
             u, lab, x0, x1, y0, y1, size, off = (int(v) for v in r)
-            words = ((x1 >> 5) - (x0 >> 5) + 1) * (y1 - y0 + 1)
-            cc = ConnectedComponent(lab - 1, np.int32(x0), np.int32(x1), np.int32(y0), np.int32(y1), np.int32(size),
-                                    packed=crops[off:off + words])
-            cc.start_time = cc.end_time = np.float32(0.0)
-            if u == len(self._uniques):                                  # new unique CC (:111-124)
-                self._uniques.append(cc)
-                self._uframes.append([(t, lab)])
-            else:                                                        # matched (:99-104)
-                self._uframes[u].append((t, lab))
+            if u < len(self._ufirst) and self._ufirst[u] == (t, lab):
+                cc = self._uniques[u]
+            else:
+                words = ((x1 >> 5) - (x0 >> 5) + 1) * (y1 - y0 + 1)
+                cc = ConnectedComponent(lab - 1, np.int32(x0), np.int32(x1), np.int32(y0), np.int32(y1), np.int32(size),
+                                        packed=crops[off:off + words])
+                cc.start_time = cc.end_time = np.float32(0.0)
             current.append((u, cc))
-        self._per_frame.append(current)
-        self._absorbed += 1
+        return current
 
     def finish_processing(self):                                         # :158-164
         self.flush()

@@ -104,7 +104,7 @@ def reference_state(est):
         iy.add(int(cc.min_y), int(cc.max_y) + 1, u)
     return {"width": est.width, "height": est.height, "min_recall": est.min_recall, "min_precision": est.min_precision,
             "max_gap": est.max_gap, "unique_cc_objects": est.unique_cc_objects, "unique_cc_frames": est.unique_cc_frames,
-            "cc_idx_per_frame": est.cc_idx_per_frame, "cc_int_index_x": ix, "cc_int_index_y": iy,
+            "cc_idx_per_frame": list(est.cc_idx_per_frame), "cc_int_index_x": ix, "cc_int_index_y": iy,
             "fake_age": None if getattr(est, "fake_age", None) is None else np.zeros((est.height, est.width), dtype=np.float32),
             "img_idx": est.img_idx, "tempo_count": est.tempo_count, "cc_last_frame": last, "cc_active": active,
             "verbose": getattr(est, "verbose", False)}

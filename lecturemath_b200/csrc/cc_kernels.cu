@@ -67,6 +67,21 @@ __global__ void k_pack_u8(const uint8_t* __restrict__ src, int W, int H, int WPR
     if ((threadIdx.x & 31) == 0 && (x >> 5) < WPR) bits[((size_t)f * H + y) * WPR + (x >> 5)] = m;
 }
 
+// the same, and flags[f] |= 1 when frame f holds a value other than 0 / 255 (such a frame has no exact 1-bit form: the clean frames
+// of stage 03 wrap to 254 where two groups overlap, cc_stability_estimator.py:660-661)
+__global__ void k_pack_u8_exact(const uint8_t* __restrict__ src, int W, int H, int WPR, uint32_t* __restrict__ bits, int* __restrict__ flags) {
+    const int f = blockIdx.z, y = blockIdx.y;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint8_t* row = src + ((size_t)f * H + y) * W;
+    const uint8_t v = x < W ? row[x] : 0;
+    const unsigned m = __ballot_sync(0xffffffffu, v != 0);
+    const unsigned odd = __ballot_sync(0xffffffffu, v != 0 && v != 255);
+    if ((threadIdx.x & 31) == 0) {
+        if ((x >> 5) < WPR) bits[((size_t)f * H + y) * WPR + (x >> 5)] = m;
+        if (odd) atomicOr(&flags[f], 1);
+    }
+}
+
 // bit-packed -> uint8 0/255 (used to hand masks back in the reference's format)
 __global__ void k_unpack_u8(const uint32_t* __restrict__ bits, int W, int H, int WPR, uint8_t* __restrict__ dst) {
     const int f = blockIdx.z, y = blockIdx.y;
@@ -1185,6 +1200,15 @@ extern "C" int am_pack_mask_u8(const uint8_t* d_mask, int width, int height, int
     int WPR = am_words_per_row_impl(width);
     dim3 grid(am_div_up((long long)WPR * 32, 256), height, batch);
     k_pack_u8<<<grid, 256, 0, S(stream)>>>(d_mask, width, height, WPR, d_bits);
+    AM_CUDA(cudaGetLastError());
+    return AM_OK;
+}
+extern "C" int am_pack_mask_u8_exact(const uint8_t* d_mask, int width, int height, int batch, uint32_t* d_bits, int* d_flags, void* stream) {
+    if (!d_mask || !d_bits || !d_flags || width <= 0 || height <= 0 || batch <= 0) return AM_ERR_ARG;
+    const int WPR = am_words_per_row_impl(width);
+    AM_CUDA(cudaMemsetAsync(d_flags, 0, sizeof(int) * batch, S(stream)));
+    dim3 grid(am_div_up(WPR * 32, 256), height, batch);
+    k_pack_u8_exact<<<grid, 256, 0, S(stream)>>>(d_mask, width, height, WPR, d_bits, d_flags);
     AM_CUDA(cudaGetLastError());
     return AM_OK;
 }

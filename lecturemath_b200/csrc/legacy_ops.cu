@@ -367,3 +367,54 @@ extern "C" int speaker_detection_handle_frame(unsigned char* frame, unsigned cha
     change_deviation[0] = res[6]; change_deviation[1] = res[7];
     return (int)res[8];
 }
+
+
+// ------------------------------------------------------------------------------------------------------------------------------
+// Small downstream reducer: VideoSegmenter.compute_binary_sums
+// (R/AccessMath/preprocessing/content/video_segmenter.py:21-28: `binary.sum() / 255` per frame, the input of the stage-04
+// regression tree).  Per frame the SUM OF THE PIXEL VALUES as an exact 64-bit integer (the caller divides by 255 in fp64 exactly as
+// numpy does): from bit-packed frames 255 * popcount, from uint8 frames the byte sum.  One pass, 128-bit loads, block reduce + atomicAdd.
+__global__ void k_frame_sums_bits(const uint32_t* __restrict__ bits, long long words_per_frame, unsigned long long* __restrict__ out) {
+    const int f = blockIdx.y;
+    const uint4* p = (const uint4*)(bits + (size_t)f * words_per_frame);          // words_per_frame % 4 == 0 (WPR is)
+    unsigned long long acc = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < words_per_frame / 4; i += (long long)gridDim.x * blockDim.x) {
+        const uint4 v = p[i];
+        acc += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
+    }
+    for (int o = 16; o; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(&out[f], 255ull * acc);
+}
+__global__ void k_frame_sums_u8(const uint8_t* __restrict__ px, long long bytes_per_frame, unsigned long long* __restrict__ out) {
+    const int f = blockIdx.y;
+    const uint8_t* p = px + (size_t)f * bytes_per_frame;
+    unsigned long long acc = 0;
+    const long long head = min(bytes_per_frame, (long long)((16 - ((uintptr_t)p & 15)) & 15));     // bytes in front of the first aligned uint4
+    const long long nvec = (bytes_per_frame - head) / 16;
+    const uint4* v4 = (const uint4*)(p + head);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+        const uint4 v = v4[i];
+        acc += __vsadu4(v.x, 0) + __vsadu4(v.y, 0) + __vsadu4(v.z, 0) + __vsadu4(v.w, 0);            // sum of the four bytes of a word
+    }
+    if (blockIdx.x == 0) {
+        for (long long i = threadIdx.x; i < head; i += blockDim.x) acc += p[i];
+        for (long long i = head + nvec * 16 + threadIdx.x; i < bytes_per_frame; i += blockDim.x) acc += p[i];
+    }
+    for (int o = 16; o; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(&out[f], acc);
+}
+extern "C" int am_frame_sums_bits(const uint32_t* d_bits, int batch, int height, int width, unsigned long long* d_sums, void* stream) {
+    if (!d_bits || !d_sums || batch <= 0 || height <= 0 || width <= 0) return AM_ERR_ARG;
+    const long long wpf = (long long)height * am_words_per_row_impl(width);
+    AM_CUDA(cudaMemsetAsync(d_sums, 0, sizeof(unsigned long long) * batch, S(stream)));
+    k_frame_sums_bits<<<dim3(32, batch), 256, 0, S(stream)>>>(d_bits, wpf, d_sums);
+    AM_CUDA(cudaGetLastError());
+    return AM_OK;
+}
+extern "C" int am_frame_sums_u8(const uint8_t* d_frames, int batch, long long bytes_per_frame, unsigned long long* d_sums, void* stream) {
+    if (!d_frames || !d_sums || batch <= 0 || bytes_per_frame <= 0) return AM_ERR_ARG;
+    AM_CUDA(cudaMemsetAsync(d_sums, 0, sizeof(unsigned long long) * batch, S(stream)));
+    k_frame_sums_u8<<<dim3(64, batch), 256, 0, S(stream)>>>(d_frames, bytes_per_frame, d_sums);
+    AM_CUDA(cudaGetLastError());
+    return AM_OK;
+}

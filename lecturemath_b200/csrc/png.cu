@@ -70,7 +70,8 @@ long long deflate_capacity(long long raw) {      // zlib stream bytes in the wor
     return 2 + (raw * 9 + 7) / 8 + 8 * n_seg + 4;
 }
 
-// deflate = 0: the stored-block container (fixed size); 1: the fixed-Huffman writer, zlen / total are then CAPACITIES
+// deflate = 0: the stored-block container (fixed size); 1: the fixed-Huffman writer, zlen / total are then CAPACITIES; 2: the same
+// writer for 8-bit grayscale frames (one byte per pixel)
 int png_plan(int width, int height, int deflate, PngPlan** out) {
     int dev = 0;
     AM_CUDA(cudaGetDevice(&dev));
@@ -80,7 +81,7 @@ int png_plan(int width, int height, int deflate, PngPlan** out) {
     if (it == g_plans.end()) {
         PngPlan* p = new PngPlan();
         p->W = width; p->H = height; p->WPR = am_words_per_row_impl(width);
-        p->row_bytes = 1 + (width + 7) / 8;
+        p->row_bytes = 1 + (deflate == 2 ? width : (width + 7) / 8);
         p->raw = (long long)height * p->row_bytes;
         p->n_blocks = (p->raw + 65534) / 65535;
         p->zlen = deflate ? deflate_capacity(p->raw) : 2 + p->raw + 5 * p->n_blocks + 4;
@@ -92,7 +93,7 @@ int png_plan(int width, int height, int deflate, PngPlan** out) {
         const uint8_t sig[8] = {0x89, 'P', 'N', 'G', '\r', '\n', 0x1a, '\n'};
         memcpy(h, sig, 8);
         be32(h + 8, 13); memcpy(h + 12, "IHDR", 4); be32(h + 16, (uint32_t)width); be32(h + 20, (uint32_t)height);
-        h[24] = 1; h[25] = 0; h[26] = 0; h[27] = 0; h[28] = 0;       // bit depth 1, grayscale, deflate, filter method 0, no interlace
+        h[24] = deflate == 2 ? 8 : 1; h[25] = 0; h[26] = 0; h[27] = 0; h[28] = 0;   // bit depth, grayscale, deflate, filter method 0, no interlace
         be32(h + 29, crc_bytes(h + 12, 17));
         be32(h + 33, (uint32_t)p->zlen); memcpy(h + 37, "IDAT", 4);
         std::vector<uint32_t> t(256 + kLevels * 32);
@@ -108,6 +109,7 @@ int png_plan(int width, int height, int deflate, PngPlan** out) {
 
 struct PngArgs {
     int W, H, WPR, row_bytes, seg;
+    int depth;                                   // 1: source = bit-packed masks; 8: source = uint8 frames [H][W]
     long long raw, n_blocks, zlen, total;
     uint8_t head[41];
 };
@@ -294,6 +296,21 @@ __device__ __forceinline__ void length_symbol(int len, uint32_t& sym, int& eb, u
 constexpr int kLanePitch = kLaneBytes + 4;
 __device__ __forceinline__ void stage_segment(const uint32_t* __restrict__ fb, const PngArgs& a, unsigned seg_r0, uint8_t* sm, int lane) {
     const unsigned raw = (unsigned)a.raw, rb = (unsigned)a.row_bytes, last_bits = (unsigned)a.W & 7u;
+    if (a.depth == 8) {                                              // 8-bit grayscale: the scanline bytes are the pixels themselves
+        const uint8_t* px = (const uint8_t*)fb;
+#pragma unroll 4
+        for (unsigned i = lane; i < (unsigned)kSegBytes; i += 32) {
+            const unsigned r = seg_r0 + i;
+            uint32_t d = 0;
+            if (r < raw) {
+                const unsigned y = r / rb, c = r - y * rb;
+                if (c > 0) d = px[(size_t)y * a.W + (c - 1)];
+            }
+            sm[(i >> 8) * kLanePitch + (i & 255u)] = (uint8_t)d;
+        }
+        __syncwarp();
+        return;
+    }
 #pragma unroll 4
     for (unsigned i = lane; i < (unsigned)kSegBytes; i += 32) {
         const unsigned r = seg_r0 + i;
@@ -352,7 +369,7 @@ k_png1_deflate_count(const uint32_t* __restrict__ bits, const PngArgs a, int n_s
     const int f = blockIdx.y, lane = threadIdx.x & 31, s = blockIdx.x * kDefWarps + (threadIdx.x >> 5);
     if (s >= n_seg) return;
     __shared__ __align__(16) uint8_t s_seg[kDefWarps][32 * kLanePitch];
-    const uint32_t* fb = bits + (size_t)f * a.H * a.WPR;
+    const uint32_t* fb = a.depth == 8 ? (const uint32_t*)((const uint8_t*)bits + (size_t)f * a.H * a.W) : bits + (size_t)f * a.H * a.WPR;
     const unsigned raw = (unsigned)a.raw;
     const unsigned r0 = min(raw, (unsigned)s * kSegBytes + (unsigned)lane * kLaneBytes), r1 = min(raw, r0 + kLaneBytes);
     uint8_t* sm = s_seg[threadIdx.x >> 5];
@@ -407,7 +424,7 @@ k_png1_deflate_emit(const uint32_t* __restrict__ bits, const PngArgs a, int n_se
     const int f = blockIdx.y, lane = threadIdx.x & 31, s = blockIdx.x * kDefWarps + (threadIdx.x >> 5);
     if (s >= n_seg) return;
     __shared__ __align__(16) uint8_t s_seg[kDefWarps][32 * kLanePitch];
-    const uint32_t* fb = bits + (size_t)f * a.H * a.WPR;
+    const uint32_t* fb = a.depth == 8 ? (const uint32_t*)((const uint8_t*)bits + (size_t)f * a.H * a.W) : bits + (size_t)f * a.H * a.WPR;
     uint32_t* words = (uint32_t*)(out + (size_t)f * a.total);         // frame buffers start on 16-byte boundaries
     const unsigned raw = (unsigned)a.raw;
     const unsigned r0 = min(raw, (unsigned)s * kSegBytes + (unsigned)lane * kLaneBytes), r1 = min(raw, r0 + kLaneBytes);
@@ -482,7 +499,7 @@ extern "C" int am_png1_encode(const uint32_t* d_bits, int batch, int height, int
     if (rc) return rc;
     if (p->zlen > 0x7FFFFFFFLL) return AM_ERR_ARG;                    // chunk length field; also keeps raw < 2^31
     PngArgs a;
-    a.W = p->W; a.H = p->H; a.WPR = p->WPR; a.row_bytes = p->row_bytes; a.seg = p->seg;
+    a.W = p->W; a.H = p->H; a.WPR = p->WPR; a.row_bytes = p->row_bytes; a.seg = p->seg; a.depth = 1;
     a.raw = p->raw; a.n_blocks = p->n_blocks; a.zlen = p->zlen; a.total = p->total;
     memcpy(a.head, p->head, 41);
     unsigned long long* d_partial = nullptr;
@@ -501,17 +518,17 @@ extern "C" long long am_png1_capacity(int width, int height) {
     return ((8 + 25 + 12 + deflate_capacity(raw) + 12) + 15) & ~15LL;
 }
 
-extern "C" int am_png1_encode_deflate(const uint32_t* d_bits, int batch, int height, int width, uint8_t* d_out, long long* d_sizes,
-                                      void* stream) {
+static int png_encode_deflate(const uint32_t* d_bits, int depth, int batch, int height, int width, uint8_t* d_out, long long* d_sizes,
+                              void* stream) {
     if (!d_bits || !d_out || !d_sizes || batch <= 0 || width <= 0 || height <= 0) return AM_ERR_ARG;
     if (((uintptr_t)d_out & 15) != 0) return AM_ERR_ARG;
     PngPlan* p = nullptr;
-    int rc = png_plan(width, height, 1, &p);
+    int rc = png_plan(width, height, depth == 8 ? 2 : 1, &p);
     if (rc) return rc;
     const long long n_seg = (p->raw + kSegBytes - 1) / kSegBytes;
     if (p->zlen > 0x7FFFFFFFLL) return AM_ERR_ARG;
     PngArgs a;
-    a.W = p->W; a.H = p->H; a.WPR = p->WPR; a.row_bytes = p->row_bytes; a.seg = p->seg;
+    a.W = p->W; a.H = p->H; a.WPR = p->WPR; a.row_bytes = p->row_bytes; a.seg = p->seg; a.depth = depth;
     a.raw = p->raw; a.n_blocks = p->n_blocks; a.zlen = p->zlen; a.total = p->total;
     memcpy(a.head, p->head, 41);
     cudaStream_t st = (cudaStream_t)stream;
@@ -547,6 +564,21 @@ extern "C" int am_png1_encode_deflate(const uint32_t* d_bits, int batch, int hei
     k_png1_checksums<<<batch, kThreads, 0, st>>>(a, p->d_tables, nullptr, 0, d_out, d_zlen, d_sizes);
     AM_CUDA(cudaGetLastError());
     return AM_OK;
+}
+
+extern "C" int am_png1_encode_deflate(const uint32_t* d_bits, int batch, int height, int width, uint8_t* d_out, long long* d_sizes,
+                                      void* stream) {
+    return png_encode_deflate(d_bits, 1, batch, height, width, d_out, d_sizes, stream);
+}
+// 8-bit grayscale frames [batch][height][width] (e.g. the clean frames of stage 03 where two groups overlap and the pixel value is 254)
+extern "C" long long am_png8_capacity(int width, int height) {
+    if (width <= 0 || height <= 0) return 0;
+    const long long raw = (long long)height * (1 + width);
+    return ((8 + 25 + 12 + deflate_capacity(raw) + 12) + 15) & ~15LL;
+}
+extern "C" int am_png8_encode_deflate(const uint8_t* d_frames, int batch, int height, int width, uint8_t* d_out, long long* d_sizes,
+                                      void* stream) {
+    return png_encode_deflate((const uint32_t*)d_frames, 8, batch, height, width, d_out, d_sizes, stream);
 }
 
 extern "C" int am_png1_scanlines_to_bits(const uint8_t* d_scan, int batch, int height, int width, uint32_t* d_bits, void* stream) {

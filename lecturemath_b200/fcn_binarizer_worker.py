@@ -18,6 +18,11 @@ import torch
 
 
 class FCN_LectureNet_Binarizer:
+    # VideoProcessor (this package's) hands such a worker the decoded frame as it is when a resolution is forced: frames whose size
+    # differs from initialize(width, height) are resized on the device (am_resize_linear_u8 = cv2.resize's INTER_LINEAR algorithm,
+    # R/AccessMath/preprocessing/video_processor/video_processor.py:164-165), whole batches at a time
+    accepts_unresized_frames = True
+
     def __init__(self, lecture_net, keep_others=None, png="device", batch=1, estimator=None):
         """png: "device" = compressed_frames are written on the GPU from the bit-packed mask (csrc/png.cu: 1-bit grayscale, deflate;
                 decodes to the same pixels), "device-stored" = the same with stored deflate blocks, "cv2" = cv2.imencode on the host
@@ -62,9 +67,11 @@ class FCN_LectureNet_Binarizer:
         if self.batch > 1:
             return self._stage(frame, abs_time, abs_frame_idx)
         net = self.lecture_net
-        h, w = frame.shape[:2]
+        if self.width and self.height and frame.shape[:2] != (self.height, self.width):
+            frame = _resize_on_device(net, frame, self.width, self.height)                   # CUDA tensor (1, H, W, 3)
+        h, w = (self.height, self.width) if torch.is_tensor(frame) else frame.shape[:2]
         # frames above 2.5 MP: binarize_frames halves them (LANCZOS) and resizes the mask back (NEAREST) on the device
-        plan = net.binarize_frames(np.ascontiguousarray(frame)[None], want_others=self.keep_others)
+        plan = net.binarize_frames(frame if torch.is_tensor(frame) else np.ascontiguousarray(frame)[None], want_others=self.keep_others)
         binary, text_mask, rec_img = net.masks_from_plan(plan, 0, self.keep_others)
         if self.png != "cv2":
             if self._png_encoder is None or (self._png_encoder.width, self._png_encoder.height) != (w, h):
@@ -94,36 +101,58 @@ class FCN_LectureNet_Binarizer:
 
     # ---- batch > 1 ----------------------------------------------------------------------------------------------
     def _stage(self, frame, abs_time, abs_frame_idx):
+        if self._pipe is not None and self._pipe.in_shape != frame.shape[:2]:      # next file of the list has another capture size
+            self._pipe.drain(self)
+            self._pipe = None
         if self._pipe is None:
-            h, w = frame.shape[:2]
+            ih, iw = frame.shape[:2]
+            w, h = (self.width, self.height) if (self.width and self.height) else (iw, ih)
             # staging buffers (100 MB of pinned memory at 1080p x 8) are kept with the network and reused by the next worker / video
-            key = ("worker_pipe", w, h, self.batch, self.png != "device-stored", self.keep_others)
+            key = ("worker_pipe", w, h, iw, ih, self.batch, self.png != "device-stored", self.keep_others)
             pipe = self.lecture_net._plans.get(key)
             if pipe is None or pipe.busy:
-                pipe = _BatchPipe(self.lecture_net, w, h, self.batch, self.png != "device-stored", self.keep_others)
+                pipe = _BatchPipe(self.lecture_net, w, h, self.batch, self.png != "device-stored", self.keep_others, in_size=(iw, ih))
                 self.lecture_net._plans.setdefault(key, pipe)
             pipe.busy = True
             self._pipe = pipe
         self._pipe.push(self, frame, abs_time, abs_frame_idx)
 
 
+def _resize_on_device(net, frame, width, height):
+    """One frame (H, W, 3) uint8 numpy -> CUDA tensor (1, height, width, 3): cv2.resize(frame, (width, height)) on the device."""
+    from . import _lib
+    lib = _lib.lib()
+    if net._device is None:
+        net.cuda()
+    with torch.cuda.device(net._device):
+        src = torch.from_numpy(np.ascontiguousarray(frame)).to(net._device, non_blocking=True)
+        dst = torch.empty((1, height, width, 3), dtype=torch.uint8, device=net._device)
+        _lib.check(lib.am_resize_linear_u8(src.data_ptr(), 1, frame.shape[0], frame.shape[1], 3, height, width, dst.data_ptr(),
+                                           ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "am_resize_linear_u8")
+    return dst
+
+
 class _BatchPipe:
     """Two staging slots: while the GPU works on one batch the host fills the other.  Per batch, all on the compute stream unless
     noted: H2D (copy stream) -> [LANCZOS halving] -> FCN -> [mask upscale] -> [estimator] -> PNG encode + file read-back (own stream)."""
 
-    def __init__(self, net, width, height, batch, compress, keep_others):
+    def __init__(self, net, width, height, batch, compress, keep_others, in_size=None):
         from .wire import PngEncoder
         from . import _lib
-        _lib.lib()
+        self.lib = _lib.lib()
+        in_w, in_h = in_size or (width, height)
+        self.in_shape = (in_h, in_w)                                      # frames as the caller hands them (before a forced resize)
+        self.resize = (in_w, in_h) != (width, height)
         if net._device is None:
             net.cuda()
         self.net, self.width, self.height, self.batch, self.keep_others = net, width, height, batch, keep_others
         self.device = net._device
         self.large = net.large_adapter(batch, height, width)             # > 2.5 MP: FCN at the halved size (FCN_lecturenet.py:434-437)
         self.plan = net.plan(batch, self.large.fcn_height, self.large.fcn_width)
-        shape = (batch, height, width, 3)
+        shape = (batch, in_h, in_w, 3)
         self.h_in = [torch.empty(shape, dtype=torch.uint8).pin_memory() for _ in range(2)]
         self.d_in = [torch.empty(shape, dtype=torch.uint8, device=self.device) for _ in range(2)]
+        self.d_sized = torch.empty((batch, height, width, 3), dtype=torch.uint8, device=self.device) if self.resize else None
         self.fcn_in = torch.empty_like(self.plan.frames) if self.large.active else None
         # the slot's own copy of the batch's masks: the PNG encoder reads it on its stream while the next FCN step rewrites plan.bits
         self.bits = [torch.zeros((batch, height, self.plan.lib.am_words_per_row(width)), dtype=torch.int32, device=self.device)
@@ -167,12 +196,19 @@ class _BatchPipe:
             t[1].record(self.copy_stream)
             t[3].record(main)
             dbg.append(t)
+        frames = self.d_in[k]
+        if self.resize:                                                  # forced resolution (video_processor.py:164-165) on the device
+            from . import _lib
+            _lib.check(self.lib.am_resize_linear_u8(frames.data_ptr(), self.batch, self.in_shape[0], self.in_shape[1], 3, self.height, self.width,
+                                                    self.d_sized.data_ptr(), ctypes.c_void_p(main.cuda_stream)), "am_resize_linear_u8")
+            frames = self.d_sized
+            self.launches += 1
         if self.large.active:
-            self.large.downscale(self.fcn_in, main.cuda_stream, src=self.d_in[k])
+            self.large.downscale(self.fcn_in, main.cuda_stream, src=frames)
             plan.run(main.cuda_stream, self.keep_others, 128, frames=self.fcn_in, want_logits=False)
             bits = self.large.upscale_bits(plan.bits, main.cuda_stream, out=self.bits[k])
         else:
-            plan.run(main.cuda_stream, self.keep_others, 128, frames=self.d_in[k], want_logits=False)
+            plan.run(main.cuda_stream, self.keep_others, 128, frames=frames, want_logits=False)
             bits = self.bits[k]
             bits.copy_(plan.bits, non_blocking=True)
         self.launches += plan.launches_per_run + self.large.launches_per_run + 3

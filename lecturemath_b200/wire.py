@@ -17,10 +17,17 @@ FIRST_D2H_BYTES = 64 << 10           # per frame in the first read-back of the c
 
 
 class PngEncoder:
-    def __init__(self, width, height, max_batch=1, device=None, compress=True):
+    def __init__(self, width, height, max_batch=1, device=None, compress=True, depth=1):
+        """depth = 1: input = bit-packed masks [n][H][WPR]; depth = 8: input = uint8 grayscale frames [n][H][W] (compressed only)."""
         self.lib = _lib.lib()
         self.width, self.height, self.max_batch, self.compress = int(width), int(height), int(max_batch), bool(compress)
-        self.size = int(self.lib.am_png1_capacity(self.width, self.height) if compress else self.lib.am_png1_size(self.width, self.height))
+        self.depth = int(depth)
+        if self.depth == 8:
+            if not compress:
+                raise ValueError("the 8-bit writer only has the compressed form")
+            self.size = int(self.lib.am_png8_capacity(self.width, self.height))
+        else:
+            self.size = int(self.lib.am_png1_capacity(self.width, self.height) if compress else self.lib.am_png1_size(self.width, self.height))
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
         self.d_out = torch.empty((self.max_batch, self.size), dtype=torch.uint8, device=self.device)
         self.h_out = torch.empty((self.max_batch, self.size), dtype=torch.uint8).pin_memory()
@@ -35,7 +42,10 @@ class PngEncoder:
             raise ValueError("batch %d exceeds the encoder's capacity %d" % (n, self.max_batch))
         copy_stream = copy_stream or stream
         st = ctypes.c_void_p(stream.cuda_stream)
-        if self.compress:
+        if self.depth == 8:
+            _lib.check(self.lib.am_png8_encode_deflate(bits.data_ptr(), n, self.height, self.width, self.d_out.data_ptr(),
+                                                       self.d_sizes.data_ptr(), st), "am_png8_encode_deflate")
+        elif self.compress:
             _lib.check(self.lib.am_png1_encode_deflate(bits.data_ptr(), n, self.height, self.width, self.d_out.data_ptr(),
                                                        self.d_sizes.data_ptr(), st), "am_png1_encode_deflate")
         else:

@@ -112,7 +112,16 @@ def png1_deflate(mask):
     """uint8 (H, W) mask -> bytes of the 1-bit grayscale PNG with the compressed zlib stream, byte for byte what the device writes."""
     h, w = mask.shape
     rows = np.packbits(np.asarray(mask) != 0, axis=1, bitorder="big")
-    raw = np.concatenate([np.zeros((h, 1), np.uint8), rows], axis=1).tobytes()
+    return _deflate_png(np.concatenate([np.zeros((h, 1), np.uint8), rows], axis=1).tobytes(), w, h, 1)
+
+
+def png8_deflate(frame):
+    """uint8 (H, W) grayscale frame -> the 8-bit PNG am_png8_encode_deflate writes (same block structure, one byte per pixel)."""
+    h, w = frame.shape
+    return _deflate_png(np.concatenate([np.zeros((h, 1), np.uint8), np.asarray(frame, dtype=np.uint8)], axis=1).tobytes(), w, h, 8)
+
+
+def _deflate_png(raw, w, h, depth):
     n_seg = (len(raw) + SEG_BYTES - 1) // SEG_BYTES
     z = b"\x78\x01"
     for s in range(n_seg):
@@ -129,10 +138,10 @@ def png1_deflate(mask):
             b.put(0x0000, 16); b.put(0xFFFF, 16)
         z += b.tobytes()
     z += struct.pack(">I", zlib.adler32(raw))
-    return SIGNATURE + _chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 1, 0, 0, 0, 0)) + _chunk(b"IDAT", z) + _chunk(b"IEND", b"")
+    return SIGNATURE + _chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, depth, 0, 0, 0, 0)) + _chunk(b"IDAT", z) + _chunk(b"IEND", b"")
 
 
-def capacity(width, height):
-    raw = height * (1 + (width + 7) // 8)
+def capacity(width, height, depth=1):
+    raw = height * (1 + (width if depth == 8 else (width + 7) // 8))
     n_seg = (raw + SEG_BYTES - 1) // SEG_BYTES
     return (8 + 25 + 12 + (2 + (raw * 9 + 7) // 8 + 8 * n_seg + 4) + 12 + 15) // 16 * 16

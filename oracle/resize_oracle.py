@@ -111,3 +111,37 @@ def nearest_resize(img, out_w, out_h):
     """cv2.resize(img, (out_w, out_h), interpolation=cv2.INTER_NEAREST)."""
     h, w = img.shape[:2]
     return np.ascontiguousarray(img[nearest_offsets(h, out_h)][:, nearest_offsets(w, out_w)])
+
+
+def cv2_linear_u8(src, out_w, out_h):
+    """cv2.resize(src, (out_w, out_h)) with the default INTER_LINEAR on uint8 HxWxC -- OpenCV's 8-bit fixed-point algorithm
+    (imgproc/resize.cpp: resizeGeneric_, HResizeLinear<uchar, int, short, 2048>, VResizeLinear for uchar), the third-party operator
+    VideoProcessor.doProcessing applies when a resolution is forced (R/AccessMath/preprocessing/video_processor/video_processor.py:
+    164-165).  Unpinned dependency (OpenCV 4.13.0 here).  Exact against cv2.resize wherever that build runs its generic code (all
+    down-scales); its IPP path for up-scales differs by one grey level on ~0.1 % of the pixels (tests/test_oracle_resize.py)."""
+    src = np.asarray(src)
+    squeeze = src.ndim == 2
+    if squeeze:
+        src = src[:, :, None]
+    ih, iw, _ = src.shape
+
+    def axis(o, i):
+        scale = 1.0 / (o / float(i))
+        f = ((np.arange(o, dtype=np.float64) + 0.5) * scale - 0.5).astype(np.float32)
+        s = np.floor(f).astype(np.int64)
+        f = (f - s.astype(np.float32)).astype(np.float32)
+        lo, hi = s < 0, s >= i - 1
+        f[lo], s[lo] = 0, 0
+        f[hi], s[hi] = 0, i - 1
+        c0 = np.rint((np.float32(1.0) - f) * np.float32(2048)).astype(np.int64)        # saturate_cast<short>: round half to even
+        c1 = np.rint(f * np.float32(2048)).astype(np.int64)
+        return s, np.minimum(s + 1, i - 1), c0, c1
+
+    sx, sx1, a0, a1 = axis(out_w, iw)
+    sy, sy1, b0, b1 = axis(out_h, ih)
+    S = src.astype(np.int64)
+    rows = S[:, sx, :] * a0[None, :, None] + S[:, sx1, :] * a1[None, :, None]
+    r0, r1 = rows[sy] >> 4, rows[sy1] >> 4
+    out = (((r0 * b0[:, None, None]) >> 16) + ((r1 * b1[:, None, None]) >> 16) + 2) >> 2
+    out = np.clip(out, 0, 255).astype(np.uint8)
+    return out[:, :, 0] if squeeze else out

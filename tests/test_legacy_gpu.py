@@ -97,3 +97,34 @@ def test_device_pointer_variants_match_host_exports():
                                         res.data_ptr(), st) == 0
     t, b, a, dv = L.speaker_detection(f1, f0, 40, 2)
     np.testing.assert_array_equal(res.cpu().numpy(), np.concatenate([b, a, dv, [float(t)]]))
+
+
+def test_compute_binary_sums_equals_numpy_on_every_kind_of_frame():
+    """VideoSegmenter.compute_binary_sums (R/AccessMath/preprocessing/content/video_segmenter.py:21-28: `binary.sum() / 255` per
+    frame): lazy bit-packed frames (PNG scanlines and device words), decoded uint8 frames incl. the 254 values stage 03 can produce,
+    odd sizes -- every entry bit-identical to the reference's expression, in the input order."""
+    from lecturemath_b200.helper import Helper
+    from lecturemath_b200.packed_mask import PackedMask
+    from lecturemath_b200.video_segmenter import VideoSegmenter
+    from oracle import png_oracle as PO
+    rng = np.random.default_rng(12)
+    frames, dense = [], []
+    for k, (h, w) in enumerate([(180, 256), (180, 256), (37, 101), (180, 256), (1080, 1920), (37, 101), (180, 256)]):
+        m = (rng.random((h, w)) < 0.1 * (k + 1)).astype(np.uint8) * 255
+        if k == 3:
+            m[5:9, 7:30] = 254                                         # a clean frame where two groups overlapped (uint8 wrap)
+            frames.append(m)
+        elif k % 3 == 0:
+            frames.append(Helper.decompress_binary_images([np.frombuffer(PO.png1_deflate(m), np.uint8)])[0])    # scanline form
+        elif k % 3 == 1:
+            frames.append(PackedMask.from_dense(m))                    # word form
+        else:
+            frames.append(m)
+        dense.append(m)
+    frames.append(np.ones((10, 10), dtype=np.int32) * 255)             # not a decoded PNG: numpy's own reduction
+    dense.append(frames[-1])
+    got = VideoSegmenter.compute_binary_sums(frames, batch=2)
+    ref = [b.sum() / 255 for b in dense]
+    assert len(got) == len(ref)
+    for a, b in zip(got, ref):
+        assert float(a) == float(b) and isinstance(float(a), float)

@@ -59,6 +59,24 @@ def test_deflate_png_bytes_checksums_and_reference_reader(hw):
         assert len(files[1]) * 50 < PO.size(w, h) and len(files[3]) * 4 < PO.size(w, h)
 
 
+@pytest.mark.parametrize("hw", [(1080, 1920), (37, 101), (5, 7), (1, 1), (64, 4096)])
+def test_deflate_png8_bytes_and_reference_reader(hw):
+    """The 8-bit form of the writer (stage 03's clean frames where overlapping groups wrapped to 254): byte-identical to the CPU
+    restatement, valid container, decoded by cv2.imdecode to the frame."""
+    from lecturemath_b200.wire import PngEncoder
+    h, w = hw
+    rng = np.random.default_rng(h * 13 + w)
+    frames = (rng.random((3, h, w)) < 0.02).astype(np.uint8) * 255
+    frames[1][rng.random((h, w)) < 0.01] = 254
+    frames[2] = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    files = PngEncoder(w, h, 3, compress=True, depth=8).encode(torch.from_numpy(frames).cuda())
+    for f in range(3):
+        png = files[f].tobytes()
+        assert PO.png8_deflate(frames[f]) == png
+        assert len(png) <= PO.capacity(w, h, 8)
+        np.testing.assert_array_equal(PO.decode(files[f]), frames[f])
+
+
 def test_scanlines_to_bits_roundtrip_on_device():
     """Decode half: file -> (host: zlib inflate, lazy PackedMask) -> am_png1_scanlines_to_bits -> the words the encoder started from."""
     from lecturemath_b200 import _lib
