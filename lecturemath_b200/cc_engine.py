@@ -40,12 +40,29 @@ class CCEngine:
         self.width, self.height, self.max_batch = int(width), int(height), int(max_batch)
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
         self.wpr = self.lib.am_words_per_row(self.width)
+        self._caps = [int(max_runs), int(max_labels), int(max_kept), int(crop_words), int(min_pixels)]
+        self._grow = 0                   # how often the default capacities have been doubled (label(sync=True) retries on overflow)
+        self._create()
+        self.counts = None
+
+    def _create(self):
+        runs, labels, kept, crops, min_pixels = self._caps
         with torch.cuda.device(self.device):
-            self.ctx = self.lib.am_cc_create(self.width, self.height, self.max_batch, max_runs, max_labels, max_kept,
-                                             crop_words, min_pixels)
+            self.ctx = self.lib.am_cc_create(self.width, self.height, self.max_batch, runs, labels, kept, crops, min_pixels)
         if not self.ctx:
             raise _lib.AccessMathB200Error("am_cc_create failed")
-        self.counts = None
+
+    def _enlarge(self):
+        """Double the kept-CC and crop capacities (the reference has no such limits: many overlapping large bounding boxes -- long
+        diagonal strokes, a board frame around everything -- need more crop words than the 4 x frame default)."""
+        P = self.width * self.height
+        self._grow += 1
+        runs, labels, kept, crops, min_pixels = self._caps
+        kept = min(P // 2 + 64, 2 * (kept if kept > 0 else P // max(1, min_pixels) + 64))
+        crops = 2 * (crops if crops > 0 else 4 * self.wpr * self.height + 1024)
+        self._caps = [runs, labels, kept, crops, min_pixels]
+        self.close()
+        self._create()
 
     def close(self):
         if getattr(self, "ctx", None):
@@ -85,7 +102,13 @@ class CCEngine:
                    "am_cc_label_batch")
         self.batch = b
         if sync:
-            self.read_counts()
+            try:
+                self.read_counts()
+            except _lib.AccessMathB200Error as e:
+                if "code 3" not in str(e) or self._grow >= 4:
+                    raise
+                self._enlarge()                                          # capacity: grow and label the same masks again
+                return self.label(bits, want_labels, sync, out)
         return labels
 
     def read_counts(self):

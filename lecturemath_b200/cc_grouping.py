@@ -43,6 +43,38 @@ def _crop_words(cc):
     return ((int(cc.max_x) >> 5) - (int(cc.min_x) >> 5) + 1) * (int(cc.max_y) - int(cc.min_y) + 1)
 
 
+def view_from_components(ccs):
+    """am_unique_view over host objects (min_x, max_x, min_y, max_y, size, img / packed crop): their boxes and bit-packed crops are
+    uploaded once.  -> (UniqueView, tensors that must stay alive as long as the view is used)."""
+    words = np.array([_crop_words(c) for c in ccs], dtype=np.int64)
+    offs = np.concatenate([[0], np.cumsum(words)]).astype(np.uint64)
+    arena = np.concatenate([_packed(c) for c in ccs]) if ccs else np.zeros(1, np.uint32)
+    cols = [_dev([int(getattr(c, k)) for c in ccs], np.int32) for k in ("min_x", "max_x", "min_y", "max_y", "size")]
+    keep = cols + [_dev(offs[:-1], np.uint64), _dev(arena.view(np.int32), np.int32)]
+    view = UniqueView()
+    for name, t in zip(("min_x", "max_x", "min_y", "max_y", "size", "crop_off", "arena"), keep):
+        setattr(view, name, t.data_ptr())
+    view.n = len(ccs)
+    return view, keep
+
+
+def overlap_pairs(view, d_ids, n, timed=None):
+    """int64 [n_pairs][3] = (a, b, matched pixels) for all positions a < b of the n listed view rows whose inclusive bounding boxes
+    intersect, ascending (am_group_overlaps)."""
+    lib = _lib.lib()
+    cap = max(1024, 8 * n)
+    while True:
+        pairs = torch.empty((cap, 3), dtype=torch.int32, device="cuda")
+        cnt = ctypes.c_longlong(0)
+        args = (ctypes.byref(view), d_ids.data_ptr(), n, pairs.data_ptr(), cap, ctypes.byref(cnt), _stream())
+        rc = timed("am_group_overlaps", lib.am_group_overlaps, *args) if timed else lib.am_group_overlaps(*args)
+        if rc == 3:
+            cap = int(cnt.value)
+            continue
+        _lib.check(rc, "am_group_overlaps")
+        return pairs[:cnt.value].cpu().numpy().astype(np.int64)
+
+
 class GroupingMixin:
     def _timed(self, name, fn, *args):
         """Run one C-ABI call; when self.device_ms is a dict (tools/grouping_bench.py) accumulate its CUDA-event time there."""
@@ -80,23 +112,16 @@ class GroupingMixin:
             rows = sorted(first.values())
             remap = {u: i for i, u in enumerate(rows)}
             obj_index = np.array([remap[int(v)] for v in obj_index], dtype=np.int32)
-            words = np.array([_crop_words(c) for c in ccs], dtype=np.int64)
-            offs = np.concatenate([[0], np.cumsum(words)]).astype(np.uint64)
-            arena = np.concatenate([_packed(c) for c in ccs]) if ccs else np.zeros(1, np.uint32)
-            cols = [_dev([int(getattr(c, k)) for c in ccs], np.int32) for k in ("min_x", "max_x", "min_y", "max_y", "size")]
-            keep = cols + [_dev(offs[:-1], np.uint64), _dev(arena.view(np.int32), np.int32)]
-            for name, t in zip(("min_x", "max_x", "min_y", "max_y", "size", "crop_off", "arena"), keep):
-                setattr(view, name, t.data_ptr())
-            view.n = len(ccs)
+            view, keep = view_from_components(ccs)
         self._view_cache = (view, obj_index, n, keep)
         return view, obj_index
 
     # ---- :166-179 ---------------------------------------------------------------------------------------------
     def rebuilt_binary_images(self, chunk=64):
         out = []
+        n_frames = len(self.cc_idx_per_frame)                         # (a live estimator builds its host view -- and the tables -- here)
         tables = getattr(self, "_frame_tables", None)
-        fast = tables is not None and len(tables) == len(self.cc_idx_per_frame)
-        n_frames = len(self.cc_idx_per_frame)
+        fast = tables is not None and len(tables) == n_frames
         for f0 in range(0, n_frames, chunk):
             if fast:                                                  # the per-frame tables exactly as stage 02 read them back
                 tb = tables[f0:f0 + chunk]
@@ -184,18 +209,7 @@ class GroupingMixin:
             return np.zeros((0, 3), dtype=np.int64)
         assert np.all(np.diff(ids) > 0), "stable_idxs must be ascending (get_stable_cc_idxs)"
         d_ids = _dev(obj_index[ids], np.int32)
-        cap = max(1024, 8 * len(ids))
-        while True:
-            pairs = torch.empty((cap, 3), dtype=torch.int32, device="cuda")
-            n = ctypes.c_longlong(0)
-            rc = self._timed("am_group_overlaps", lib.am_group_overlaps, ctypes.byref(view), d_ids.data_ptr(), len(ids), pairs.data_ptr(), cap,
-                             ctypes.byref(n), _stream())
-            if rc == 3:
-                cap = int(n.value)
-                continue
-            _lib.check(rc, "am_group_overlaps")
-            break
-        p = pairs[:n.value].cpu().numpy().astype(np.int64)
+        p = overlap_pairs(view, d_ids, len(ids), self._timed)
         p[:, 0], p[:, 1] = ids[p[:, 0]], ids[p[:, 1]]
         return p
 
@@ -300,7 +314,12 @@ class GroupingMixin:
         cached = getattr(self, "_box_cache", None)
         if cached is not None and len(cached) == len(objs):
             return cached
-        t = np.array([(c.min_x, c.max_x, c.min_y, c.max_y) for c in objs], dtype=np.int64).reshape(-1, 4)
+        dev_boxes = getattr(self, "_uboxes", None)
+        if dev_boxes is not None and len(dev_boxes) and getattr(self, "_est", None) is not None:
+            _, obj_index = self._unique_view()                            # live estimator: the boxes as the device reported them
+            t = dev_boxes[obj_index]
+        else:
+            t = np.array([(c.min_x, c.max_x, c.min_y, c.max_y) for c in objs], dtype=np.int64).reshape(-1, 4)
         self._box_cache = t
         return t
 

@@ -83,6 +83,7 @@ class CCStabilityEstimator(GroupingMixin):
         self.min_recall, self.min_precision, self.max_gap = min_recall, min_precision, max_gap
         self._uniques, self._uframes, self._per_frame = [], [], _LazyFrames(self)
         self._ufirst = []                # per unique of the device numbering: (frame, raw label) of its first appearance
+        self._uboxes = np.zeros((0, 4), dtype=np.int64)
         self.fake_age = None
         self.img_idx = 0                 # frames handed in (staged frames included)
         self._tempo = 0
@@ -332,17 +333,17 @@ class CCStabilityEstimator(GroupingMixin):
             # new uniques are numbered in order of appearance: the first row carrying each index >= n_old is its first-seen instance
             new_u, first_row = np.unique(u, return_index=True)
             first_row = first_row[new_u >= n_old]
-            crop_of = {}
-            for i in first_row.tolist():                                 # (:111-124)
-                f = int(frame_of[i]) - t0
-                _, lb, x0, x1, y0, y1, size, off = (int(v) for v in rows[i])
+            founders = rows[first_row]
+            self._uboxes = np.concatenate([self._uboxes, founders[:, 2:6].astype(np.int64)])      # min_x, max_x, min_y, max_y per unique
+            zero = np.float32(0.0)
+            for f, (_, lb, x0, x1, y0, y1, size, off), b32 in zip((frame_of[first_row] - t0).tolist(), founders.tolist(),
+                                                                  founders[:, 2:7]):            # (:111-124)
                 words = ((x1 >> 5) - (x0 >> 5) + 1) * (y1 - y0 + 1)
-                cc = ConnectedComponent(lb - 1, np.int32(x0), np.int32(x1), np.int32(y0), np.int32(y1), np.int32(size),
-                                        packed=raw[f][1][off:off + words])
-                cc.start_time = cc.end_time = np.float32(0.0)
+                cc = ConnectedComponent(lb - 1, b32[0], b32[1], b32[2], b32[3], b32[4], packed=raw[f][1][off:off + words])
+                cc.start_time = cc.end_time = zero
                 self._uniques.append(cc)
                 self._uframes.append([])
-                self._ufirst.append((int(frame_of[i]), lb))
+                self._ufirst.append((f + t0, lb))
             order = np.argsort(u, kind="stable")                          # (frame, label) order is kept inside every unique
             us, fs, ls = u[order], frame_of[order].tolist(), lab[order].tolist()
             cuts = np.flatnonzero(np.diff(us)) + 1

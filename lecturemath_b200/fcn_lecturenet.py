@@ -164,9 +164,21 @@ TUNED_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tuned_pla
 _TUNED = None
 
 
+def arch_signature(sd):
+    """Key of the tuned table: everything the per-layer GEMM shapes depend on besides (batch, H, W) -- channel widths and kernel sizes
+    (the FCN_BINARIZER_NET_* keys are configurable; a table measured for one architecture must not steer another)."""
+    w = lambda n: sd[n].shape
+    down = ".".join(str(w("conv_down_block_%d.0.weight" % i)[0]) for i in range(1, 6))
+    ups = ".".join(str(w("transposed_conv_%d.weight" % i)[1]) for i in range(1, 6))
+    upc = ".".join(str(w("conv_up_block_%d.0.weight" % i)[0]) for i in range(1, 6))
+    return "c%d_d%s_m%d_t%s_u%s_k%d_p%d_pm%d.%d" % (w("conv_down_block_1.0.weight")[1], down, w("mid_block.0.weight")[0], ups, upc,
+                                                    w("conv_down_block_1.0.weight")[-1], w("conv_pixels_1.0.weight")[-1],
+                                                    w("conv_pixels_1.0.weight")[0], w("conv_pixels_2.0.weight")[0])
+
+
 def tuned_table():
-    """{"B<batch>_<H>x<W>": {layer name: [S, Sy, NT, MT]}} measured on a B200 by tools/autotune_fcn.py (per-layer CUDA-event
-    timings of every feasible packing / tiling); layers or shapes without an entry fall back to the cycle model."""
+    """{architecture signature: {"B<batch>_<H>x<W>": {layer name: [S, Sy, NT, MT]}}} measured on a B200 by tools/autotune_fcn.py
+    (per-layer CUDA-event timings of every feasible packing / tiling); layers or shapes without an entry fall back to the cycle model."""
     global _TUNED
     if _TUNED is None:
         _TUNED = {}
@@ -282,8 +294,12 @@ class FCNPlan:
         self.lib = _lib.load()          # building a plan needs no device; run() does (and fails loudly without one)
         self.B, self.H, self.W, self.device, self.rowrun = B, H, W, device, rowrun
         sd = {k: v.detach().float().cpu() for k, v in net.state_dict().items()}
+        self.arch = arch_signature(sd)
         k = sd["conv_down_block_1.0.weight"].shape[-1]
         pk = sd["conv_pixels_1.0.weight"].shape[-1]
+        if k > pk:
+            raise ValueError("FCN_BINARIZER_NET_KERNEL_SIZE (%d) larger than FCN_BINARIZER_NET_PIXEL_KERNEL_SIZE (%d): the text-mask and "
+                             "reconstruction heads share one %dx%d GEMM, which cannot hold the larger filter" % (k, pk, pk, pk))
         p3, p7 = (k - 1) // 2, (pk - 1) // 2
         down = [sd["conv_down_block_%d.0.weight" % i].shape[0] for i in range(1, 6)]
         mid = sd["mid_block.0.weight"].shape[0]
@@ -427,12 +443,14 @@ class FCNPlan:
         if not self.rowrun:
             return 1, 1, choose_nt(cout), None
         forced = self.ov.get("cfg", {}).get(name)
-        if forced is None and "sy" not in self.ov and "mt" not in self.ov and not self.ov.get("no_tuned"):
-            forced = tuned_table().get("B%d_%dx%d" % (self.B, self.H, self.W), {}).get(name)
         if forced is not None:
             return tuple(forced)
-        best = None
         cands = self._candidates(width, height, cout, seg_cs, KW, KH, cap)
+        if "sy" not in self.ov and "mt" not in self.ov and not self.ov.get("no_tuned"):
+            tuned = tuned_table().get(self.arch, {}).get("B%d_%dx%d" % (self.B, self.H, self.W), {}).get(name)
+            if tuned is not None and any(tuple(c[1:]) == tuple(tuned) for c in cands):      # only a configuration that is feasible HERE
+                return tuple(tuned)
+        best = None
         if "mt" in self.ov and any(c[4] == self.ov["mt"] for c in cands):       # tests: force the M-tiles per work item where feasible
             cands = [c for c in cands if c[4] == self.ov["mt"]]
         for c in cands:
@@ -545,7 +563,9 @@ class FCNPlan:
         cin, cout = wt.shape[0], wt.shape[1]
         forced = self.ov.get("cfg", {}).get(name)
         if forced is None and self.rowrun and "sy" not in self.ov and "mt" not in self.ov and not self.ov.get("no_tuned"):
-            forced = tuned_table().get("B%d_%dx%d" % (self.B, self.H, self.W), {}).get(name)
+            forced = tuned_table().get(self.arch, {}).get("B%d_%dx%d" % (self.B, self.H, self.W), {}).get(name)
+            if forced is not None and layer_cost(src.W, src.H, 4 * cout, [src.C], 1, self.B, nt=forced[2], mt=forced[3]) is None:
+                forced = None                                             # not feasible for this shape: fall back to the model
         if forced is not None:
             NT, MT = forced[2], forced[3]
         else:

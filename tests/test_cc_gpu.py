@@ -233,3 +233,23 @@ def test_4k_label_rows_crops_and_match_vs_oracle(kind):
     st = est.state()
     assert st["tempo_count"] == est_o.tempo_count and st["n_unique"] == len(est_o.unique_cc_objects)
     assert (len(est_o.unique_cc_objects) > 15000) if kind == "dense" else (len(est_o.unique_cc_objects) > 50)
+
+
+def test_capacity_overflow_grows_and_retries(golden):
+    """The reference has no capacity limits.  A synchronous label() whose kept-CC / crop capacities overflow doubles them and labels
+    the same masks again (CCEngine._enlarge) instead of failing; the asynchronous pipelines still fail loudly (their temporal state
+    has already consumed the truncated tables)."""
+    from lecturemath_b200.cc_engine import CCEngine
+    from lecturemath_b200._lib import AccessMathB200Error
+    z = golden("cc_label_stats.npz")
+    mask = z["glyph_180x320_mask"]
+    eng = CCEngine(320, 180, 1, max_kept=64, crop_words=1024)
+    bits = eng.pack(torch.from_numpy(mask[None]).cuda())
+    eng.label(bits, want_labels=False)                                 # sync=True: overflows, grows, relabels
+    assert eng._grow >= 1
+    rows = eng.kept_rows(0)
+    np.testing.assert_array_equal(rows[:, 1:7].astype(np.int64), z["glyph_180x320_table"])
+    tiny = CCEngine(320, 180, 1, max_kept=64, crop_words=1024)
+    tiny.label(bits, want_labels=False, sync=False)
+    with pytest.raises(AccessMathB200Error):
+        tiny.read_counts()

@@ -80,3 +80,20 @@ def test_paint_wraparound_and_unaligned_rows():
     got = est._paint(2, frames, ccs)
     np.testing.assert_array_equal(np.stack(got), ref)
     assert ref.max() == 255 and len(np.unique(ref)) > 4
+
+
+@pytest.mark.parametrize("name", sorted(RUNS))
+def test_keyframes_for_intervals_vs_reference_golden(golden, name):
+    """KeyframeExtractor.GenerateFromST3DForIntervals with the overlap tests and the painting on the device: key-frames and sorted
+    (time, box) lists equal the unmodified reference's (tests/golden/keyframes.npz) on four videos x five intervals."""
+    from types import SimpleNamespace
+    from lecturemath_b200.keyframe_extractor import KeyframeExtractor
+    from oracle.gen_golden_keyframes import unpack_st3d
+    from tests.test_oracle_keyframes import check, expected
+    z = golden("keyframes.npz")
+    n, h, w, segs, content, ref_times = expected(z, name)
+    ages, images, bounds = unpack_st3d(z, name + "/")
+    st3d = SimpleNamespace(frame_times=[40.0 * t for t in range(n)], frame_indices=list(range(n)), height=h, width=w, cc_group_ages=ages,
+                           cc_group_images=images, cc_group_boundaries=bounds)
+    kfs, times = KeyframeExtractor.GenerateFromST3DForIntervals(st3d, segs, False)
+    check(kfs, times, content, ref_times)

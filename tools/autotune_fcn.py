@@ -86,7 +86,7 @@ def main():
     if os.path.exists(path):
         with open(path) as f:
             table = json.load(f)
-    table.setdefault("B%d_%dx%d" % (args.batch, h, w), {}).update(result)
+    table.setdefault(plan.arch, {}).setdefault("B%d_%dx%d" % (args.batch, h, w), {}).update(result)
     with open(path, "w") as f:
         json.dump(table, f, indent=1, sort_keys=True)
     print("wrote", path)
