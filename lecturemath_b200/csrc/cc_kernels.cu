@@ -1463,6 +1463,8 @@ extern "C" int am_est_add_frames(am_estimator* e, am_cc_ctx* c, int first, int n
         if (per_sm < 1) per_sm = 1;
         if (per_sm > occ) per_sm = occ;
         e->fused_grid = sms * per_sm;
+        const char* gabs = getenv("AM_B200_MATCH_GRID");                // tuning knob: absolute CTA count of the cooperative launch
+        if (gabs && atoi(gabs) >= 2 && atoi(gabs) <= sms * occ) e->fused_grid = atoi(gabs);
         e->fused_mode = (coop && e->fused_grid >= 2 && !(env && strcmp(env, "multi") == 0)) ? 1 : 0;
     }
     const int fused_mode = e->fused_mode, fused_grid = e->fused_grid;

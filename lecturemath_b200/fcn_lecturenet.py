@@ -629,6 +629,23 @@ class FCNPlan:
         _lib.check(self.lib.am_conv_plan_info(self._conv_plan(i, self.ops[i][1]), info), "am_conv_plan_info")
         return list(info)
 
+    def executed_flops(self, i):
+        """FLOPs the tensor cores execute for conv op i per frame: valid GEMM rows x padded N x executed K (Toeplitz taps of the S / Sy
+        packing, channel padding, 16-wide K steps), with the half-width edge taps of the CTA-pair kernel counted as halves.  The ratio
+        to op_flops[i] (algorithmic) is the padding overhead `--layer-table` reports."""
+        d = self.ops[i][1]
+        k_per_tap = 0
+        for s in range(d.nseg):
+            g = d.seg[s]
+            length, reps = (g.run_len, 1) if g.rowrun else (g.C, g.KW)
+            nck = (length + 63) // 64
+            k_per_tap += reps * ((nck - 1) * 64 + ((length - (nck - 1) * 64) + 15) // 16 * 16)
+        taps = float(d.KH)
+        if (d.flags & AM_CONV_CTA_PAIR) and d.in_ystep == 2 and d.Sy == 2 and d.KH >= 4 and d.Ntot_pad == d.NT == d.Ntot and d.NT % 32 == 0 \
+                and d.NT >= 128:
+            taps -= 1.0                                                   # two edge taps at N / 2 (csrc/fcn_conv.cu: edge_half)
+        return 2.0 * d.Hin * d.nR * d.Ntot_pad * k_per_tap * taps
+
     def __del__(self):
         try:
             for h in self._cplans.values():

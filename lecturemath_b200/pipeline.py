@@ -230,8 +230,11 @@ class StreamingExtractor:
         main = torch.cuda.current_stream(self.device)
         kin = s & 1
         src = self.inbuf[kin]
-        if frames.is_cuda:
-            src.copy_(frames, non_blocking=True)
+        if frames.is_cuda:                                               # already resident: read in place (the caller keeps it alive and
+            if frames.is_contiguous() and frames.dtype == torch.uint8 and frames.shape == src.shape:    # unchanged until the step ran)
+                src = frames
+            else:
+                src.copy_(frames, non_blocking=True)
         else:                                                            # pinned host frames: H2D on the copy stream
             with torch.cuda.stream(self.copy_stream):
                 if self.ev_in_free[kin] is not None:
@@ -246,7 +249,7 @@ class StreamingExtractor:
             plan.run(main.cuda_stream, False, 128, timing, frames=src, want_logits=False)
         if self.ev_in_free[kin] is None:
             self.ev_in_free[kin] = torch.cuda.Event()
-        self.ev_in_free[kin].record(main)
+        self.ev_in_free[kin].record(main)                                 # (the heads epilogue is the last reader of the frames)
         self.bits = self.large.upscale_bits(plan.bits, main.cuda_stream) if self.large.active else plan.bits   # :481-486
         if inject_bits is not None:
             self.bits = inject_bits
@@ -366,6 +369,31 @@ class StreamingExtractor:
 
     def masks_host(self):
         return self.engines[0].unpack(self.bits).cpu().numpy()
+
+
+def bind_host_to_gpu(device_index):
+    """Pin this process to the CPU cores next to its GPU (NVML's ideal CPU affinity of the device) BEFORE it allocates pinned staging
+    memory: with one process per GPU on a two-socket box, first-touch then places every rank's host buffers on the socket its PCIe
+    root hangs off, instead of wherever the launcher started the process.  Returns the core list, or None when NVML / the affinity call
+    is unavailable (nothing is changed then)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = device_index
+        if visible and all(v.strip().isdigit() for v in visible.split(",")):
+            phys = int(visible.split(",")[device_index])
+        handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        n_words = (os.cpu_count() + 63) // 64
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, n_words)
+        cores = [64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1]
+        allowed = sorted(set(cores) & os.sched_getaffinity(0))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return allowed
+    except Exception:
+        return None
 
 
 def shard_ranges(n_frames, world):
