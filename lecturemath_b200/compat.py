@@ -141,7 +141,8 @@ class _ReferencePickler(pickle.Pickler):
 
 
 def dump_reference_pickle(est, file, protocol=pickle.HIGHEST_PROTOCOL):
-    """pickle `est` (this package's CCStabilityEstimator, any state) into `file` the way the reference's stage 02 would have
+    """pickle `est` -- this package's CCStabilityEstimator, or any object graph holding one, e.g. stage 02's hand-off tuple
+    (frame_times, frame_indices, estimator) of R/pre_ST3D_v3.0_02_cc_analaysis.py:43 -- into `file` the way the reference would have
     (R/AM_CommonTools/util/misc_helper.py:157-163 uses HIGHEST_PROTOCOL), loadable by the unmodified reference."""
     targets, temp = {}, []
     for path in (EST_PATH, CC_PATH, IDX_PATH):

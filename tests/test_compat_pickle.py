@@ -97,7 +97,8 @@ shutil.copy(os.path.join(repo, "oracle", "_ref", "accessmath_lib_ref.so"), os.pa
 os.chdir(tmp)                                   # the reference CDLL-loads ./accessmath_lib.so at import time (labeler.py:24)
 sys.path.insert(0, ref)
 with open(path, "rb") as f:
-    est = pickle.load(f)
+    frame_times, frame_indices, est = pickle.load(f)          # stage 02's hand-off tuple (pre_ST3D_v3.0_02_cc_analaysis.py:43)
+assert frame_indices == list(range(len(frame_times)))
 import AccessMath.preprocessing.content.cc_stability_estimator as M
 assert type(est) is M.CCStabilityEstimator and not hasattr(M, "__lecturemath_b200_alias__")
 split_gap, min_times, t_window = (int(v) for v in sys.argv[4:7])
@@ -120,7 +121,7 @@ def test_unmodified_reference_loads_and_runs_stage03_on_it(golden, tmp_path):
     split_gap, min_times, t_window, _, _ = zg[name + "/params"]
     path = tmp_path / "tempo_stability_test.dat"
     with open(path, "wb") as f:
-        compat.dump_reference_pickle(est, f)
+        compat.dump_reference_pickle(([40.0 * t for t in range(est.img_idx)], list(range(est.img_idx)), est), f)
     script = tmp_path / "load_in_reference.py"
     script.write_text(_REF_SCRIPT)
     CO.build()
