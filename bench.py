@@ -364,7 +364,9 @@ def run_ours(args):
     # streams ~19 GB of activations through it), so no step finds its inputs cached; --l2-flush adds the 256 MB flush write as well
     frame_bytes = H * W * 3
     pool_n = max(4 * B, B * (-(-(160 << 20) // (B * frame_bytes))))
-    pool_h = torch.from_numpy(frame_pool(pool_n, 1234 + rank)).pin_memory()
+    # ONE synthetic video for the whole job (every rank builds the same seeded pool): global chunk c = step * world + rank reads pool
+    # chunk c mod (pool / B), i.e. the ranks process consecutive chunks of the same cyclic video, as a sharded lecture would be
+    pool_h = torch.from_numpy(frame_pool(pool_n, 1234)).pin_memory()
     pool_d = pool_h.to(dev)
     l2_flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if args.l2_flush else None
     main = torch.cuda.current_stream(dev)
@@ -390,8 +392,9 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def batch_of(pool, i):                                # contiguous slice of the (pinned host | device) frame pool
-        s = (i % (pool_n // B)) * B
+    def batch_of(pool, i, r=None):                        # global chunk i * world + r of the (pinned host | device) frame pool
+        c = i * world + (rank if r is None else r)
+        s = (c % (pool_n // B)) * B
         return pool[s:s + B]
 
     def run_video(n_steps, host_io, timing=None, keep=None, ex=None, chunk_of=None):
@@ -480,11 +483,10 @@ def run_ours(args):
             rows_n = {}
             for g in gathered:
                 rows_n.update(g)
-            pools = [pool_h] + [torch.from_numpy(frame_pool(pool_n, 1234 + r)).pin_memory() for r in range(1, world)]
             ref = StreamingExtractor(net, W, H, 0.85, 0.85, 85, batch=B, rank=0, world=1, device=dev)
             rows_1 = {}
             run_video(world * K, True, keep=rows_1, ex=ref,
-                      chunk_of=lambda c: (batch_of(pools[c % world], c // world), inject_of(c % world, c // world)))
+                      chunk_of=lambda c: (batch_of(pool_h, c // world, c % world), inject_of(c % world, c // world)))
             st1 = ref.finish()
             same_rows = sorted(rows_n) == sorted(rows_1) and all(
                 len(rows_n[c]) == len(rows_1[c]) and all(np.array_equal(a, b) for a, b in zip(rows_n[c], rows_1[c])) for c in rows_1)
@@ -493,7 +495,7 @@ def run_ours(args):
                            "n_unique": [int(fin[0].item()), st1["n_unique"]], "tempo_count": [int(fin[1].item()), st1["tempo_count"]],
                            "what": "per-frame result rows, unique count and tempo_count of the %d-rank e2e run vs a 1-rank replay of the same %d chunks"
                                    % (world, world * K)}
-            del ref, pools
+            del ref
         barrier()
     if rank == 0:
         sampler.stop_flag = True
