@@ -148,3 +148,35 @@ def test_fused_pipeline_on_large_frames_vs_oracle(golden):
         ref = np.array(est.frame_table(f), dtype=np.int64).reshape(-1, 7)
         np.testing.assert_array_equal(rows[f].astype(np.int64), ref)
     assert ex.est.state()["tempo_count"] == est.tempo_count
+
+
+def test_batching_worker_on_large_frames_equals_fused_pipeline(golden):
+    """The asynchronous worker on frames above 2.5 MP (device LANCZOS halving, FCN at half size, NEAREST mask upscale, per-slot mask
+    copies for the PNG writer) with an estimator attached: the files decode to the masks the fused ContentExtractor produces for the
+    same batches, and the estimator reaches the same rows / tempo_count."""
+    from lecturemath_b200 import synth
+    from lecturemath_b200.cc_stability_estimator import CCStabilityEstimator
+    from lecturemath_b200.fcn_binarizer_worker import FCN_LectureNet_Binarizer
+    from lecturemath_b200.helper import Helper
+    from lecturemath_b200.pipeline import ContentExtractor
+    h, w, b, n = 1300, 2000, 2, 5
+    net = golden_net("tiny", golden("fcn_forward.npz")).cuda()
+    frames = np.stack(list(synth.whiteboard_frames(n + 1, h, w, seed=23)))
+    ex = ContentExtractor(net, w, h, 0.85, 0.85, 85, batch=b, device="cuda:0")
+    ref_rows, ref_masks = [], []
+    for s in range(0, n + 1, b):                                        # three full batches (the last frame only pads the third)
+        ref_rows += ex.process_batch(frames[s:s + b])
+        ref_masks.append(ex.masks_host())
+    ref_masks = np.concatenate(ref_masks)
+    est = CCStabilityEstimator(w, h, 0.85, 0.85, 85, max_batch=b)
+    worker = FCN_LectureNet_Binarizer(net, batch=b, estimator=est)
+    worker.initialize(w, h)
+    for i in range(n):                                                 # five frames: the last batch is partial
+        worker.handleFrame(frames[i], None, 0, 40.0 * i, 40.0 * i, i)
+    worker.finalize()
+    masks = Helper.decompress_binary_images(worker.compressed_frames)
+    assert len(masks) == n and worker.frame_indices == list(range(n))
+    for i in range(n):
+        np.testing.assert_array_equal(np.asarray(masks[i]), ref_masks[i])
+    got = [[(u, cc.cc_id + 1, int(cc.min_x), int(cc.max_x), int(cc.min_y), int(cc.max_y), int(cc.size)) for u, cc in fr] for fr in est.cc_idx_per_frame]
+    assert got == [[tuple(int(v) for v in r) for r in ref_rows[i]] for i in range(n)]
