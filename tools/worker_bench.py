@@ -39,7 +39,19 @@ def main():
         line[mode + "_frames_per_s"] = round(args.frames / dt, 1)
         line[mode + "_png_kb_per_frame"] = round(float(np.mean([len(r) for r in w.compressed_frames])) / 1e3, 1)
         decoded[mode] = Helper.decompress_binary_images(w.compressed_frames[:4])
-    line["decoded_identical"] = all(np.array_equal(a, b) for a, b in zip(decoded["device"], decoded["cv2"]))
+    line["decoded_identical"] = all(np.array_equal(np.asarray(a), np.asarray(b)) for a, b in zip(decoded["device"], decoded["cv2"]))
+    # the same calls through the batching worker (handleFrame stages, one GPU step per 8 frames, finalize drains)
+    for rep in range(2):
+        w = FCN_LectureNet_Binarizer(net, batch=8)
+        w.initialize(1920, 1080)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(args.frames):
+            w.handleFrame(frames[i % 16], None, 0, 33.3 * i, 33.3 * i, i)
+        w.finalize()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+    line["device_batch8_frames_per_s"] = round(args.frames / dt, 1)
     print(json.dumps(line))
 
 
