@@ -69,6 +69,7 @@ struct alignas(64) ConvParams {
     int Cout, Sy, Sx, Ntot, act;
     unsigned cout_magic;  // floor(2^32 / Cout) + 1 (Cout >= 2)
     void* pool_out; int pool_H, pool_W, pool_sx, pool_padx; long long pool_sn, pool_sy;   // fused MaxPool2d(2) destination (NULL = off)
+    int pool2;            // fused MaxPool2d(2) with Sx = Sy = 2 packing: the 2x2 block of a pooled pixel is ONE GEMM row (see kPOOL2)
     int epi_per_q;        // epilogue warps per TMEM lane quarter that take part in this launch (<= compiled EPI_WARPS / 4)
     unsigned nrt_magic, nyt_magic, nnb_magic;   // floor(2^32 / d) + 1 for d = nRT, nYT, nNB (0 when d == 1): exact for n * d < 2^32
     const float* bias;
@@ -333,10 +334,10 @@ __device__ __forceinline__ void epi_threshold(const ConvParams& p, const uint32_
 // Epilogue of one 16-column unit of one accumulator row: bias + activation + NHWC store.
 // With a fused max-pool (p.pool_out) EVERY lane of the warp calls this (row_ok only predicates the stores): the 2x2 block of an
 // output pixel sits in lanes l, l^1 (x) and l^RT (y), so the pooled value is two shuffle + max rounds on the packed bf16 pairs.
-template <bool kFUSED>
+template <bool kFUSED, bool kPOOL2 = false>
 __device__ __forceinline__ void epi_unit(const ConvParams& p, const uint32_t (&v)[16], const float* __restrict__ sbias, int n0, int j0,
                                          long long base, bool vec16, bool vec8, bool f32fast, bool sy1_ok, bool row_ok = true,
-                                         long long pbase = 0, bool pool_ok = false) {
+                                         long long pbase = 0, bool pool_ok = false, uint4* spool = nullptr) {
     if (kFUSED) {                                          // the instantiations the two fp32 layers are launched with
         if (p.epi_mode == AM_EPI_HEADS) epi_heads(p, v, sbias, n0, j0, base, pbase, sy1_ok);
         else epi_threshold(p, v, sbias, n0, j0, base, pbase, sy1_ok);
@@ -379,7 +380,10 @@ __device__ __forceinline__ void epi_unit(const ConvParams& p, const uint32_t (&v
                 *(uint4*)(o + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
             }
         }
-        if (p.pool_out != nullptr) {                       // warp-uniform
+        if (kPOOL2) {                                      // this lane's 16 activated channels of one (sy, sx) group -> shared memory
+            spool[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            spool[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        } else if (p.pool_out != nullptr) {                // warp-uniform
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 uint32_t t = __shfl_xor_sync(0xffffffffu, pk[i], 1);
@@ -485,7 +489,12 @@ __device__ __forceinline__ int sched_next(uint32_t schedFull, uint32_t schedEmpt
 // kMT = M-tiles per work item, kRES = weights resident in shared memory (compile-time so the single-warp issue loops stay short)
 // kMT = 4 (four issuer warps, warps 1..4) takes the epilogue down to 12 warps (8..19) so that the CTA stays at 640 threads
 // (96 registers each: 20 warps is what the register file holds).
-template <int kMT, bool kRES, bool kFUSED>
+// kPOOL2 (kMT = 1 only): MaxPool2d(2) fused for Sx = Sy = 2 packing (conv_down_block_1).  A GEMM row holds the whole 2x2 block of one
+// pooled pixel, but as four 16-column units per channel slice that the unit interleaving hands to four DIFFERENT warps of the lane
+// quarter (same lane).  Every warp parks its packed bf16 results in shared memory (32 B per unit and lane), the quarter's warps meet at
+// a named barrier, then each warp takes channel slices h, h + epiPerQ, ..., maxes the four groups and stores the pooled pixel: the
+// 1.5 GB re-read of the separate k_maxpool2 pass disappears for ~5 % more epilogue instructions.
+template <int kMT, bool kRES, bool kFUSED, bool kPOOL2 = false>
 __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv_gemm(const __grid_constant__ ConvParams p) {
     constexpr int kEpiFirst = (kMT == 4) ? 8 : 4;                      // first epilogue warp (multiple of 4: TMEM lane quarters)
     constexpr int kEpiWarps = (CONV_THREADS / 32) - kEpiFirst;
@@ -507,6 +516,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv_gemm(const __grid_cons
     const uint32_t schedFull = accEmpty + 16, schedEmpty = schedFull + 8 * SCHED_DEPTH;
     const uint32_t sched_w = schedEmpty + 8 * SCHED_DEPTH;             // SCHED_DEPTH ints
     const uint32_t tmem_slot = sched_w + 4 * SCHED_DEPTH;
+    const uint32_t sPool = (tmem_slot + 4u + 15u) & ~15u;             // kPOOL2: [4 quarters][NT / 16 units][32 lanes] x 32 B
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform for ptxas
     const int lane = threadIdx.x & 31;
 
@@ -703,7 +713,10 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv_gemm(const __grid_cons
                     const TileCoord tc = decode_tile(p, st * kMT + mt);
                     const int y = tc.y0 + yy, r = tc.r0 + rr;
                     row_ok = tc.valid && (y < p.Hin) && (r < p.nR);
-                    if (p.pool_out != nullptr) {             // Sx = Sy = 1: (y, r) is the output pixel; even lanes of even rows write the pooled pixel
+                    if (kPOOL2) {                            // Sx = Sy = 2: GEMM row (y, r) IS the pooled pixel
+                        pool_ok = tc.valid && y < p.pool_H && r < p.pool_W;
+                        pbase = (long long)tc.frame * p.pool_sn + (long long)y * p.pool_sy + (long long)(r + p.pool_padx) * p.pool_sx;
+                    } else if (p.pool_out != nullptr) {      // Sx = Sy = 1: (y, r) is the output pixel; even lanes of even rows write the pooled pixel
                         pool_ok = tc.valid && !((y | r) & 1) && (y >> 1) < p.pool_H && (r >> 1) < p.pool_W;
                         pbase = (long long)tc.frame * p.pool_sn + (long long)(y >> 1) * p.pool_sy + (long long)((r >> 1) + p.pool_padx) * p.pool_sx;
                     }
@@ -714,19 +727,21 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv_gemm(const __grid_cons
                 }
                 return (g - mt * units_per_tile) * 16;
             };
+            uint4* spool_q = (uint4*)(smem_raw + (sPool - smem_u32(smem_raw))) + (size_t)q * units_per_tile * 64;     // 2 x uint4 per lane
+            auto spool_of = [&](int g) -> uint4* { return kPOOL2 ? spool_q + ((size_t)g * 32 + lane) * 2 : nullptr; };
             int g = h;
             if (g < units) tmem_ld16_async(unit_addr(g), va);
             while (g < units) {
                 tmem_wait16(va);
                 int g2 = g + epiPerQ;
                 if (g2 < units) tmem_ld16_async(unit_addr(g2), vb);
-                { const int j0 = enter(g); if (row_ok || p.pool_out != nullptr) epi_unit<kFUSED>(p, va, sbias, n0, j0, base, vec16, vec8, f32fast, sy1_ok, row_ok, pbase, pool_ok); }
+                { const int j0 = enter(g); if (row_ok || p.pool_out != nullptr) epi_unit<kFUSED, kPOOL2>(p, va, sbias, n0, j0, base, vec16, vec8, f32fast, sy1_ok, row_ok, pbase, pool_ok, spool_of(g)); }
                 g = g2;
                 if (g >= units) break;
                 tmem_wait16(vb);
                 g2 = g + epiPerQ;
                 if (g2 < units) tmem_ld16_async(unit_addr(g2), va);
-                { const int j0 = enter(g); if (row_ok || p.pool_out != nullptr) epi_unit<kFUSED>(p, vb, sbias, n0, j0, base, vec16, vec8, f32fast, sy1_ok, row_ok, pbase, pool_ok); }
+                { const int j0 = enter(g); if (row_ok || p.pool_out != nullptr) epi_unit<kFUSED, kPOOL2>(p, vb, sbias, n0, j0, base, vec16, vec8, f32fast, sy1_ok, row_ok, pbase, pool_ok, spool_of(g)); }
                 g = g2;
             }
             // all tcgen05.ld of this stage have completed (tmem_wait16 in the last iteration): hand the stage back
@@ -734,6 +749,38 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv_gemm(const __grid_cons
             __syncwarp();
             if (lane == 0) mbar_arrive(accEmpty + 8 * as);
             if (++as == p.acc_stages) { as = 0; pacc ^= 1; }
+            if (kPOOL2) {
+                // the quarter's warps have parked all units of this tile: max over the four (sy, sx) groups per channel slice
+                asm volatile("bar.sync %0, %1;" ::"r"(2 + q), "r"(epiPerQ * 32) : "memory");
+                const int slices = units_per_tile >> 2;                              // Cout / 16
+                for (int sl = h; sl < slices; sl += epiPerQ) {
+                    uint4 m0, m1;
+                    {
+                        const uint4* a = spool_q + ((size_t)sl * 32 + lane) * 2;
+                        m0 = a[0]; m1 = a[1];
+                    }
+#pragma unroll
+                    for (int grp = 1; grp < 4; ++grp) {
+                        const uint4* a = spool_q + ((size_t)(grp * slices + sl) * 32 + lane) * 2;
+                        const uint4 b0 = a[0], b1 = a[1];
+                        __nv_bfloat162 t;
+                        t = __hmax2(*(__nv_bfloat162*)&m0.x, *(const __nv_bfloat162*)&b0.x); m0.x = *(uint32_t*)&t;
+                        t = __hmax2(*(__nv_bfloat162*)&m0.y, *(const __nv_bfloat162*)&b0.y); m0.y = *(uint32_t*)&t;
+                        t = __hmax2(*(__nv_bfloat162*)&m0.z, *(const __nv_bfloat162*)&b0.z); m0.z = *(uint32_t*)&t;
+                        t = __hmax2(*(__nv_bfloat162*)&m0.w, *(const __nv_bfloat162*)&b0.w); m0.w = *(uint32_t*)&t;
+                        t = __hmax2(*(__nv_bfloat162*)&m1.x, *(const __nv_bfloat162*)&b1.x); m1.x = *(uint32_t*)&t;
+                        t = __hmax2(*(__nv_bfloat162*)&m1.y, *(const __nv_bfloat162*)&b1.y); m1.y = *(uint32_t*)&t;
+                        t = __hmax2(*(__nv_bfloat162*)&m1.z, *(const __nv_bfloat162*)&b1.z); m1.z = *(uint32_t*)&t;
+                        t = __hmax2(*(__nv_bfloat162*)&m1.w, *(const __nv_bfloat162*)&b1.w); m1.w = *(uint32_t*)&t;
+                    }
+                    if (pool_ok) {
+                        __nv_bfloat16* po = (__nv_bfloat16*)p.pool_out + pbase + sl * 16;
+                        *(uint4*)po = m0;
+                        *(uint4*)(po + 8) = m1;
+                    }
+                }
+                asm volatile("bar.sync %0, %1;" ::"r"(2 + q), "r"(epiPerQ * 32) : "memory");      // parked values consumed: next tile may overwrite
+            }
         }
         tc_fence_before();
     }
@@ -1153,7 +1200,16 @@ static int conv_prepare(const am_conv_desc* d, am_conv_plan* plan) {
     p.Cout = d->Cout; p.Sy = d->Sy; p.Sx = d->Sx; p.Ntot = d->Ntot; p.act = d->act; p.bias = d->bias;
     p.pool_out = d->pool_out; p.pool_H = d->pool_H; p.pool_W = d->pool_W; p.pool_sn = d->pool_sn; p.pool_sy = d->pool_sy;
     p.pool_sx = d->pool_sx; p.pool_padx = d->pool_padx;
-    if (d->pool_out) {            // the fused pool rides on the single-address 16-channel epilogue path
+    p.pool2 = 0;
+    if (d->pool_out && d->Sx == 2 && d->Sy == 2) {        // the 2x2 block of a pooled pixel is one GEMM row (kPOOL2)
+        const bool vec16 = (d->Cout & 15) == 0 && !d->out_f32 && ((d->out_coff | d->out_sx | (int)(d->out_sy & 7) | (int)(d->out_sn & 7)) & 7) == 0;
+        if (ystep != 2 || !vec16 || d->Ntot != 4 * d->Cout || d->Ntot_pad != d->NT || d->NT != d->Ntot || (d->pool_sx & 7) || (d->pool_sy & 7) ||
+            (d->pool_sn & 7) || d->pool_H != d->out_H / 2 || d->pool_W != d->out_W / 2 || pair || (d->flags & (AM_CONV_FORCE_MT2 | AM_CONV_FORCE_MT4))) {
+            fprintf(stderr, "[accessmath_b200] am_conv: fused max-pool with Sx = Sy = 2 needs one N block of 4 x Cout columns, Cout %% 16 == 0, one M-tile per item\n");
+            return AM_ERR_ARG;
+        }
+        p.pool2 = 1;
+    } else if (d->pool_out) {            // the fused pool rides on the single-address 16-channel epilogue path
         const bool vec16 = (d->Cout & 15) == 0 && !d->out_f32 && ((d->out_coff | d->out_sx | (int)(d->out_sy & 7) | (int)(d->out_sn & 7)) & 7) == 0;
         if (d->Sx != 1 || d->Sy != 1 || d->RT > 16 || !vec16 || d->Ntot != d->Cout || (d->pool_sx & 15) || (d->pool_sy & 15) || (d->pool_sn & 15) ||
             d->pool_H != d->out_H / 2 || d->pool_W != d->out_W / 2) {
@@ -1195,8 +1251,9 @@ static int conv_prepare(const am_conv_desc* d, am_conv_plan* plan) {
     // ---- shared-memory / TMEM budget -------------------------------------------------------------------
     const size_t bytesA1 = (size_t)box_rows * d->RT * 128, bytesB = (size_t)d->NT * 128;
     const size_t fixed = 1024 /*align*/ + 1024 /*bias (<= 256 floats)*/ + 512 /*barriers*/;
-    const size_t budget = 226 * 1024;
-    if (pair) {          // two M-tiles per CTA, streamed half weight tiles
+    const size_t budget_total = 226 * 1024;
+    if (pair) {
+        const size_t budget = budget_total;          // two M-tiles per CTA, streamed half weight tiles
         if (2 * p.NTc > 512) return AM_ERR_ARG;
         const size_t bytesBh = bytesB / 2;
         int sa = 2, sb = 2;
@@ -1217,6 +1274,8 @@ static int conv_prepare(const am_conv_desc* d, am_conv_plan* plan) {
         plan->grid = 2 * clusters;
         return AM_OK;
     }
+    const size_t pool_bytes = p.pool2 ? (size_t)4 * (d->NT / 16) * 32 * 32 + 16 : 0;      // kPOOL2 staging: [4 quarters][units][32 lanes] x 32 B
+    const size_t budget = budget_total - pool_bytes;
     const size_t allB = bytesB * (size_t)total_chunks * d->KH;
     // Mode choice (mirrored by fcn_lecturenet.layer_cost):
     //   MT = 2 (two M-tiles per work item, one MMA issuer warp each) whenever there is enough work to keep every SM busy;
@@ -1226,10 +1285,11 @@ static int conv_prepare(const am_conv_desc* d, am_conv_plan* plan) {
     const bool many = !(d->flags & AM_CONV_NO_MT2) && p.n_mtiles * p.nNB >= 4 * sm_count() && tmem2;
     const bool can_res = !(d->flags & AM_CONV_NO_RESIDENT) && p.nNB == 1;
     const bool res2 = can_res && fixed + allB + 2 * 2 * bytesA1 <= budget;
-    const bool res1 = can_res && fixed + allB + 3 * bytesA1 <= budget;
+    const bool res1 = can_res && fixed + allB + (p.pool2 ? 2 : 3) * bytesA1 <= budget;
     int resident, MT;
     const bool res4 = can_res && fixed + allB + 2 * 4 * bytesA1 <= budget;
-    if ((d->flags & AM_CONV_FORCE_MT4) && 4 * p.NTc <= 512) { MT = 4; resident = res4 ? 1 : 0; }  // the planner decided
+    if (p.pool2) { MT = 1; resident = res1 ? 1 : 0; }
+    else if ((d->flags & AM_CONV_FORCE_MT4) && 4 * p.NTc <= 512) { MT = 4; resident = res4 ? 1 : 0; }  // the planner decided
     else if ((d->flags & AM_CONV_FORCE_MT2) && tmem2) { MT = 2; resident = res2 ? 1 : 0; }
     else if (d->flags & AM_CONV_NO_MT2) { MT = 1; resident = res1 ? 1 : 0; }
     else if (res2 && many) { resident = 1; MT = 2; }
@@ -1238,7 +1298,7 @@ static int conv_prepare(const am_conv_desc* d, am_conv_plan* plan) {
     else { resident = res1 ? 1 : 0; MT = 1; }
     int sa, sb;
     if (resident) {
-        sb = 1; sa = MT >= 2 ? 2 : 3;
+        sb = 1; sa = (MT >= 2 || p.pool2) ? 2 : 3;
         while (sa < 8 && fixed + allB + (size_t)(sa + 1) * MT * bytesA1 <= budget) ++sa;
     } else {
         sa = 2; sb = 2;
@@ -1258,7 +1318,7 @@ static int conv_prepare(const am_conv_desc* d, am_conv_plan* plan) {
     p.tmem_cols = 32; while (p.tmem_cols < p.acc_stages * MT * p.NTc) p.tmem_cols <<= 1;
     p.n_work = ((p.n_mtiles + MT - 1) / MT) * p.nNB;
     const size_t nB = resident ? (size_t)total_chunks * d->KH : (size_t)sb;
-    plan->smem = 1024 + bytesA1 * MT * sa + ((bytesB * nB + 1023) & ~(size_t)1023) + 1024 + 512;
+    plan->smem = 1024 + bytesA1 * MT * sa + ((bytesB * nB + 1023) & ~(size_t)1023) + 1024 + 512 + pool_bytes;
     if (plan->smem > 227 * 1024) return AM_ERR_ARG;
     plan->grid = p.n_work < sm_count() ? p.n_work : sm_count();
     return AM_OK;
@@ -1267,15 +1327,16 @@ static int conv_prepare(const am_conv_desc* d, am_conv_plan* plan) {
 typedef void (*conv_kernel_t)(const ConvParams);
 static int conv_launch(const am_conv_plan* plan, void* stream) {
     // [fused epilogue][MT 1 / 2 / 4][streamed / resident weights], then the two CTA-pair kernels
-    static const conv_kernel_t kernels[14] = {
+    static const conv_kernel_t kernels[16] = {
         k_conv_gemm<1, false, false>, k_conv_gemm<1, true, false>, k_conv_gemm<2, false, false>, k_conv_gemm<2, true, false>,
         k_conv_gemm<4, false, false>, k_conv_gemm<4, true, false>,
         k_conv_gemm<1, false, true>, k_conv_gemm<1, true, true>, k_conv_gemm<2, false, true>, k_conv_gemm<2, true, true>,
         k_conv_gemm<4, false, true>, k_conv_gemm<4, true, true>,
-        k_conv_gemm_pair<false>, k_conv_gemm_pair<true>};
+        k_conv_gemm_pair<false>, k_conv_gemm_pair<true>,
+        k_conv_gemm<1, false, false, true>, k_conv_gemm<1, true, false, true>};
     static bool attr_set = false;
     if (!attr_set) {
-        for (int i = 0; i < 14; ++i) AM_CUDA(cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+        for (int i = 0; i < 16; ++i) AM_CUDA(cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
         attr_set = true;
     }
     const int fused = plan->p.epi_mode != AM_EPI_PLAIN ? 1 : 0;
@@ -1284,7 +1345,8 @@ static int conv_launch(const am_conv_plan* plan, void* stream) {
         AM_CUDA(cudaGetLastError());
         return AM_OK;
     }
-    const conv_kernel_t k = kernels[6 * fused + (plan->p.MT == 4 ? 4 : plan->p.MT == 2 ? 2 : 0) + (plan->p.residentB ? 1 : 0)];
+    const conv_kernel_t k = plan->p.pool2 ? kernels[14 + (plan->p.residentB ? 1 : 0)]
+                                          : kernels[6 * fused + (plan->p.MT == 4 ? 4 : plan->p.MT == 2 ? 2 : 0) + (plan->p.residentB ? 1 : 0)];
     k<<<plan->grid, CONV_THREADS, plan->smem, (cudaStream_t)stream>>>(plan->p);
     AM_CUDA(cudaGetLastError());
     return AM_OK;

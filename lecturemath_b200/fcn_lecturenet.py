@@ -525,10 +525,17 @@ class FCNPlan:
         d.Cout, d.Sy, d.Sx, d.act = nrows, Sy, S, act
         d.flags = 0 if MT is None else MT_FLAGS[MT]
         # MaxPool2d(2) fused into the epilogue where the 2x2 block of a pixel sits in four lanes of one warp (csrc/fcn_conv.cu epi_unit)
-        # ... and where the main loop is long enough to hide the extra epilogue work (K > 640: on the epilogue-bound conv_down_block_2
-        # the fused pool cost as much as the separate pass saved)
-        if (pool_dst is not None and f32_out is None and S == 1 and Sy == 1 and d.RT <= 16 and nrows % 16 == 0 and self.rowrun
-                and (cin_total * KHc * KW > 640 or self.ov.get("fused_pool") == "all") and not self.ov.get("no_fused_pool")):
+        fuse = False
+        if pool_dst is not None and f32_out is None and nrows % 16 == 0 and self.rowrun and not self.ov.get("no_fused_pool"):
+            if S == 1 and Sy == 1 and d.RT <= 16:
+                # (level 2, K = 432, is epilogue bound: the fused pool costs its conv 0.11 ms and saves a 0.15 ms pass; level 1 has K = 27 and
+                # never takes this branch with the tuned S = Sy = 2 packing)
+                fuse = cin_total * KHc * KW > 400 or self.ov.get("fused_pool") == "all"
+            elif S == 2 and Sy == 2 and MT == 1 and ntot == ntot_pad == NT and not self.ov.get("no_fused_pool2"):
+                # the 2x2 block of a pooled pixel is ONE GEMM row: parked in shared memory per 16-channel unit, reduced after a named
+                # barrier of the lane quarter's warps (csrc/fcn_conv.cu, kPOOL2) -- conv_down_block_1, whose separate pool pass re-read 1.5 GB
+                fuse = True
+        if fuse:
             d.pool_out, d.pool_H, d.pool_W = pool_dst.ptr, pool_dst.H, pool_dst.W
             d.pool_sx, d.pool_sy, d.pool_sn = pool_dst.C, pool_dst.Wp * pool_dst.C, pool_dst.H * pool_dst.Wp * pool_dst.C
             d.pool_padx = pool_dst.pad

@@ -101,11 +101,15 @@ def emulate_conv(d, mem):
                (ox[vx].view(1, 1, -1) + d.out_padx) * d.out_sx + d.out_coff + int(co[j]))
         vals = x[:, vy][:, :, vx][..., j]
         out[off.reshape(-1)] = vals.reshape(-1).to(out.dtype)
-    if d.pool_out:                                                         # fused MaxPool2d(2) of the bf16 output (Sx = Sy = 1)
-        assert d.Sx == 1 and d.Sy == 1 and d.RT <= 16
+    if d.pool_out:                                                         # fused MaxPool2d(2) of the bf16 output
         pout = mem[d.pool_out]
-        v = x[:, :d.pool_H * 2, :d.pool_W * 2, :d.Cout].to(torch.bfloat16).float()
-        v = v.reshape(B, d.pool_H, 2, d.pool_W, 2, d.Cout).amax(dim=(2, 4))
+        if d.Sx == 2 and d.Sy == 2:                                        # kPOOL2: the 2x2 block is the four column groups of one GEMM row
+            assert d.Ntot == 4 * d.Cout == d.NT
+            v = x[:, :d.pool_H, :d.pool_W, :d.Ntot].to(torch.bfloat16).float().reshape(B, d.pool_H, d.pool_W, 4, d.Cout).amax(dim=3)
+        else:
+            assert d.Sx == 1 and d.Sy == 1 and d.RT <= 16
+            v = x[:, :d.pool_H * 2, :d.pool_W * 2, :d.Cout].to(torch.bfloat16).float()
+            v = v.reshape(B, d.pool_H, 2, d.pool_W, 2, d.Cout).amax(dim=(2, 4))
         off = (torch.arange(B).view(B, 1, 1, 1) * d.pool_sn + torch.arange(d.pool_H).view(1, -1, 1, 1) * d.pool_sy +
                (torch.arange(d.pool_W).view(1, 1, -1, 1) + d.pool_padx) * d.pool_sx + torch.arange(d.Cout).view(1, 1, 1, -1))
         pout[off.reshape(-1)] = v.reshape(-1).to(pout.dtype)
