@@ -70,7 +70,14 @@ def main():
             ms = e0.elapsed_time(e1) / args.iters
             lib.am_conv_plan_destroy(hdl)
             del keep
-            rows.append((ms, S, Sy, NT, MT, "model %.3f ms" % (clk / 1.85e6)))
+            note = "model %.3f ms" % (clk / 1.85e6)
+            pool_dst = plan.specs[name].get("pool_dst")
+            if pool_dst is not None and not d.pool_out:            # this packing cannot pool in its epilogue: charge the separate pass
+                src = plan.specs[name]["dst"]                      # (k_maxpool2 runs at the HBM roofline: read the output, write a quarter)
+                extra = args.batch * (src.H * src.Wp * src.C + pool_dst.H * pool_dst.Wp * pool_dst.C) * 2 / 6.5e12 * 1e3
+                ms += extra
+                note += ", + %.3f ms separate max-pool pass" % extra
+            rows.append((ms, S, Sy, NT, MT, note))
         rows.sort(key=lambda r: r[0])
         base = [r for r in rows if tuple(r[1:5]) == chosen]
         best = rows[0]
