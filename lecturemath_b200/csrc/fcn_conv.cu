@@ -70,6 +70,7 @@ struct alignas(64) ConvParams {
     unsigned cout_magic;  // floor(2^32 / Cout) + 1 (Cout >= 2)
     void* pool_out; int pool_H, pool_W, pool_sx, pool_padx; long long pool_sn, pool_sy;   // fused MaxPool2d(2) destination (NULL = off)
     int pool2;            // fused MaxPool2d(2) with Sx = Sy = 2 packing: the 2x2 block of a pooled pixel is ONE GEMM row (see kPOOL2)
+    int poolx;            // fused MaxPool2d(2) with Sx even, Sy = 1: x pairs in two column units of one warp, y pairs in lanes l, l ^ RT (kPOOLX)
     int epi_per_q;        // epilogue warps per TMEM lane quarter that take part in this launch (<= compiled EPI_WARPS / 4)
     unsigned nrt_magic, nyt_magic, nnb_magic;   // floor(2^32 / d) + 1 for d = nRT, nYT, nNB (0 when d == 1): exact for n * d < 2^32
     const float* bias;
@@ -152,6 +153,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((unsigned long long)tm) : "memory");
 }
+// Programmatic dependent launch: a conv kernel launched with programmaticStreamSerialization may start its prologue (barrier init,
+// TMEM allocation, tensor-map prefetch, resident weights) while the tail of its predecessor still runs on other SMs; nothing the
+// predecessor wrote is read and nothing is written before pdl_wait() returns (= predecessor complete and flushed).  Both are no-ops
+// in a launch without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -334,10 +341,13 @@ __device__ __forceinline__ void epi_threshold(const ConvParams& p, const uint32_
 // Epilogue of one 16-column unit of one accumulator row: bias + activation + NHWC store.
 // With a fused max-pool (p.pool_out) EVERY lane of the warp calls this (row_ok only predicates the stores): the 2x2 block of an
 // output pixel sits in lanes l, l^1 (x) and l^RT (y), so the pooled value is two shuffle + max rounds on the packed bf16 pairs.
-template <bool kFUSED, bool kPOOL2 = false>
+// kPX (kPOOLX kernels: Sx even, Sy = 1): the two x neighbours of a pooled pixel are the same 16-channel slice of two column units that
+// one warp visits back to back -- kPX = 1 keeps the first unit's packed bf16 results in `carry`, kPX = 2 maxes them with the second
+// unit's, then with the row below (lane ^ RT) and stores the pooled pixel.
+template <bool kFUSED, bool kPOOL2 = false, int kPX = 0>
 __device__ __forceinline__ void epi_unit(const ConvParams& p, const uint32_t (&v)[16], const float* __restrict__ sbias, int n0, int j0,
                                          long long base, bool vec16, bool vec8, bool f32fast, bool sy1_ok, bool row_ok = true,
-                                         long long pbase = 0, bool pool_ok = false, uint4* spool = nullptr) {
+                                         long long pbase = 0, bool pool_ok = false, uint4* spool = nullptr, uint32_t* carry = nullptr) {
     if (kFUSED) {                                          // the instantiations the two fp32 layers are launched with
         if (p.epi_mode == AM_EPI_HEADS) epi_heads(p, v, sbias, n0, j0, base, pbase, sy1_ok);
         else epi_threshold(p, v, sbias, n0, j0, base, pbase, sy1_ok);
@@ -380,7 +390,28 @@ __device__ __forceinline__ void epi_unit(const ConvParams& p, const uint32_t (&v
                 *(uint4*)(o + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
             }
         }
-        if (kPOOL2) {                                      // this lane's 16 activated channels of one (sy, sx) group -> shared memory
+        if (kPX == 1) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) carry[i] = pk[i];
+        } else if (kPX == 2) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                __nv_bfloat162 m = __hmax2(*(const __nv_bfloat162*)&pk[i], *(const __nv_bfloat162*)&carry[i]);
+                const uint32_t t = __shfl_xor_sync(0xffffffffu, *(const uint32_t*)&m, p.RT);
+                m = __hmax2(m, *(const __nv_bfloat162*)&t);
+                pk[i] = *(const uint32_t*)&m;
+            }
+            if (pool_ok) {                                 // even rows: pooled pixel (y / 2, Sx / 2 * r + sx / 2)
+                __nv_bfloat16* po = (__nv_bfloat16*)p.pool_out + pbase + (long long)(sx >> 1) * p.pool_sx + co;
+                if ((((uintptr_t)po) & 31) == 0) {
+                    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(po), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]),
+                                 "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
+                } else {
+                    *(uint4*)po = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    *(uint4*)(po + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                }
+            }
+        } else if (kPOOL2) {                               // this lane's 16 activated channels of one (sy, sx) group -> shared memory
             spool[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             spool[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
         } else if (p.pool_out != nullptr) {                // warp-uniform
@@ -494,7 +525,7 @@ __device__ __forceinline__ int sched_next(uint32_t schedFull, uint32_t schedEmpt
 // quarter (same lane).  Every warp parks its packed bf16 results in shared memory (32 B per unit and lane), the quarter's warps meet at
 // a named barrier, then each warp takes channel slices h, h + epiPerQ, ..., maxes the four groups and stores the pooled pixel: the
 // 1.5 GB re-read of the separate k_maxpool2 pass disappears for ~5 % more epilogue instructions.
-template <int kMT, bool kRES, bool kFUSED, bool kPOOL2 = false>
+template <int kMT, bool kRES, bool kFUSED, bool kPOOL2 = false, bool kPOOLX = false>
 __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv_gemm(const __grid_constant__ ConvParams p) {
     constexpr int kEpiFirst = (kMT == 4) ? 8 : 4;                      // first epilogue warp (multiple of 4: TMEM lane quarters)
     constexpr int kEpiWarps = (CONV_THREADS / 32) - kEpiFirst;
@@ -542,17 +573,20 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv_gemm(const __grid_cons
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    pdl_launch_dependents();                      // the next conv launch may stage its prologue as soon as SMs free up
+    if (warp != 0) pdl_wait();
 
     if (warp == 0) {
         // ===================== TMA producer (warp-uniform, elected lane issues) =====================
         int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
         if (kRES) {                               // all weight tiles once (single N block): fullB[0] collects them
-            if (elect_one()) {
+            if (elect_one()) {                    // (weights are constants: loaded before the predecessor's results are waited for)
                 mbar_expect_tx(fullB, bytesB * nB);
                 for (uint32_t i = 0; i < nB; ++i) tma_load_2d(sB0 + bytesB * i, &p.tmB, fullB, 0, (int)i * p.Ntot_pad);
             }
             __syncwarp();
         }
+        pdl_wait();
         int slot = 0; uint32_t ps = 0;
         int w_next = sched_fetch(p.work_counter, lane);
         while (true) {
@@ -677,6 +711,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv_gemm(const __grid_cons
         const bool f32fast = p.out_f32 && p.out_sx == p.Cout && (p.Sy == 1 || ((p.Sx * p.Cout) & 15) == 0) && p.out_coff == 0 &&
                              ((p.Ntot | (int)p.out_sy | (int)p.out_sn) & 3) == 0;
         int slot = 0; uint32_t ps = 0;
+        int tile_no = 0;                                 // kPOOLX: rotates the unit-pair assignment
         while (true) {
             const int w = sched_next(schedFull, schedEmpty, sched_w, slot, ps, lane);
             if (w < 0) break;
@@ -713,7 +748,11 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv_gemm(const __grid_cons
                     const TileCoord tc = decode_tile(p, st * kMT + mt);
                     const int y = tc.y0 + yy, r = tc.r0 + rr;
                     row_ok = tc.valid && (y < p.Hin) && (r < p.nR);
-                    if (kPOOL2) {                            // Sx = Sy = 2: GEMM row (y, r) IS the pooled pixel
+                    if (kPOOLX) {                            // Sx even, Sy = 1: GEMM row (y, r) holds Sx / 2 pooled pixels of pooled row y / 2
+                        pool_ok = tc.valid && !(y & 1) && (y >> 1) < p.pool_H && r < p.nR;
+                        pbase = (long long)tc.frame * p.pool_sn + (long long)(y >> 1) * p.pool_sy +
+                                (long long)((p.Sx >> 1) * r + p.pool_padx) * p.pool_sx;
+                    } else if (kPOOL2) {                     // Sx = Sy = 2: GEMM row (y, r) IS the pooled pixel
                         pool_ok = tc.valid && y < p.pool_H && r < p.pool_W;
                         pbase = (long long)tc.frame * p.pool_sn + (long long)y * p.pool_sy + (long long)(r + p.pool_padx) * p.pool_sx;
                     } else if (p.pool_out != nullptr) {      // Sx = Sy = 1: (y, r) is the output pixel; even lanes of even rows write the pooled pixel
@@ -729,6 +768,34 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv_gemm(const __grid_cons
             };
             uint4* spool_q = (uint4*)(smem_raw + (sPool - smem_u32(smem_raw))) + (size_t)q * units_per_tile * 64;     // 2 x uint4 per lane
             auto spool_of = [&](int g) -> uint4* { return kPOOL2 ? spool_q + ((size_t)g * 32 + lane) * 2 : nullptr; };
+            if (kPOOLX) {
+                // kMT = 1, one N block of Sx x Cout columns: unit (sx, slice) = sx * cpu + slice.  A warp takes PAIRS of units, the same
+                // slice of pixels 2 sxp and 2 sxp + 1, back to back (same ping-pong of the two register sets); the pair -> warp assignment
+                // rotates from tile to tile so that an uneven pair count (6 pairs on 4 warps) evens out over the two accumulator stages.
+                const int cpu = p.Cout >> 4, npairs = units_per_tile >> 1;
+                int hr = h + ((tile_no & 1) ? (epiPerQ >> 1) : 0);
+                if (hr >= epiPerQ) hr -= epiPerQ;
+                ++tile_no;
+                auto first_of = [&](int pi) -> int {         // first unit of pair pi = (sxp, slice): pixel 2 sxp
+                    const int sxp = (int)__umulhi((unsigned)(pi << 4), p.cout_magic);
+                    return (2 * sxp) * cpu + (pi - sxp * cpu);
+                };
+                uint32_t carry[8];
+                int pi = hr;
+                int gA = pi < npairs ? first_of(pi) : 0;
+                if (pi < npairs) tmem_ld16_async(unit_addr(gA), va);
+                while (pi < npairs) {
+                    tmem_wait16(va);
+                    tmem_ld16_async(unit_addr(gA + cpu), vb);
+                    { const int j0 = enter(gA); epi_unit<kFUSED, false, 1>(p, va, sbias, n0, j0, base, vec16, vec8, f32fast, sy1_ok, row_ok, pbase, pool_ok, nullptr, carry); }
+                    const int pn = pi + epiPerQ;
+                    const int gN = pn < npairs ? first_of(pn) : 0;
+                    tmem_wait16(vb);
+                    if (pn < npairs) tmem_ld16_async(unit_addr(gN), va);
+                    { const int j0 = enter(gA + cpu); epi_unit<kFUSED, false, 2>(p, vb, sbias, n0, j0, base, vec16, vec8, f32fast, sy1_ok, row_ok, pbase, pool_ok, nullptr, carry); }
+                    pi = pn; gA = gN;
+                }
+            } else {
             int g = h;
             if (g < units) tmem_ld16_async(unit_addr(g), va);
             while (g < units) {
@@ -743,6 +810,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv_gemm(const __grid_cons
                 if (g2 < units) tmem_ld16_async(unit_addr(g2), va);
                 { const int j0 = enter(g); if (row_ok || p.pool_out != nullptr) epi_unit<kFUSED, kPOOL2>(p, vb, sbias, n0, j0, base, vec16, vec8, f32fast, sy1_ok, row_ok, pbase, pool_ok, spool_of(g)); }
                 g = g2;
+            }
             }
             // all tcgen05.ld of this stage have completed (tmem_wait16 in the last iteration): hand the stage back
             tc_fence_before();
@@ -883,6 +951,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) k_c
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    pdl_launch_dependents();
+    pdl_wait();
 
     if (warp == 0) {
         // ===================== TMA producer: own A tiles, own half of every weight tile; completes on the leader =====================
@@ -1200,7 +1270,7 @@ static int conv_prepare(const am_conv_desc* d, am_conv_plan* plan) {
     p.Cout = d->Cout; p.Sy = d->Sy; p.Sx = d->Sx; p.Ntot = d->Ntot; p.act = d->act; p.bias = d->bias;
     p.pool_out = d->pool_out; p.pool_H = d->pool_H; p.pool_W = d->pool_W; p.pool_sn = d->pool_sn; p.pool_sy = d->pool_sy;
     p.pool_sx = d->pool_sx; p.pool_padx = d->pool_padx;
-    p.pool2 = 0;
+    p.pool2 = 0; p.poolx = 0;
     if (d->pool_out && d->Sx == 2 && d->Sy == 2) {        // the 2x2 block of a pooled pixel is one GEMM row (kPOOL2)
         const bool vec16 = (d->Cout & 15) == 0 && !d->out_f32 && ((d->out_coff | d->out_sx | (int)(d->out_sy & 7) | (int)(d->out_sn & 7)) & 7) == 0;
         if (ystep != 2 || !vec16 || d->Ntot != 4 * d->Cout || d->Ntot_pad != d->NT || d->NT != d->Ntot || (d->pool_sx & 7) || (d->pool_sy & 7) ||
@@ -1209,6 +1279,16 @@ static int conv_prepare(const am_conv_desc* d, am_conv_plan* plan) {
             return AM_ERR_ARG;
         }
         p.pool2 = 1;
+    } else if (d->pool_out && d->Sx >= 2 && d->Sy == 1) { // x neighbours in two column units, y neighbours in two lanes (kPOOLX)
+        const bool vec16 = (d->Cout & 15) == 0 && !d->out_f32 && ((d->out_coff | d->out_sx | (int)(d->out_sy & 7) | (int)(d->out_sn & 7)) & 7) == 0;
+        if ((d->Sx & 1) || d->RT > 16 || (d->YT & 1) || !vec16 || d->Ntot != d->Sx * d->Cout || d->Ntot_pad != d->NT || d->NT != d->Ntot ||
+            (d->pool_sx & 7) || (d->pool_sy & 7) || (d->pool_sn & 7) || d->pool_H != d->out_H / 2 || d->pool_W != d->out_W / 2 ||
+            d->pool_W * 2 != d->Sx * d->nR || pair || (d->flags & (AM_CONV_FORCE_MT2 | AM_CONV_FORCE_MT4))) {
+            fprintf(stderr, "[accessmath_b200] am_conv: fused max-pool with Sx > 1 needs even Sx, Sy = 1, RT <= 16, one N block of Sx x Cout columns, "
+                            "Cout %% 16 == 0, one M-tile per item\n");
+            return AM_ERR_ARG;
+        }
+        p.poolx = 1;
     } else if (d->pool_out) {            // the fused pool rides on the single-address 16-channel epilogue path
         const bool vec16 = (d->Cout & 15) == 0 && !d->out_f32 && ((d->out_coff | d->out_sx | (int)(d->out_sy & 7) | (int)(d->out_sn & 7)) & 7) == 0;
         if (d->Sx != 1 || d->Sy != 1 || d->RT > 16 || !vec16 || d->Ntot != d->Cout || (d->pool_sx & 15) || (d->pool_sy & 15) || (d->pool_sn & 15) ||
@@ -1288,7 +1368,7 @@ static int conv_prepare(const am_conv_desc* d, am_conv_plan* plan) {
     const bool res1 = can_res && fixed + allB + (p.pool2 ? 2 : 3) * bytesA1 <= budget;
     int resident, MT;
     const bool res4 = can_res && fixed + allB + 2 * 4 * bytesA1 <= budget;
-    if (p.pool2) { MT = 1; resident = res1 ? 1 : 0; }
+    if (p.pool2 || p.poolx) { MT = 1; resident = res1 ? 1 : 0; }
     else if ((d->flags & AM_CONV_FORCE_MT4) && 4 * p.NTc <= 512) { MT = 4; resident = res4 ? 1 : 0; }  // the planner decided
     else if ((d->flags & AM_CONV_FORCE_MT2) && tmem2) { MT = 2; resident = res2 ? 1 : 0; }
     else if (d->flags & AM_CONV_NO_MT2) { MT = 1; resident = res1 ? 1 : 0; }
@@ -1327,28 +1407,34 @@ static int conv_prepare(const am_conv_desc* d, am_conv_plan* plan) {
 typedef void (*conv_kernel_t)(const ConvParams);
 static int conv_launch(const am_conv_plan* plan, void* stream) {
     // [fused epilogue][MT 1 / 2 / 4][streamed / resident weights], then the two CTA-pair kernels
-    static const conv_kernel_t kernels[16] = {
+    static const conv_kernel_t kernels[18] = {
         k_conv_gemm<1, false, false>, k_conv_gemm<1, true, false>, k_conv_gemm<2, false, false>, k_conv_gemm<2, true, false>,
         k_conv_gemm<4, false, false>, k_conv_gemm<4, true, false>,
         k_conv_gemm<1, false, true>, k_conv_gemm<1, true, true>, k_conv_gemm<2, false, true>, k_conv_gemm<2, true, true>,
         k_conv_gemm<4, false, true>, k_conv_gemm<4, true, true>,
         k_conv_gemm_pair<false>, k_conv_gemm_pair<true>,
-        k_conv_gemm<1, false, false, true>, k_conv_gemm<1, true, false, true>};
+        k_conv_gemm<1, false, false, true>, k_conv_gemm<1, true, false, true>,
+        k_conv_gemm<1, false, false, false, true>, k_conv_gemm<1, true, false, false, true>};
     static bool attr_set = false;
     if (!attr_set) {
-        for (int i = 0; i < 16; ++i) AM_CUDA(cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+        for (int i = 0; i < 18; ++i) AM_CUDA(cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
         attr_set = true;
     }
     const int fused = plan->p.epi_mode != AM_EPI_PLAIN ? 1 : 0;
-    if (plan->pair) {
-        kernels[12 + fused]<<<plan->grid, CONV_THREADS, plan->smem, (cudaStream_t)stream>>>(plan->p);      // __cluster_dims__(2,1,1)
-        AM_CUDA(cudaGetLastError());
-        return AM_OK;
-    }
-    const conv_kernel_t k = plan->p.pool2 ? kernels[14 + (plan->p.residentB ? 1 : 0)]
+    const conv_kernel_t k = plan->pair ? kernels[12 + fused]                                               // __cluster_dims__(2,1,1)
+                          : plan->p.pool2 ? kernels[14 + (plan->p.residentB ? 1 : 0)]
+                          : plan->p.poolx ? kernels[16 + (plan->p.residentB ? 1 : 0)]
                                           : kernels[6 * fused + (plan->p.MT == 4 ? 4 : plan->p.MT == 2 ? 2 : 0) + (plan->p.residentB ? 1 : 0)];
-    k<<<plan->grid, CONV_THREADS, plan->smem, (cudaStream_t)stream>>>(plan->p);
-    AM_CUDA(cudaGetLastError());
+    // programmatic dependent launch, see pdl_wait().  Opt-in (AM_B200_PDL=1): measured on a B200 it does not pay -- 9.60 ms per step with it
+    // against 9.43-9.53 without (profile r02_z): the persistent CTAs own every SM until they exit, so only the ~3 us prologue can overlap.
+    static const int use_pdl = [] { const char* e = getenv("AM_B200_PDL"); return (e && e[0] == '1') ? 1 : 0; }();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(plan->grid); cfg.blockDim = dim3(CONV_THREADS); cfg.dynamicSmemBytes = plan->smem; cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = use_pdl ? 1 : 0;
+    AM_CUDA(cudaLaunchKernelEx(&cfg, k, plan->p));
     return AM_OK;
 }
 

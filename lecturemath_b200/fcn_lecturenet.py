@@ -160,7 +160,7 @@ def pack_weights(w, bias, segs, S, rowrun, NT, Sy=1):
     return packed, b, ntot, ntot_pad
 
 
-TUNED_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tuned_plans.json")
+TUNED_PATH = os.environ.get("AM_B200_TUNED") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "tuned_plans.json")  # env: tuning A/B only
 _TUNED = None
 
 
@@ -534,6 +534,10 @@ class FCNPlan:
             elif S == 2 and Sy == 2 and MT == 1 and ntot == ntot_pad == NT and not self.ov.get("no_fused_pool2"):
                 # the 2x2 block of a pooled pixel is ONE GEMM row: parked in shared memory per 16-channel unit, reduced after a named
                 # barrier of the lane quarter's warps (csrc/fcn_conv.cu, kPOOL2) -- conv_down_block_1, whose separate pool pass re-read 1.5 GB
+                fuse = True
+            elif S >= 2 and S % 2 == 0 and Sy == 1 and MT == 1 and d.RT <= 16 and ntot == ntot_pad == NT and not self.ov.get("no_fused_poolx"):
+                # x neighbours = the same 16-channel slice of two column units, which one epilogue warp visits back to back (first unit kept
+                # in registers); y neighbours = lanes l, l ^ RT: no shared memory, no barrier (csrc/fcn_conv.cu, kPOOLX)
                 fuse = True
         if fuse:
             d.pool_out, d.pool_H, d.pool_W = pool_dst.ptr, pool_dst.H, pool_dst.W

@@ -106,6 +106,10 @@ def emulate_conv(d, mem):
         if d.Sx == 2 and d.Sy == 2:                                        # kPOOL2: the 2x2 block is the four column groups of one GEMM row
             assert d.Ntot == 4 * d.Cout == d.NT
             v = x[:, :d.pool_H, :d.pool_W, :d.Ntot].to(torch.bfloat16).float().reshape(B, d.pool_H, d.pool_W, 4, d.Cout).amax(dim=3)
+        elif d.Sx >= 2:                                                    # kPOOLX: x pairs in column units, y pairs in GEMM rows
+            assert d.Sx % 2 == 0 and d.Sy == 1 and d.RT <= 16 and d.Ntot == d.Sx * d.Cout == d.NT
+            v = x[..., :d.Ntot].to(torch.bfloat16).float().reshape(B, Hin, nR * d.Sx, d.Cout)[:, :d.pool_H * 2, :d.pool_W * 2]
+            v = v.reshape(B, d.pool_H, 2, d.pool_W, 2, d.Cout).amax(dim=(2, 4))
         else:
             assert d.Sx == 1 and d.Sy == 1 and d.RT <= 16
             v = x[:, :d.pool_H * 2, :d.pool_W * 2, :d.Cout].to(torch.bfloat16).float()

@@ -30,21 +30,27 @@ def _check_mask(ink, ink_ref, p_ref):
 
 
 @pytest.mark.parametrize("tag", ["tiny", "full"])
-@pytest.mark.parametrize("mode", ["rowrun", "kx", "sy2", "mt1", "mt2", "mt4", "mt22", "poolall", "nopool"])
+@pytest.mark.parametrize("mode", ["rowrun", "kx", "sy2", "mt1", "mt2", "mt4", "mt22", "poolall", "nopool", "poolx"])
 def test_forward_vs_reference_golden(golden, tag, mode):
     """mode: rowrun = planner's choice, kx = one TMA load per horizontal tap, sy2 = 2-D (row-pair) packing forced,
     mtN = N M-tiles per work item (N MMA issuer warps) forced wherever TMEM / shared memory allow; mt22 = CTA pairs
     (cta_group::2 clusters, M = 256 MMAs); poolall / nopool = MaxPool2d fused into the epilogue of every eligible encoder conv /
-    of none (the planner's default fuses it where K > 640)."""
+    of none (the planner's default fuses it where K > 640); poolx = conv_down_block_1 / 2 forced into Sx = 4 / 2, Sy = 1 packings whose
+    pool is fused through the unit-pair epilogue (kPOOLX)."""
     z = golden("fcn_forward.npz")
     net = golden_net(tag, z).cuda()
     net.rowrun = mode != "kx"
     net.plan_overrides = {"sy": 2} if mode == "sy2" else ({"mt": int(mode[2:])} if mode.startswith("mt") else None)
     if mode in ("poolall", "nopool"):
         net.plan_overrides = {"fused_pool": "all"} if mode == "poolall" else {"no_fused_pool": True}
+    if mode == "poolx":
+        from tests.test_fcn_host_logic import poolx_overrides
+        net.plan_overrides = poolx_overrides(net)
     frame = z["frame_bgr"]
     plan = net.binarize_frames(frame[None], want_others=True)
     torch.cuda.synchronize()
+    if mode == "poolx":
+        assert sum(1 for k, d in plan.ops if k == "conv" and d.pool_out and d.Sx >= 2 and d.Sy == 1) == 2
     n_pool_ops = sum(1 for k, _ in plan.ops if k == "pool")
     n_fused = sum(1 for k, d in plan.ops if k == "conv" and d.pool_out)
     assert n_pool_ops + n_fused == 5

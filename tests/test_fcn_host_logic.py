@@ -45,16 +45,27 @@ def test_seeded_init_reproduces_reference_weights(golden):
         np.testing.assert_array_equal(v.numpy(), z["tiny_sd/" + k])
 
 
-@pytest.mark.parametrize("mode", ["rowrun", "kx", "sy2"])
+def poolx_overrides(net):
+    """Forces conv_down_block_1 / 2 into Sx = 4 / 2, Sy = 1 packings with one M-tile per item: the max-pool is fused through the
+    unit-pair epilogue (csrc/fcn_conv.cu kPOOLX)."""
+    sd = net.state_dict()
+    c1, c2 = sd["conv_down_block_1.0.weight"].shape[0], sd["conv_down_block_2.0.weight"].shape[0]
+    return {"cfg": {"conv_down_block_1": (4, 1, 4 * c1, 1), "conv_down_block_2": (2, 1, 2 * c2, 1)}}
+
+
+@pytest.mark.parametrize("mode", ["rowrun", "kx", "sy2", "poolx"])
 def test_emulated_kernel_plan_matches_reference_logits(golden, mode):
-    """mode: rowrun = planner's choice, kx = one TMA load per horizontal tap, sy2 = 2-D (row-pair) packing forced."""
+    """mode: rowrun = planner's choice, kx = one TMA load per horizontal tap, sy2 = 2-D (row-pair) packing forced,
+    poolx = Sx-packed encoder convs with the max-pool fused."""
     z = golden("fcn_forward.npz")
     net = golden_net("tiny", z)
     frame = z["frame_bgr"]
     plan = FCNPlan(net.params, 1, frame.shape[0], frame.shape[1], torch.device("cpu"), rowrun=(mode != "kx"),
-                   overrides={"sy": 2} if mode == "sy2" else None)
+                   overrides={"sy": 2} if mode == "sy2" else (poolx_overrides(net) if mode == "poolx" else None))
     if mode == "sy2":
         assert sum(1 for k, d in plan.ops if k == "conv" and d.in_ystep == 2) >= 10
+    if mode == "poolx":
+        assert sum(1 for k, d in plan.ops if k == "conv" and d.pool_out and d.Sx >= 2 and d.Sy == 1) == 2
     logits, text, rec, ink = emulate_plan(plan, frame[None])
     # bf16 activations/weights with fp32 accumulation: stated tolerance 1e-2 on probabilities (BASELINE north_star)
     p, p_ref = torch.sigmoid(logits[0]).numpy(), 1 / (1 + np.exp(-z["tiny_logit"]))
