@@ -338,6 +338,7 @@ class FCNPlan:
         self.rec = torch.zeros((B, H, W, 3), dtype=torch.float32, device=device)
         self.wpr = self.lib.am_words_per_row(W)
         self.bits = torch.zeros((B, H, self.wpr), dtype=torch.int32, device=device)
+        self._borders_filled = False
         self._cplans = {}       # op index -> am_conv_plan handle
         self.keep = []          # keeps packed weights alive
         self.ops = []           # (kind, payload)
@@ -667,7 +668,9 @@ class FCNPlan:
 
     @property
     def launches_per_run(self):
-        return 1 + len(self.ops)
+        """Kernel launches of the NEXT run(): the border fills (constants, outside what the transposed convs write) only run once."""
+        n_border = sum(1 for k, _ in self.ops if k == "border")
+        return 1 + len(self.ops) - (n_border if self._borders_filled else 0)
 
     def run(self, stream, want_others=False, threshold=128, timing=None, frames=None, want_logits=True):
         """frames (uint8 BGR [B][H][W][3] device tensor; default self.frames) -> self.logits / self.bits (and text_logit /
@@ -705,10 +708,13 @@ class FCNPlan:
                 src, dst = a
                 chk(lib.am_fcn_maxpool2(src.ptr, B, src.H, src.W, src.C, src.pad, dst.ptr, dst.pad, st), "am_fcn_maxpool2")
             elif kind == "border":
+                if self._borders_filled:                 # gelu(bias) constants in the rows / columns no conv launch writes: filled by the first run
+                    continue
                 dst, yf, xf, vals = a
                 chk(lib.am_fcn_fill_border(dst.ptr, B, dst.H, dst.W, dst.C, dst.pad, yf, xf, vals.data_ptr(), st), "am_fcn_fill_border")
             elif kind == "threshold":
                 chk(lib.am_fcn_threshold_pack(self.logits.data_ptr(), B, H, W, int(threshold), self.bits.data_ptr(), st), "am_fcn_threshold_pack")
+        self._borders_filled = True
 
 
 # ----------------------------------------------------------------------------------------------------
