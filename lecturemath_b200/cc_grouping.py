@@ -75,6 +75,37 @@ def overlap_pairs(view, d_ids, n, timed=None):
         return pairs[:cnt.value].cpu().numpy().astype(np.int64)
 
 
+def frame_segment_items(groups_per_frame, group_ages, seg_index, n_groups):
+    """int32 [n][2] = (frame, segment row) of every group alive in every frame, in (frame, list position) order.  Segment s of group g
+    at frame t = the first s with marks[s + 1] >= t (the reference advances a per-group cursor frame by frame, :655-660); found for
+    all pairs at once in the concatenated, (g, mark)-sorted age marks.  seg_index: {(g, s): row}, rows of one group consecutive."""
+    import itertools
+    alive = np.fromiter((len(p) for p in groups_per_frame), dtype=np.int64, count=len(groups_per_frame))
+    n_items = int(alive.sum())
+    items = np.zeros((n_items, 2), dtype=np.int32)
+    if not n_items:
+        return items
+    g_of = np.fromiter(itertools.chain.from_iterable(groups_per_frame), dtype=np.int64, count=n_items)
+    t_of = np.repeat(np.arange(len(groups_per_frame), dtype=np.int64), alive)
+    gs = sorted(set(g_of.tolist()))
+    n_marks = np.zeros(n_groups, dtype=np.int64)
+    n_marks[gs] = [len(group_ages[g]) for g in gs]
+    m_start = np.cumsum(n_marks) - n_marks
+    marks = np.fromiter(itertools.chain.from_iterable(group_ages[g] for g in gs), dtype=np.int64, count=int(n_marks.sum()))
+    big = int(max(int(marks.max()), len(groups_per_frame))) + 2
+    keys = np.repeat(np.array(gs, dtype=np.int64), n_marks[gs]) * big + marks
+    j = np.searchsorted(keys, g_of * big + t_of, side="left") - m_start[g_of]      # first mark >= t inside the group's marks
+    seg = np.maximum(j - 1, 0)
+    if int((seg + 1 >= n_marks[g_of]).sum()):
+        raise IndexError("a frame lies beyond the last age mark of one of its groups")     # the reference's cursor would overrun too
+    base = np.full(n_groups, -1, dtype=np.int64)
+    for (g, s0), row in seg_index.items():
+        if s0 == 0:
+            base[g] = row
+    items[:, 0], items[:, 1] = t_of, base[g_of] + seg
+    return items
+
+
 class GroupingMixin:
     def _timed(self, name, fn, *args):
         """Run one C-ABI call; when self.device_ms is a dict (tools/grouping_bench.py) accumulate its CUDA-event time there."""
@@ -264,14 +295,29 @@ class GroupingMixin:
     # ---- :415-444 ---------------------------------------------------------------------------------------------
     def compute_groups_temporal_information(self, cc_groups):
         n_frames = len(self.cc_idx_per_frame)
-        ages, per_frame = {}, [[] for _ in range(n_frames)]
+        uframes = self.unique_cc_frames                                # (the property guards the lazy host view: read it once)
+        ages, gids, first, stop = {}, [], [], []
         for g, grp in enumerate(cc_groups):
             if not grp:
                 continue
-            marks = sorted({self.unique_cc_frames[u][0][0] for u in grp} | {self.unique_cc_frames[u][-1][0] for u in grp})
+            marks = set()
+            for u in grp:
+                fr = uframes[u]
+                marks.add(fr[0][0]); marks.add(fr[-1][0])
+            marks = sorted(marks)
             ages[g] = marks
-            for t in range(marks[0], min(marks[-1] + 1, n_frames)):
-                per_frame[t].append(g)
+            gids.append(g); first.append(marks[0]); stop.append(min(marks[-1] + 1, n_frames))
+        # per_frame[t] = groups alive at t, ascending (the reference appends g to every frame of its span, group by group)
+        per_frame = [[] for _ in range(n_frames)]
+        if gids:
+            first, span = np.array(first, dtype=np.int64), np.maximum(np.array(stop, dtype=np.int64) - np.array(first, dtype=np.int64), 0)
+            total = int(span.sum())
+            if total:
+                g_rep = np.repeat(np.array(gids, dtype=np.int64), span)
+                t_rep = np.repeat(first, span) + (np.arange(total) - np.repeat(np.cumsum(span) - span, span))
+                order = np.argsort(t_rep, kind="stable")               # stable: ascending g inside every frame
+                cuts = np.cumsum(np.bincount(t_rep, minlength=n_frames))[:-1]
+                per_frame = [part.tolist() for part in np.split(g_rep[order], cuts)]
         return ages, per_frame
 
     # ---- :446-500 ---------------------------------------------------------------------------------------------
@@ -328,21 +374,37 @@ class GroupingMixin:
         lib = _lib.lib()
         view, obj_index = self._unique_view()
         bounds, seg_rows, members, seg_key = {}, [], [], []
+        objs, uframes, rows_of = self.unique_cc_objects, self.unique_cc_frames, obj_index.tolist()    # (lazy-view properties: read once)
+        b_left, b_right = bisect.bisect_left, bisect.bisect_right
         for g, grp in enumerate(cc_groups):
             if not grp:
                 continue
-            ccs = [self.unique_cc_objects[u] for u in grp]
-            box = (min(c.min_x for c in ccs), max(c.max_x for c in ccs), min(c.min_y for c in ccs), max(c.max_y for c in ccs))
-            bounds[g] = box
-            times = [[t for t, _ in self.unique_cc_frames[u]] for u in grp]  # ascending frame indices
+            c = objs[grp[0]]
+            x0, x1, y0, y1 = c.min_x, c.max_x, c.min_y, c.max_y
+            for u in grp[1:]:
+                c = objs[u]
+                if c.min_x < x0: x0 = c.min_x
+                if c.max_x > x1: x1 = c.max_x
+                if c.min_y < y0: y0 = c.min_y
+                if c.max_y > y1: y1 = c.max_y
+            bounds[g] = (x0, x1, y0, y1)
+            box = (int(x0), int(x1), int(y0), int(y1))
             marks = group_ages[g]
+            if len(grp) == 1 and len(marks) == 2:                            # one CC, one segment that spans all of its frames
+                fr = uframes[grp[0]]
+                if marks[0] <= fr[0][0] and fr[-1][0] <= marks[1]:
+                    members.append((rows_of[grp[0]], len(fr)))
+                    seg_rows.append(box + (len(members) - 1, len(members)))
+                    seg_key.append((g, 0))
+                    continue
+            times = [[t for t, _ in uframes[u]] for u in grp]                # ascending frame indices
             for s, (t0, t1) in enumerate(zip(marks[:-1], marks[1:])):
                 begin = len(members)
                 for u, ts in zip(grp, times):
-                    seen = bisect.bisect_right(ts, t1) - bisect.bisect_left(ts, t0)      # frames of u inside [t0, t1] (:607)
+                    seen = b_right(ts, t1) - b_left(ts, t0)                  # frames of u inside [t0, t1] (:607)
                     if seen:
-                        members.append((int(obj_index[u]), seen))
-                seg_rows.append(tuple(int(v) for v in box) + (begin, len(members)))
+                        members.append((rows_of[u], seen))
+                seg_rows.append(box + (begin, len(members)))
                 seg_key.append((g, s))
         images = {g: [] for g in bounds}
         self._group_device = None
@@ -358,12 +420,13 @@ class GroupingMixin:
         # one unpack for all segments (format conversion only: bit-packed -> the reference's uint8 0/255 arrays)
         px = np.unpackbits(d_out[:int(offs[-1])].cpu().numpy().view(np.uint8), bitorder="little")
         px *= np.uint8(255)
-        cws = ((seg[:, 1] >> 5) - (seg[:, 0] >> 5) + 1) * 32
-        lead = seg[:, 0] & 31
+        cws = (((seg[:, 1] >> 5) - (seg[:, 0] >> 5) + 1) * 32).tolist()
+        lead, width = (seg[:, 0] & 31).tolist(), (seg[:, 1] - seg[:, 0] + 1).tolist()
+        bit0 = (offs.astype(np.int64) * 32).tolist()
+        contiguous = np.ascontiguousarray
         for i, (g, s) in enumerate(seg_key):
-            a, b = int(offs[i]) * 32, int(offs[i + 1]) * 32
-            x0 = int(lead[i])
-            images[g].append(np.ascontiguousarray(px[a:b].reshape(-1, int(cws[i]))[:, x0:x0 + int(seg[i, 1] - seg[i, 0]) + 1]))
+            x0 = lead[i]
+            images[g].append(contiguous(px[bit0[i]:bit0[i + 1]].reshape(-1, cws[i])[:, x0:x0 + width[i]]))
         # kept on the device for frames_from_groups: segment boxes, word offsets, bit-packed images
         self._group_device = ({k: i for i, k in enumerate(seg_key)}, _dev(seg[:, :4], np.int32), d_off, d_out)
         return images, bounds
@@ -381,15 +444,7 @@ class GroupingMixin:
         if dev is None:
             dev = self._upload_group_images(group_images, group_boundaries)
         seg_index, d_boxes, d_off, d_imgs = dev
-        seg_of = [0] * len(cc_groups)
-        items = []                                                           # (frame, segment row)
-        for t, present in enumerate(groups_per_frame):
-            for g in present:
-                marks = group_ages[g]
-                while marks[seg_of[g] + 1] < t:
-                    seg_of[g] += 1
-                items.append((t, seg_index[(g, seg_of[g])]))
-        items = np.array(items, dtype=np.int32).reshape(-1, 2)
+        items = frame_segment_items(groups_per_frame, group_ages, seg_index, len(cc_groups))
         clean, n_frames = [], len(groups_per_frame)
         from .wire import PngEncoder
         chunk = min(chunk, max(n_frames, 1))

@@ -78,3 +78,30 @@ def test_pixel_methods_fail_loudly_without_a_device():
         host.rebuilt_binary_images()
     with pytest.raises(_lib.AccessMathB200Error):
         host.compute_group_images([[0]], {0: [0, 2]}, 0.5)
+
+
+def test_frame_segment_items_equals_the_reference_cursor():
+    """frames_from_groups picks, per frame and alive group, the age segment the reference's per-group cursor stands on
+    (cc_stability_estimator.py:655-660); the drop-in finds all of them with one searchsorted -- same rows, same order."""
+    import random
+    from lecturemath_b200.cc_grouping import frame_segment_items
+    rng = random.Random(7)
+    for _ in range(150):
+        n_frames, n_groups = rng.randint(1, 40), rng.randint(1, 30)
+        ages, per_frame, seg_index = {}, [[] for _ in range(n_frames)], {}
+        for g in range(n_groups):
+            marks = sorted(rng.sample(range(n_frames + 5), min(rng.randint(2, 6), n_frames + 5)))
+            if rng.random() < 0.2 or len(marks) < 2:
+                continue
+            ages[g] = marks
+            for s in range(len(marks) - 1):
+                seg_index[(g, s)] = len(seg_index)
+            for t in range(marks[0], min(marks[-1] + 1, n_frames)):
+                per_frame[t].append(g)
+        cursor, want = [0] * n_groups, []
+        for t, present in enumerate(per_frame):
+            for g in present:
+                while ages[g][cursor[g] + 1] < t:
+                    cursor[g] += 1
+                want.append((t, seg_index[(g, cursor[g])]))
+        np.testing.assert_array_equal(frame_segment_items(per_frame, ages, seg_index, n_groups), np.array(want, dtype=np.int32).reshape(-1, 2))
