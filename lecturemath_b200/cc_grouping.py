@@ -10,6 +10,8 @@ order-dependent list / dictionary bookkeeping whose ORDER is part of the referen
 There is no CPU path for the pixel work: without the library / a device these methods raise."""
 import bisect
 import ctypes
+import functools
+import gc
 import os
 
 import numpy as np
@@ -27,6 +29,22 @@ class UniqueView(ctypes.Structure):
 
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def gc_paused(fn):
+    """These methods build hundreds of thousands of long-lived lists / tuples / objects (the reference's result shapes) and no reference
+    cycles; with the cyclic collector running, its full passes over the growing heap were 100 of the 262 ms of stage 03 on the 32-frame
+    dense workload (tools/grouping_bench.py --gc-report).  Paused for the duration of the call, restored afterwards."""
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        was = gc.isenabled()
+        gc.disable()
+        try:
+            return fn(*args, **kwargs)
+        finally:
+            if was:
+                gc.enable()
+    return wrapper
 
 
 def _dev(a, dtype):
@@ -148,6 +166,7 @@ class GroupingMixin:
         return view, obj_index
 
     # ---- :166-179 ---------------------------------------------------------------------------------------------
+    @gc_paused
     def rebuilt_binary_images(self, chunk=64):
         out = []
         n_frames = len(self.cc_idx_per_frame)                         # (a live estimator builds its host view -- and the tables -- here)
@@ -196,6 +215,7 @@ class GroupingMixin:
         return [host[t] for t in range(n_frames)]
 
     # ---- :181-228 (list bookkeeping; no arithmetic) ----------------------------------------------------------------
+    @gc_paused
     def split_stable_cc_by_gaps(self, max_gap, stable_min_frames):
         split = 0
         objects, uframes, per_frame = self.unique_cc_objects, self.unique_cc_frames, self.cc_idx_per_frame
@@ -244,6 +264,7 @@ class GroupingMixin:
         p[:, 0], p[:, 1] = ids[p[:, 0]], ids[p[:, 1]]
         return p
 
+    @gc_paused
     def compute_overlapping_stable_cc(self, stable_idxs, temporal_window):
         n = len(self.unique_cc_objects)
         all_ov, time_ov, total = [[] for _ in range(n)], [[] for _ in range(n)], 0
@@ -270,6 +291,7 @@ class GroupingMixin:
         return time_ov, total, all_ov
 
     # ---- :308-413 (sequential merge; the numbering of the groups is part of the result) ---------------------------------
+    @gc_paused
     def compute_groups(self, stable_idxs, overlapping_cc, min_recall, t_fmeasure, t_time_IOU):
         groups, owner = [], {}
         for u1 in stable_idxs:
@@ -293,6 +315,7 @@ class GroupingMixin:
         return final, {m: g for g, grp in enumerate(final) for m in grp}
 
     # ---- :415-444 ---------------------------------------------------------------------------------------------
+    @gc_paused
     def compute_groups_temporal_information(self, cc_groups):
         n_frames = len(self.cc_idx_per_frame)
         uframes = self.unique_cc_frames                                # (the property guards the lazy host view: read it once)
@@ -321,6 +344,7 @@ class GroupingMixin:
         return ages, per_frame
 
     # ---- :446-500 ---------------------------------------------------------------------------------------------
+    @gc_paused
     def compute_conflicting_groups(self, stable_idxs, all_overlapping_cc, n_groups, group_idx_per_cc):
         """Same dictionary as the reference's loop (:446-500); the per-pair arithmetic (box areas, intersection, unmatched pixels) runs
         on arrays, only the dictionary is filled pair by pair, in the reference's order."""
@@ -370,6 +394,7 @@ class GroupingMixin:
         return t
 
     # ---- :575-636 ---------------------------------------------------------------------------------------------
+    @gc_paused
     def compute_group_images(self, cc_groups, group_ages, segment_threshold):
         lib = _lib.lib()
         view, obj_index = self._unique_view()
@@ -432,6 +457,7 @@ class GroupingMixin:
         return images, bounds
 
     # ---- :638-681 ---------------------------------------------------------------------------------------------
+    @gc_paused
     def frames_from_groups(self, cc_groups, group_boundaries, groups_per_frame, group_ages, group_images, save_prefix=None,
                            stable_min_frames=3, show_unstable=True, chunk=64):
         """-> list of PNG-encoded clean binary frames (channel 0 of the reference's canvas).  The stable groups are painted on

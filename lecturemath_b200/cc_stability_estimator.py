@@ -17,7 +17,7 @@ import torch
 
 from . import _lib
 from .cc_engine import CCEngine, Estimator
-from .cc_grouping import GroupingMixin
+from .cc_grouping import GroupingMixin, gc_paused
 from .connected_component import ConnectedComponent
 from .packed_mask import PackedMask
 
@@ -305,11 +305,15 @@ class CCStabilityEstimator(GroupingMixin):
         self._n_unique_dev = st["n_unique"]
 
     def _materialise(self):
-        """Host view of everything the device has processed so far.  Vectorised over all outstanding frames: one ConnectedComponent
-        per NEW unique (its first-seen instance), the (frame, label) lists per unique, the per-frame tables stage 03 paints from;
-        the per-frame instance lists stay raw (see _LazyFrames)."""
+        """Host view of everything the device has processed so far (cheap guard in front of every attribute read)."""
         if getattr(self, "_engines", None) is None or (not self._raw and not self._staged and self._inflight == [None, None]):
             return
+        self._materialise_now()
+
+    @gc_paused
+    def _materialise_now(self):
+        """Vectorised over all outstanding frames: one ConnectedComponent per NEW unique (its first-seen instance), the (frame, label)
+        lists per unique, the per-frame tables stage 03 paints from; the per-frame instance lists stay raw (see _LazyFrames)."""
         self.flush()
         raw, self._raw = self._raw, []
         if not raw:

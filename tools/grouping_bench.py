@@ -37,6 +37,7 @@ def stage03(est, timings):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--frames", type=int, default=48)
+    ap.add_argument("--gc-report", action="store_true", help="also report the time spent inside Python's cyclic garbage collector")
     ap.add_argument("--no-oracle", action="store_true", help="(kept for old command lines; the CPU-oracle timing lives in oracle/time_grouping_oracle.py)")
     args = ap.parse_args()
     import torch
@@ -53,7 +54,21 @@ def main():
     est.add_frames(masks)
     torch.cuda.synchronize()
     est.device_ms = {}
+    gc_ms = [0.0, 0]
+    if args.gc_report:
+        import gc
+        t_gc = [0.0]
+
+        def on_gc(phase, info):
+            if phase == "start":
+                t_gc[0] = time.perf_counter()
+            else:
+                gc_ms[0] += 1000.0 * (time.perf_counter() - t_gc[0]); gc_ms[1] += 1
+        gc.callbacks.append(on_gc)
     info = stage03(est, t_gpu)
+    if args.gc_report:
+        gc.callbacks.remove(on_gc)
+        info["gc_ms"], info["gc_runs"] = round(gc_ms[0], 1), gc_ms[1]
     line = {"workload": "stage 03 on %d dense 1080p glyph-mask frames" % args.frames, **info, "gpu_ms": t_gpu,
             "gpu_total_ms": round(sum(t_gpu.values()), 1),
             "device_kernel_ms": {k: round(v, 3) for k, v in est.device_ms.items()}}
