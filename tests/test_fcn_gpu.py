@@ -98,19 +98,23 @@ def test_binarize_and_worker_api_vs_oracle(golden):
     assert np.abs(_sig(lg[0, 0].cpu().numpy()) - _sig(z["tiny_logit"])).max() < PROB_TOL
 
 
-@pytest.mark.parametrize("hw", [(720, 1280), (1080, 1920)])
+@pytest.mark.parametrize("hw", [(720, 1280), (1080, 1920), (1080, 1920, "poolx")])
 def test_full_size_random_init_vs_fp32_oracle_on_gpu(hw):
     """BASELINE configs 1/2 shapes with the reference's seed-0 random init: compare with the fp32 oracle run on the
-    same GPU (torch/cuDNN fp32, TF32 off).  Also a size-independent property: batch invariance."""
+    same GPU (torch/cuDNN fp32, TF32 off).  Also a size-independent property: batch invariance.  "poolx": the encoder convs 1 / 2 in
+    the Sx-packed form whose max-pool is fused through unit pairs (what shapes without a tuned table get)."""
     from lecturemath_b200 import synth
     from lecturemath_b200.configuration import Configuration
     from lecturemath_b200.fcn_lecturenet import FCN_LectureNet
     from tests.conftest import GOLDEN
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
-    h, w = hw
+    h, w = hw[:2]
     torch.manual_seed(0)
     net = FCN_LectureNet.CreateFromConfig(Configuration.from_file(GOLDEN + "/fcn_full.conf"), 3, False).eval().cuda()
+    if len(hw) > 2:
+        from tests.test_fcn_host_logic import poolx_overrides
+        net.plan_overrides = poolx_overrides(net)
     frames = np.stack(list(synth.whiteboard_frames(2, h, w, seed=1234)))
     plan = net.binarize_frames(frames)
     torch.cuda.synchronize()
