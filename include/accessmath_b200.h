@@ -172,7 +172,8 @@ typedef struct am_conv_desc {
     long long out_sn, out_sy;      /* element strides: frame, row */
     int out_sx, out_padx, out_coff;/* pixel stride (channels), left pad (pixels), channel offset */
     int Cout, Sy, Sx;              /* GEMM column n = ((sy*Sx)+sx)*Cout + co  ->  pixel (Sy*y+sy, Sx*r+sx), channel co */
-    int act;                       /* 0 = none, 1 = exact-erf GELU */
+    int act;                       /* 0 = none, 1 = nn.GELU() (erf form) evaluated as 0.5 x (1 + tanh z(x)), z = a three-term minimax fit of
+                                      atanh(erf(x / sqrt 2)), one tanh.approx per element: |error| <= 2.6e-5 + 2.5e-4 |x| (csrc/fcn_conv.cu) */
     int flags;                     /* AM_CONV_* tuning overrides (0 = let the library choose) */
     int in_ystep;                  /* input rows per GEMM row step: 1, or 2 = "2-D packing": a GEMM row produces Sy = 2 output rows,
                                       KH is then the Toeplitz-extended tap count KH_conv + 1 and RT must be 8 (0 means 1) */
