@@ -1425,8 +1425,8 @@ static int conv_launch(const am_conv_plan* plan, void* stream) {
                           : plan->p.pool2 ? kernels[14 + (plan->p.residentB ? 1 : 0)]
                           : plan->p.poolx ? kernels[16 + (plan->p.residentB ? 1 : 0)]
                                           : kernels[6 * fused + (plan->p.MT == 4 ? 4 : plan->p.MT == 2 ? 2 : 0) + (plan->p.residentB ? 1 : 0)];
-    // programmatic dependent launch, see pdl_wait().  Opt-in (AM_B200_PDL=1): measured on a B200 it does not pay -- 9.60 ms per step with it
-    // against 9.43-9.53 without (profile r02_z): the persistent CTAs own every SM until they exit, so only the ~3 us prologue can overlap.
+    // programmatic dependent launch, see pdl_wait().  Opt-in (AM_B200_PDL=1): measured on a B200 it changes nothing (end to end 813 vs 812
+    // frames/s, ABBA runs, tools/ab_pdl.sh): the persistent CTAs own every SM until they exit, so only the ~3 us prologue can overlap.
     static const int use_pdl = [] { const char* e = getenv("AM_B200_PDL"); return (e && e[0] == '1') ? 1 : 0; }();
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(plan->grid); cfg.blockDim = dim3(CONV_THREADS); cfg.dynamicSmemBytes = plan->smem; cfg.stream = (cudaStream_t)stream;
