@@ -133,3 +133,37 @@ def test_full_size_random_init_vs_fp32_oracle_on_gpu(hw):
     single = net.binarize_frames(frames[1:2])
     torch.cuda.synchronize()
     assert torch.equal(single.bits[0], bits[1])                          # batch invariance (bit-exact)
+
+
+@pytest.mark.gpu
+def test_programmatic_dependent_launch_gives_identical_bits():
+    """AM_B200_PDL=1 (opt-in): the conv launches carry programmaticStreamSerialization and wait for their predecessor with
+    griddepcontrol.wait -- same kernels, same arithmetic, so the masks and logits must be bit-identical to the default launches.
+    The switch is read once per process: both arms run in their own interpreter."""
+    import os
+    import subprocess
+    import sys
+    from tests.conftest import GOLDEN
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = (
+        "import sys, hashlib, numpy as np, torch\n"
+        "sys.path.insert(0, %r)\n"
+        "from lecturemath_b200 import synth\n"
+        "from lecturemath_b200.configuration import Configuration\n"
+        "from lecturemath_b200.fcn_lecturenet import FCN_LectureNet\n"
+        "torch.manual_seed(0)\n"
+        "net = FCN_LectureNet.CreateFromConfig(Configuration.from_file(%r), 3, False).eval().cuda()\n"
+        "frames = np.stack(list(synth.whiteboard_frames(2, 720, 1280, seed=99)))\n"
+        "h = hashlib.sha256()\n"
+        "for _ in range(3):\n"
+        "    plan = net.binarize_frames(frames)\n"
+        "    torch.cuda.synchronize()\n"
+        "    h.update(plan.bits.cpu().numpy().tobytes()); h.update(plan.logits.cpu().numpy().tobytes())\n"
+        "print('HASH', h.hexdigest())\n") % (repo, os.path.join(GOLDEN, "fcn_full.conf"))
+    hashes = []
+    for flag in ("0", "1"):
+        env = dict(os.environ, AM_B200_PDL=flag)
+        out = subprocess.run([sys.executable, "-c", script], env=env, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        hashes.append([ln for ln in out.stdout.splitlines() if ln.startswith("HASH")][-1])
+    assert hashes[0] == hashes[1]
