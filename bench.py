@@ -441,13 +441,20 @@ def run_ours(args):
     run_video(K, False, timing)
     e1.record()
     barrier()
-    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    ms_own = e0.elapsed_time(e1)
+    ms = torch.tensor([ms_own], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
     launches = sx.launches
     state = sx.finish()
     conv_ms = sum(a.elapsed_time(b) for _, a, b in timing)
+    per_rank = None
+    if world > 1:           # diagnostics: every rank's own timed region and conv time (the step time above is the maximum over the ranks)
+        mine = torch.tensor([ms_own / max(K, 1), conv_ms / max(K, 1)], dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {"ms_per_step": [round(float(t[0].item()), 3) for t in allr], "conv_ms_per_step": [round(float(t[1].item()), 3) for t in allr]}
     per_op = {}
     for i, a, b in timing:
         per_op.setdefault(i, []).append(a.elapsed_time(b))
@@ -567,6 +574,8 @@ def run_ours(args):
             line["gpu_reference"] = gref
         if ring_parity is not None:
             line["ring_parity"] = ring_parity
+        if per_rank is not None:
+            line["per_rank"] = per_rank
         if numa_cores is not None:
             line["config"]["host_binding"] = "each rank pinned to its GPU's NVML CPU affinity (%d cores on rank 0) before allocating pinned memory" % len(numa_cores)
         if args.masks != "fcn":
