@@ -84,3 +84,22 @@ def test_full_config_flops_match_survey():
     for (h, w, gf) in ((720, 1280, 414.5), (1080, 1920, 931.8)):
         plan = FCNPlan.__new__(FCNPlan)                                    # flop count only: no buffers
         assert abs(FCNPlan.count_flops(net.params, h, w) / 1e9 - gf) < 0.5
+
+
+@pytest.mark.parametrize("hw", [(1080, 1920), (720, 1280)])
+def test_tuned_table_entries_are_adopted_for_their_shapes(hw):
+    """Every (S, Sy, NT, MT) of lecturemath_b200/tuned_plans.json for the reference architecture at batch 8 is among the feasible
+    candidates of its layer (a stale table would silently fall back to the cycle model), and the plan built from it pools all five
+    encoder levels in the conv epilogues (no separate k_maxpool2 pass in the headline shapes)."""
+    from lecturemath_b200 import fcn_lecturenet as F
+    h, w = hw
+    net = FCN_LectureNet.CreateFromConfig(Configuration.from_file(GOLDEN + "/fcn_full.conf"), 3, False)
+    plan = FCNPlan(net.params, 8, h, w, torch.device("cpu"))
+    table = F.tuned_table().get(plan.arch, {}).get("B8_%dx%d" % (h, w))
+    assert table, "no tuned entry for B8 %dx%d under architecture %s" % (h, w, plan.arch)
+    for name, cfg in table.items():
+        assert name in plan.specs, name
+        assert tuple(plan.specs[name]["cfg"]) == tuple(cfg), "%s: tuned %s not adopted (plan uses %s)" % (name, cfg, plan.specs[name]["cfg"])
+    kinds = [k for k, _ in plan.ops]
+    assert kinds.count("pool") == 0 and kinds.count("conv") == 20                  # 15 conv launches (the two heads share one) + 5 transposed convs
+    assert sum(1 for k, d in plan.ops if k == "conv" and d.pool_out) == 5
