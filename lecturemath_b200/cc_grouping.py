@@ -12,13 +12,12 @@ import bisect
 import ctypes
 import functools
 import gc
-import os
 
 import numpy as np
 import torch
 
 from . import _lib
-from .connected_component import pack_crop, unpack_crop
+from .connected_component import pack_crop
 
 
 class UniqueView(ctypes.Structure):
@@ -462,7 +461,6 @@ class GroupingMixin:
                            stable_min_frames=3, show_unstable=True, chunk=64):
         """-> list of PNG-encoded clean binary frames (channel 0 of the reference's canvas).  The stable groups are painted on
         the device from the images compute_group_images left there; `save_prefix` debugging dumps are not supported."""
-        import cv2
         if save_prefix is not None:
             raise NotImplementedError("frames_from_groups(save_prefix=...) writes debugging PNGs; only the returned frames are produced here")
         lib = _lib.lib()

@@ -863,7 +863,6 @@ class FCN_LectureNet:
 
     def binarize(self, PIL_image, return_others=False, force_binary=False, binary_treshold=128, apply_sigmoid=True):
         import cv2
-        import PIL.Image
         o_width, o_height = PIL_image.size
         width, height = o_width, o_height
         rgb = np.asarray(PIL_image.convert("RGB"), dtype=np.uint8)

@@ -8,7 +8,6 @@ csrc/png.cu writes a 1-bit grayscale PNG -- compressed (fixed-Huffman deflate wi
 cv2's files on whiteboard masks) or with stored blocks -- checksums included, and only the finished files cross PCIe."""
 import ctypes
 
-import numpy as np
 import torch
 
 from . import _lib
